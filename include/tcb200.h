@@ -1,0 +1,130 @@
+/*
+ * tcb200.h — C ABI of the B200-native engine for TensorCircuit-NG's two
+ * contraction hot paths (statevector evolution and pairwise tensor-network
+ * contraction).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference (/root/reference, pure Python) has no FFI; the seams this
+ * library replaces are the *library call sites* of SURVEY.md §2.3:
+ *
+ *   K1  tn.contract_between -> backend.tensordot      tensorcircuit/cons.py:948 (also :396,:413,:450)
+ *   K2  final_node.reorder_edges (full-state permute)  tensorcircuit/cons.py:960
+ *   K3  tn.copy(nodes, conjugate=True) (bra copy)      tensorcircuit/basecircuit.py:161,:384
+ *   K4  contractor([psi, psi*, P...]) expectation      tensorcircuit/circuit.py:899-902
+ *   K6  tree.contract_core(sliced_arrays)              tensorcircuit/experimental.py:1008
+ *   K7  tree.slice_arrays(input_arrays, slice_idx)     tensorcircuit/experimental.py:1007
+ *
+ * Conventions (verified against the reference's golden values):
+ *   - a state is 2^n complex64 (interleaved re,im float32), qubit 0 = MOST significant bit
+ *     of the flat index (tensorcircuit/circuit.py:711-719).  This ABI speaks in *bit
+ *     positions* of the flat index: qubit q of an n-qubit register is bit (n-1-q).
+ *   - a k-qubit gate matrix is row-major 2^k x 2^k complex64, row = (out_0..out_{k-1})_2,
+ *     col = (in_0..in_{k-1})_2, first listed qubit most significant
+ *     (tensorcircuit/gates.py:497-516, tensorcircuit/basecircuit.py:288-290).
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - every entry point returns 0 on success, nonzero on error; tcb_last_error()
+ *     returns a thread-local message.  Nothing falls back to the CPU.
+ */
+#ifndef TCB200_H
+#define TCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCB_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------ */
+int tcb_abi_version(void);
+const char* tcb_last_error(void);
+/* number of SMs / total global memory of the current device */
+int tcb_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+
+/* ---- statevector: unfused per-gate kernels (R7/R9 literal order) ---------
+ * state      : [batch][2^nbits] complex64
+ * bitpos[k]  : flat-index bit position of gate qubit 0..k-1 (gate qubit 0 = matrix MSB)
+ * mat        : [batch or 1][2^k * 2^k] complex64 row-major; mat_batch_stride in complex elems (0 = shared)
+ * index_base : OR-ed into the flat index when a control/diagonal qubit lives above the
+ *              local shard (sharded statevector); 0 on one GPU.              */
+int tcb_sv_init_zero(void* state, int nbits, int64_t batch, void* stream);
+int tcb_sv_apply_dense(void* state, int nbits, int64_t batch, const int* bitpos_host, int k,
+                       const void* mat, int64_t mat_batch_stride, void* stream);
+/* diagonal gate given as 2^k complex64 entries spaced `diag_stride` apart (2^k+1 for the
+ * diagonal of a dense row-major matrix, 1 for a packed diagonal). bitpos may exceed nbits-1:
+ * such bits are read from index_base (global qubits of a sharded state).                  */
+int tcb_sv_apply_diag(void* state, int nbits, int64_t batch, const int* bitpos_host, int k,
+                      const void* diag, int64_t diag_stride, int64_t mat_batch_stride,
+                      uint64_t index_base, void* stream);
+
+/* ---- statevector: fused tile pass (the hot kernel) ------------------------
+ * One launch = one HBM pass over the state applying a whole *pass program*
+ * (many gates).  `program` is an int32 word stream built by the host planner
+ * (tensorcircuit_ng_b200/passplan.py; layout in csrc/pass_core.cuh).
+ * `gatebuf` holds every gate matrix of the circuit, concatenated, complex64;
+ * program ops address it by element offset.  Replaces the tensordot+permute
+ * loop of tensorcircuit/cons.py:937-953 for circuit-shaped networks.          */
+int tcb_sv_run_pass(void* state, int nbits, int64_t batch, const int32_t* program,
+                    int32_t program_words, int tile_bits, int low_bits, const void* gatebuf,
+                    int64_t gate_batch_stride, uint64_t index_base, void* stream);
+/* same kernel reading `src` and writing `dst` (out-of-place; src may equal dst).
+ * tile_bits / low_bits repeat the program header's T / L (the host needs them to size the
+ * launch without reading device memory).                                                  */
+int tcb_sv_run_pass_oop(const void* src, void* dst, int nbits, int64_t batch,
+                        const int32_t* program, int32_t program_words, int tile_bits,
+                        int low_bits, const void* gatebuf, int64_t gate_batch_stride,
+                        uint64_t index_base, void* stream);
+
+/* ---- statevector: reductions (K3/K4 without materialising the bra) --------
+ * out[b][t] (float64) += sum_x sign_t(x) |psi_b[x]|^2, sign = (-1)^popc((x|index_base) & zmask[t]).
+ * One read of the state serves all nterms Z-strings.                          */
+int tcb_sv_expect_z(const void* state, int nbits, int64_t batch, const uint64_t* zmasks,
+                    int nterms, uint64_t index_base, double* out, void* stream);
+/* general Pauli string P = i^{ny} X^{xmask} Z^{zmask}:  out[b] (2 x float64: re,im) +=
+ * sum_x conj(psi[x ^ xmask]) * phase(x) * psi[x]   (xmask must be local: < 2^nbits)      */
+int tcb_sv_expect_pauli(const void* state, int nbits, int64_t batch, uint64_t xmask,
+                        uint64_t zmask, int ny, uint64_t index_base, double* out, void* stream);
+/* out[b] (2 x float64) += <a_b | b_b>  */
+int tcb_sv_inner(const void* a, const void* b, int nbits, int64_t batch, double* out, void* stream);
+
+/* ---- statevector: adjoint-mode vjp helpers (R17) --------------------------
+ * grad[b][r][c] (complex128 as 2 x float64, +=) = sum_rest lam[rest, r] * conj(psi_in[rest, c])
+ * over every amplitude group the k-qubit gate touches (k = 1, 2); grad_batch_stride in complex
+ * elements.  With lam = torch's gradient of a real loss w.r.t. psi_out this is torch's gradient
+ * w.r.t. the gate matrix (torch complex convention, tests/test_backends.py:992-996).        */
+int tcb_sv_gate_grad(const void* lam, const void* psi_in, int nbits, int64_t batch,
+                     const int* bitpos_host, int k, double* grad, int64_t grad_batch_stride,
+                     void* stream);
+
+/* ---- sharded statevector: local half of a global<->local qubit swap -------
+ * Packs the amplitudes whose local bit `local_bit` == `want` into a contiguous
+ * send buffer (and the inverse), so the exchange itself is one NCCL send/recv.           */
+int tcb_sv_pack_half(const void* state, void* buf, int nbits, int local_bit, int want, void* stream);
+int tcb_sv_unpack_half(void* state, const void* buf, int nbits, int local_bit, int want, void* stream);
+
+/* ---- tensor network: pairwise contraction (K1/K6/K7) ----------------------
+ * All tensor modes have extent 2.  Every mode of A, B and C is described by the flat-index
+ * bit position it occupies in each operand (-1 = absent).  Mode classes:
+ *   batch (in A, B and C), M (A and C), N (B and C), K (A and B, summed).
+ * A mode of A or B may also be *sliced* (K7): it is absent from the arrays as stored
+ * *after* slicing — slicing is folded in by passing a_offset / b_offset (element offsets)
+ * computed by the host from the slice id, so no sliced copies are ever made.           */
+typedef struct tcb_contract_desc {
+  int32_t n_batch, n_m, n_n, n_k;
+  /* bit positions, most-significant-first is NOT required; any order is fine */
+  int8_t batch_a[32], batch_b[32], batch_c[32];
+  int8_t m_a[32], m_c[32];
+  int8_t n_b[32], n_c[32];
+  int8_t k_a[32], k_b[32];
+  int32_t conj_a, conj_b; /* conjugate operand on load (K3 folded in) */
+} tcb_contract_desc;
+
+int tcb_tn_contract(const void* a, int64_t a_offset, const void* b, int64_t b_offset, void* c,
+                    const tcb_contract_desc* desc_host, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCB200_H */

@@ -1,0 +1,456 @@
+"""
+Contractor plugin surface — the drop-in boundary.
+
+Mirrors /root/reference/tensorcircuit/cons.py: the module-global `contractor`
+(rebound in every loaded module of the package, cons.py:84-87), `set_contractor`
+(cons.py:1123-1261), `runtime_contractor` / `set_function_contractor` scoping
+(cons.py:1269-1314), the "before" capture hack (cons.py:976-1004), and the contractor
+callable contract
+
+    cf(nodes, output_edge_order=None, ignore_edge_order=False, **kws) -> tn.Node
+
+with the reference's two ValueErrors (cons.py:886-896) and its edge re-pointing
+(cons.py:742-761).  The default contractor here is `b200_contractor`:
+
+  circuit-shaped network  -> fused statevector passes           (svengine / passplan)
+  [psi, psi*, ops] network -> reduction kernels, bra never built (K3/K4)
+  anything else            -> planned pairwise GPU contractions  (tnengine)
+
+No branch computes on the CPU.
+"""
+
+from __future__ import annotations
+
+import sys
+from collections import deque
+from contextlib import contextmanager
+from functools import partial, wraps
+from typing import Any, Callable, Dict, Iterator, List, Optional, Sequence, Set, Tuple
+
+import torch
+
+from . import _lib, planner, svengine, tn, tnengine
+
+package_name = "tensorcircuit_ng_b200"
+thismodule = sys.modules[__name__]
+dtypestr = "complex64"
+rdtypestr = "float32"
+idtypestr = "int32"
+
+contractor: Callable[..., Any]
+
+
+def _set_global_contractor(contractor_fn: Callable[..., Any]) -> None:  # cons.py:84-87
+    for module in list(sys.modules):
+        if module.startswith(package_name):
+            setattr(sys.modules[module], "contractor", contractor_fn)
+
+
+# cons.py:56-69 -----------------------------------------------------------------------
+def _get_edge_stable_key(edge: Any) -> Tuple[int, int, int, int]:
+    n1, n2 = edge.node1, edge.node2
+    id1 = getattr(n1, "_stable_id_", -1)
+    id2 = getattr(n2, "_stable_id_", -1) if n2 is not None else -2
+    if id1 > id2 or (id1 == id2 and edge.axis1 > edge.axis2):
+        id1, id2, ax1, ax2 = id2, id1, edge.axis2, edge.axis1
+    else:
+        ax1, ax2 = edge.axis1, edge.axis2
+    return (id1, ax1, id2, ax2)
+
+
+def sorted_edges(edges: Any) -> List[Any]:
+    return sorted(edges, key=_get_edge_stable_key)
+
+
+_einsum_symbols_base = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+
+
+def get_symbol(i: int) -> str:  # cons.py:472-489
+    if i < 52:
+        return _einsum_symbols_base[i]
+    i += 140
+    if i >= 55296:
+        i += 2048
+    return chr(i)
+
+
+def _all_edges(nodes: Sequence[Any]) -> Set[Any]:
+    out: Set[Any] = set()
+    for n in nodes:
+        out.update(n.edges)
+    return out
+
+
+def _subgraph_dangling(nodes: Sequence[Any]) -> Set[Any]:
+    ids = {id(n) for n in nodes}
+    out: Set[Any] = set()
+    for n in nodes:
+        for e in n.edges:
+            if e.is_dangling() or id(e.node1) not in ids or id(e.node2) not in ids:
+                out.add(e)
+    return out
+
+
+def _is_copynode(n: Any) -> bool:
+    return type(n).__name__ == "CopyNode"
+
+
+class _UnionFind:
+    def __init__(self) -> None:
+        self.parent: Dict[int, int] = {}
+        self.obj: Dict[int, Any] = {}
+
+    def find(self, x: Any) -> Any:
+        k = id(x)
+        if k not in self.parent:
+            self.parent[k] = k
+            self.obj[k] = x
+        r = k
+        while self.parent[r] != r:
+            r = self.parent[r]
+        while self.parent[k] != r:
+            self.parent[k], k = r, self.parent[k]
+        return self.obj[r]
+
+    def union(self, a: Any, b: Any) -> None:
+        ra, rb = id(self.find(a)), id(self.find(b))
+        if ra != rb:
+            self.parent[rb] = ra
+
+
+def get_tn_info(nodes: Sequence[Any]):
+    """(input_sets, output_set, size_dict), sorted nodes — cons.py:773-804 for plain networks and
+    cons.py:492-547 (`_extract_topology`) when CopyNode hyperedges are present: same node order
+    (`_stable_id_`), same edge order (`sorted_edges`), same symbol assignment."""
+    nodes_new = sorted(nodes, key=lambda node: getattr(node, "_stable_id_", -1))
+    has_hyper = any(_is_copynode(n) for n in nodes_new)
+    if not has_hyper:
+        all_edges_sorted = sorted_edges(_all_edges(nodes_new))
+        mapping: Dict[int, str] = {}
+        for edge in all_edges_sorted:
+            if id(edge) not in mapping:
+                mapping[id(edge)] = get_symbol(len(mapping))
+        input_sets = [[mapping[id(e)] for e in node.edges] for node in nodes_new]
+        output_set = [mapping[id(e)] for e in sorted_edges(_subgraph_dangling(nodes_new))]
+        size_dict = {mapping[id(e)]: e.dimension for e in all_edges_sorted}
+        return (input_sets, output_set, size_dict), nodes_new
+    regular = [n for n in nodes_new if not _is_copynode(n)]
+    uf = _UnionFind()
+    for e in _all_edges(nodes_new):
+        uf.find(e)
+    for cn in nodes_new:
+        if _is_copynode(cn) and cn.edges:
+            for e in cn.edges[1:]:
+                uf.union(cn.edges[0], e)
+    mapping = {}
+    roots: Dict[int, Any] = {}
+    input_sets = []
+    for node in regular:
+        syms = []
+        for e in node.edges:
+            r = uf.find(e)
+            if id(r) not in mapping:
+                mapping[id(r)] = get_symbol(len(mapping))
+                roots[id(r)] = r
+            syms.append(mapping[id(r)])
+        input_sets.append(syms)
+    output_set = []
+    for e in sorted_edges(_subgraph_dangling(nodes_new)):
+        r = uf.find(e)
+        if id(r) not in mapping:
+            mapping[id(r)] = get_symbol(len(mapping))
+            roots[id(r)] = r
+        output_set.append(mapping[id(r)])
+    size_dict = {sym: roots[k].dimension for k, sym in mapping.items()}
+    return (input_sets, output_set, size_dict), regular
+
+
+def _validate_edge_order(nodes: Sequence[Any], output_edge_order: Optional[Sequence[Any]],
+                         ignore_edge_order: bool) -> Optional[List[Any]]:  # fmt: skip
+    """The reference's checks and messages, cons.py:882-896."""
+    if ignore_edge_order:
+        return None if output_edge_order is None else list(output_edge_order)
+    dangling = _subgraph_dangling(nodes)
+    if output_edge_order is None:
+        output_edge_order = list(dangling)
+        if len(output_edge_order) > 1:
+            raise ValueError(
+                "The final node after contraction has more than "
+                "one remaining edge. In this case `output_edge_order` "
+                "has to be provided."
+            )
+    if set(output_edge_order) != dangling:
+        raise ValueError(
+            "output edges are not equal to the remaining " "non-contracted edges of the final node."
+        )
+    return list(output_edge_order)
+
+
+def _finalize(nodes: Sequence[Any], tensor: torch.Tensor, tensor_edges: Sequence[Any],
+              output_edge_order: Optional[Sequence[Any]], ignore_edge_order: bool) -> Any:  # fmt: skip
+    """Wrap the result: the returned node owns the ORIGINAL dangling Edge objects, re-pointed
+    to it (cons.py:742-761; pinned by the reference's tests/test_hyperedge.py:498-527)."""
+    final_node = tn.Node(tensor)
+    ids = {id(n) for n in nodes}
+    for i, edge in enumerate(tensor_edges):
+        if id(edge.node1) in ids:
+            edge.node1, edge.axis1 = final_node, i
+        else:
+            edge.node2, edge.axis2 = final_node, i
+    final_node.edges = list(tensor_edges)
+    for n in nodes:
+        n.edges = []  # inputs are consumed, as after tn.contract_between
+    if not ignore_edge_order and output_edge_order is not None and list(output_edge_order) != list(tensor_edges):
+        final_node.reorder_edges(list(output_edge_order))
+    return final_node
+
+
+# ---- [psi, psi*, ops...] networks (tensorcircuit/basecircuit.py:393-447) ---------------------
+def _same_storage_conj(a: torch.Tensor, b: torch.Tensor) -> bool:
+    if a.shape != b.shape or a.is_conj() == b.is_conj():
+        return False
+    pa, pb = (a.conj() if a.is_conj() else a), (b.conj() if b.is_conj() else b)
+    return pa.data_ptr() == pb.data_ptr() and pa.stride() == pb.stride() and pa.is_contiguous()
+
+
+def _recognize_expectation(nodes: Sequence[Any]):
+    """Returns (ket tensor, n, [(op node, qubit axes)]) for <psi|ops|psi>, else None."""
+    if len(nodes) < 2 or _subgraph_dangling(nodes):
+        return None
+    big = [x for x in nodes if not _is_copynode(x)]
+    if len(big) != len(nodes):
+        return None
+    ranks = sorted(((x.get_rank(), i) for i, x in enumerate(nodes)), reverse=True)
+    a, b = nodes[ranks[0][1]], nodes[ranks[1][1]]
+    n = a.get_rank()
+    if n < 1 or b.get_rank() != n or not _same_storage_conj(a.tensor, b.tensor):
+        return None
+    ket, bra = (a, b) if b.tensor.is_conj() else (b, a)
+    ops = [x for x in nodes if x is not ket and x is not bra]
+    covered: Set[int] = set()
+    found = []
+    for op in ops:
+        r = op.get_rank()
+        if r % 2 or r == 0:
+            return None
+        k = r // 2
+        axes = []
+        for j in range(k):
+            eb, ek = op.edges[j], op.edges[j + k]
+            nb, ab = svengine._other_end(eb, op, j)
+            nk, ak = svengine._other_end(ek, op, j + k)
+            if nb is not bra or nk is not ket or ab != ak or ab in covered:
+                return None
+            covered.add(ab)
+            axes.append(ab)
+        found.append((op, tuple(axes)))
+    for j in range(n):
+        if j in covered:
+            continue
+        e = ket.edges[j]
+        o, ax = svengine._other_end(e, ket, j)
+        if o is not bra or ax != j:
+            return None
+    return ket.tensor, n, found
+
+
+def _pauli_of(op: Any) -> Optional[str]:
+    if getattr(op, "_b200_kind", None) is None or op.get_rank() != 2:
+        return None
+    name = str(getattr(op, "name", ""))
+    return name if name in ("x", "y", "z", "i") else None
+
+
+def _expectation_value(ket: torch.Tensor, n: int, ops: Sequence[Tuple[Any, Tuple[int, ...]]]) -> torch.Tensor:
+    from . import expect
+
+    psi = ket.reshape(-1)
+    paulis = [_pauli_of(op) for op, _ in ops]
+    if all(p is not None for p in paulis):
+        xs = [ax[0] for (op, ax), p in zip(ops, paulis) if p == "x"]
+        ys = [ax[0] for (op, ax), p in zip(ops, paulis) if p == "y"]
+        zs = [ax[0] for (op, ax), p in zip(ops, paulis) if p == "z"]
+        return expect.pauli_expectation(psi, n, xs, ys, zs)
+    return expect.operator_expectation(psi, n, [(op.tensor, ax) for op, ax in ops])
+
+
+# ---- the default contractor -------------------------------------------------------------------
+def b200_contractor(nodes: List[Any], output_edge_order: Optional[List[Any]] = None,
+                    ignore_edge_order: bool = False, optimizer: Any = None, **kws: Any) -> Any:  # fmt: skip
+    nodes = list(nodes)
+    order = _validate_edge_order(nodes, output_edge_order, ignore_edge_order)
+    if kws.get("debug_level", 0) == 2:  # cons.py:928-933: shape only
+        shape = [e.dimension for e in order] if order else []
+        return tn.Node(torch.zeros(shape, dtype=torch.complex64))
+    # 1. statevector route
+    if order and not kws.get("force_tn", False):
+        try:
+            state = svengine.run_circuit_network(nodes, order)
+            return _finalize(nodes, state, order, order, ignore_edge_order)
+        except svengine.NotCircuitShaped:
+            pass
+    # 2. expectation sandwich on a cached state
+    if not kws.get("force_tn", False):
+        rec = _recognize_expectation(nodes)
+        if rec is not None:
+            val = _expectation_value(*rec)
+            return _finalize(nodes, val, [], order, ignore_edge_order)
+    # 3. general tensor network
+    return _tn_route(nodes, order, ignore_edge_order, optimizer, **kws)
+
+
+def _tn_route(nodes: List[Any], order: Optional[List[Any]], ignore_edge_order: bool, optimizer: Any,
+              **kws: Any) -> Any:  # fmt: skip
+    (input_sets, output_set, size_dict), sorted_nodes = get_tn_info(nodes)
+    tensors = [n.tensor for n in sorted_nodes]
+    device = svengine.pick_device(tensors)
+    tensors = [t if t.device == device else t.to(device) for t in tensors]
+    dangling = sorted_edges(_subgraph_dangling(nodes))
+    if len(tensors) == 1:
+        path: List[Tuple[int, ...]] = []
+    elif isinstance(optimizer, list):
+        path = optimizer
+    elif optimizer is not None:
+        path = optimizer(input_sets, output_set, size_dict)
+    else:
+        path = planner.greedy(input_sets, output_set, size_dict)
+    # the tree writes the caller's edge order directly (no final transpose, K2)
+    if order is not None and not ignore_edge_order and len(set(output_set)) == len(output_set):
+        sym_of = {id(e): s for e, s in zip(dangling, output_set)}
+        want = [sym_of[id(e)] for e in order]
+        result_edges = list(order)
+    else:
+        want = list(output_set)
+        result_edges = list(dangling)
+    out = tnengine.contract_tree(tensors, input_sets, want, path)
+    return _finalize(nodes, out, result_edges, order, ignore_edge_order)
+
+
+def plain_contractor(nodes: List[Any], output_edge_order: Optional[List[Any]] = None,
+                     ignore_edge_order: bool = False) -> Any:  # fmt: skip
+    """cons.py:429-463: literal sequential statevector order, node by node (GPU kernel per pair)."""
+    nodes = list(reversed(list(nodes)))
+    while len(nodes) > 1:
+        new_node = tn.contract_between(nodes[-1], nodes[-2], allow_outer_product=True)
+        nodes = nodes[:-2] + [new_node]
+    final_node = nodes[0]
+    if output_edge_order is not None:
+        final_node.reorder_edges(output_edge_order)
+    return final_node
+
+
+def custom(nodes: List[Any], optimizer: Any, memory_limit: Optional[int] = None,
+           output_edge_order: Optional[List[Any]] = None, ignore_edge_order: bool = False,
+           debug_level: int = 0, **kws: Any) -> Any:  # fmt: skip
+    """cons.py:1007-1050 Level-1 plug: the caller's planner, our executor."""
+    nodes = list(nodes)
+    order = _validate_edge_order(nodes, output_edge_order, ignore_edge_order)
+    if debug_level == 2:
+        shape = [e.dimension for e in order] if order else []
+        return tn.Node(torch.zeros(shape, dtype=torch.complex64))
+    if not isinstance(optimizer, list) and optimizer is not None:
+        optimizer = partial(optimizer, memory_limit=memory_limit)
+    return _tn_route(nodes, order, ignore_edge_order, optimizer)
+
+
+class NodesReturn(Exception):  # cons.py:964-973
+    def __init__(self, value_to_return: Any):
+        self.value = value_to_return
+        super().__init__(f"Intentionally stopping execution to return: {value_to_return}")
+
+
+def _get_sorted_nodes(nodes: List[Any], *args: Any, **kws: Any) -> Any:
+    raise NodesReturn(sorted(nodes, key=lambda node: getattr(node, "_stable_id_", -1)))
+
+
+def set_contractor(method: Optional[str] = None, optimizer: Optional[Any] = None,
+                   memory_limit: Optional[int] = None, opt_conf: Optional[Dict[str, Any]] = None,
+                   set_global: bool = True, contraction_info: bool = False, debug_level: int = 0,
+                   use_primitives: Optional[bool] = None, **kws: Any) -> Callable[..., Any]:  # fmt: skip
+    """Same signature as the reference's `set_contractor` (cons.py:1123-1261).
+
+    method: "b200" (default: statevector passes + GPU tensor-network fallback), "tn" / "greedy"
+    (always the planned tensor-network executor, our greedy planner), "plain", "custom"
+    (caller's `optimizer`: callable `f(inputs, output, size_dict, memory_limit=None) -> path` or a
+    literal path), "before" (node capture).  "cotengra*" / "omeco*" need those packages and raise
+    ImportError like the reference when they are absent (cons.py:678-683)."""
+    if not method:
+        method = "b200"
+    if method.startswith("cotengra") or method.startswith("omeco"):
+        raise ImportError(
+            f"contractor {method!r} needs the optional third-party planner, which is not installed; "
+            "load a plan with experimental.DistributedContractor.from_path or pass "
+            "method='custom', optimizer=<callable>"
+        )
+    if method == "plain":
+        cf: Callable[..., Any] = plain_contractor
+    elif method == "before":
+        cf = _get_sorted_nodes
+    elif method == "b200":
+        cf = partial(b200_contractor, debug_level=debug_level, **kws)
+    elif method in ("tn", "greedy"):
+        cf = partial(b200_contractor, force_tn=True, debug_level=debug_level)
+    elif method == "custom":
+        cf = partial(custom, optimizer=optimizer, memory_limit=memory_limit, debug_level=debug_level)
+    else:
+        raise ValueError(f"Unknown contractor type: {method}")
+    if set_global:
+        _set_global_contractor(cf)
+    return cf
+
+
+get_contractor = partial(set_contractor, set_global=False)
+
+
+def set_function_contractor(*confargs: Any, **confkws: Any) -> Callable[..., Any]:  # cons.py:1269-1294
+    def wrapper(f: Callable[..., Any]) -> Callable[..., Any]:
+        @wraps(f)
+        def newf(*args: Any, **kws: Any) -> Any:
+            old = getattr(thismodule, "contractor")
+            set_contractor(*confargs, **confkws)
+            try:
+                return f(*args, **kws)
+            finally:
+                _set_global_contractor(old)
+
+        return newf
+
+    return wrapper
+
+
+@contextmanager
+def runtime_contractor(*confargs: Any, **confkws: Any) -> Iterator[Any]:  # cons.py:1297-1314
+    old = getattr(thismodule, "contractor")
+    nc = set_contractor(*confargs, **confkws)
+    try:
+        yield nc
+    finally:
+        _set_global_contractor(old)
+
+
+def function_nodes_capture(func: Callable[..., Any]) -> Callable[..., Any]:  # cons.py:981-991
+    @wraps(func)
+    def wrapper(*args: Any, **kwargs: Any) -> Any:
+        with runtime_contractor(method="before"):
+            try:
+                return func(*args, **kwargs)
+            except NodesReturn as e:
+                return e.value
+
+    return wrapper
+
+
+@contextmanager
+def runtime_nodes_capture(key: str = "nodes") -> Iterator[Any]:  # cons.py:994-1004
+    old = getattr(thismodule, "contractor")
+    set_contractor(method="before")
+    captured: Dict[str, List[Any]] = {}
+    try:
+        yield captured
+    except NodesReturn as e:
+        captured[key] = e.value
+    finally:
+        _set_global_contractor(old)
+
+
+contractor = set_contractor("b200", set_global=False)

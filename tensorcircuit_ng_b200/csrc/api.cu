@@ -1,0 +1,166 @@
+// api.cu — the extern "C" surface declared in include/tcb200.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/tcb200.h"
+#include "common.cuh"
+
+namespace tcb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+int launch_init_zero(void*, int, int64_t, cudaStream_t);
+int launch_dense(void*, int, int64_t, const int*, int, const void*, int64_t, cudaStream_t);
+int launch_diag(void*, int, int64_t, const int*, int, const void*, int64_t, int64_t, uint64_t,
+                cudaStream_t);
+int launch_pass(const void*, void*, int, int64_t, const int32_t*, int32_t, int, int, const void*,
+                int64_t, uint64_t, cudaStream_t);
+int launch_expect_z(const void*, int, int64_t, const uint64_t*, int, uint64_t, double*, cudaStream_t);
+int launch_expect_pauli(const void*, int, int64_t, uint64_t, uint64_t, int, uint64_t, double*,
+                        cudaStream_t);
+int launch_inner(const void*, const void*, int, int64_t, double*, cudaStream_t);
+int launch_gate_grad(const void*, const void*, int, int64_t, const int*, int, void*, int64_t,
+                     cudaStream_t);
+int launch_pack_half(const void*, void*, int, int, int, int, cudaStream_t);
+int launch_contract(const void*, int64_t, const void*, int64_t, void*, const tcb_contract_desc*, int,
+                    cudaStream_t);
+
+}  // namespace tcb
+
+using namespace tcb;
+#define S(x) reinterpret_cast<cudaStream_t>(x)
+#define NOTNULL(p, fn) TCB_REQUIRE((p) != nullptr, fn ": null pointer argument `" #p "`")
+
+extern "C" {
+
+int tcb_abi_version(void) { return TCB_ABI_VERSION; }
+const char* tcb_last_error(void) { return g_err; }
+
+int tcb_device_info(int* sm, int* cc_major, int* cc_minor, uint64_t* total_mem) {
+  int dev = 0;
+  TCB_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  TCB_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm) *sm = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (total_mem) *total_mem = (uint64_t)prop.totalGlobalMem;
+  return 0;
+}
+
+int tcb_sv_init_zero(void* state, int nbits, int64_t batch, void* stream) {
+  NOTNULL(state, "tcb_sv_init_zero");
+  return launch_init_zero(state, nbits, batch, S(stream));
+}
+
+int tcb_sv_apply_dense(void* state, int nbits, int64_t batch, const int* bitpos, int k,
+                       const void* mat, int64_t mat_batch_stride, void* stream) {
+  NOTNULL(state, "tcb_sv_apply_dense");
+  NOTNULL(bitpos, "tcb_sv_apply_dense");
+  NOTNULL(mat, "tcb_sv_apply_dense");
+  return launch_dense(state, nbits, batch, bitpos, k, mat, mat_batch_stride, S(stream));
+}
+
+int tcb_sv_apply_diag(void* state, int nbits, int64_t batch, const int* bitpos, int k,
+                      const void* diag, int64_t diag_stride, int64_t mat_batch_stride,
+                      uint64_t index_base, void* stream) {
+  NOTNULL(state, "tcb_sv_apply_diag");
+  NOTNULL(bitpos, "tcb_sv_apply_diag");
+  NOTNULL(diag, "tcb_sv_apply_diag");
+  return launch_diag(state, nbits, batch, bitpos, k, diag, diag_stride, mat_batch_stride, index_base,
+                     S(stream));
+}
+
+int tcb_sv_run_pass(void* state, int nbits, int64_t batch, const int32_t* program,
+                    int32_t program_words, int tile_bits, int low_bits, const void* gatebuf,
+                    int64_t gate_batch_stride, uint64_t index_base, void* stream) {
+  NOTNULL(state, "tcb_sv_run_pass");
+  NOTNULL(program, "tcb_sv_run_pass");
+  NOTNULL(gatebuf, "tcb_sv_run_pass");
+  return launch_pass(state, state, nbits, batch, program, program_words, tile_bits, low_bits, gatebuf,
+                     gate_batch_stride, index_base, S(stream));
+}
+
+int tcb_sv_run_pass_oop(const void* src, void* dst, int nbits, int64_t batch, const int32_t* program,
+                        int32_t program_words, int tile_bits, int low_bits, const void* gatebuf,
+                        int64_t gate_batch_stride, uint64_t index_base, void* stream) {
+  NOTNULL(src, "tcb_sv_run_pass_oop");
+  NOTNULL(dst, "tcb_sv_run_pass_oop");
+  NOTNULL(program, "tcb_sv_run_pass_oop");
+  NOTNULL(gatebuf, "tcb_sv_run_pass_oop");
+  return launch_pass(src, dst, nbits, batch, program, program_words, tile_bits, low_bits, gatebuf,
+                     gate_batch_stride, index_base, S(stream));
+}
+
+int tcb_sv_expect_z(const void* state, int nbits, int64_t batch, const uint64_t* zmasks, int nterms,
+                    uint64_t index_base, double* out, void* stream) {
+  NOTNULL(state, "tcb_sv_expect_z");
+  NOTNULL(zmasks, "tcb_sv_expect_z");
+  NOTNULL(out, "tcb_sv_expect_z");
+  return launch_expect_z(state, nbits, batch, zmasks, nterms, index_base, out, S(stream));
+}
+
+int tcb_sv_expect_pauli(const void* state, int nbits, int64_t batch, uint64_t xmask, uint64_t zmask,
+                        int ny, uint64_t index_base, double* out, void* stream) {
+  NOTNULL(state, "tcb_sv_expect_pauli");
+  NOTNULL(out, "tcb_sv_expect_pauli");
+  return launch_expect_pauli(state, nbits, batch, xmask, zmask, ny, index_base, out, S(stream));
+}
+
+int tcb_sv_inner(const void* a, const void* b, int nbits, int64_t batch, double* out, void* stream) {
+  NOTNULL(a, "tcb_sv_inner");
+  NOTNULL(b, "tcb_sv_inner");
+  NOTNULL(out, "tcb_sv_inner");
+  return launch_inner(a, b, nbits, batch, out, S(stream));
+}
+
+int tcb_sv_gate_grad(const void* lam, const void* psi_in, int nbits, int64_t batch, const int* bitpos,
+                     int k, double* grad, int64_t grad_batch_stride, void* stream) {
+  NOTNULL(lam, "tcb_sv_gate_grad");
+  NOTNULL(psi_in, "tcb_sv_gate_grad");
+  NOTNULL(bitpos, "tcb_sv_gate_grad");
+  NOTNULL(grad, "tcb_sv_gate_grad");
+  return launch_gate_grad(lam, psi_in, nbits, batch, bitpos, k, grad, grad_batch_stride, S(stream));
+}
+
+int tcb_sv_pack_half(const void* state, void* buf, int nbits, int local_bit, int want, void* stream) {
+  NOTNULL(state, "tcb_sv_pack_half");
+  NOTNULL(buf, "tcb_sv_pack_half");
+  return launch_pack_half(state, buf, nbits, local_bit, want, 0, S(stream));
+}
+
+int tcb_sv_unpack_half(void* state, const void* buf, int nbits, int local_bit, int want, void* stream) {
+  NOTNULL(state, "tcb_sv_unpack_half");
+  NOTNULL(buf, "tcb_sv_unpack_half");
+  return launch_pack_half(state, const_cast<void*>(buf), nbits, local_bit, want, 1, S(stream));
+}
+
+int tcb_tn_contract(const void* a, int64_t a_offset, const void* b, int64_t b_offset, void* c,
+                    const tcb_contract_desc* desc, int accumulate, void* stream) {
+  NOTNULL(a, "tcb_tn_contract");
+  NOTNULL(b, "tcb_tn_contract");
+  NOTNULL(c, "tcb_tn_contract");
+  return launch_contract(a, a_offset, b, b_offset, c, desc, accumulate, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,486 @@
+// sv_kernels.cu — unfused statevector kernels: per-gate dense / diagonal application
+// (the literal R7/R9 order of tensorcircuit/cons.py:429-463), reductions for
+// expectations (tensorcircuit/circuit.py:899-902 without a materialised bra), the
+// adjoint-mode gate-gradient reduction and the pack/unpack halves of a qubit swap.
+// All are HBM-bound streaming kernels: 128-bit accesses, grid = multiple of the SM count.
+#include "common.cuh"
+#include "pass_core.cuh"  // cmul / cfma
+
+namespace tcb {
+
+static inline unsigned grid_for(uint64_t work_items, int threads, int per_sm = 8) {
+  uint64_t blocks = (work_items + threads - 1) / threads;
+  const uint64_t cap = (uint64_t)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void init_zero_kernel(float4* state, uint64_t nvec_per_state, uint64_t nvec_total) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_total; i += stride) {
+    const bool first = (i % nvec_per_state) == 0;
+    state[i] = make_float4(first ? 1.f : 0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+int launch_init_zero(void* state, int nbits, int64_t batch, cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_init_zero: nbits=%d out of range", nbits);
+  const uint64_t nvec = 1ull << (nbits - 1);
+  const uint64_t total = nvec * (uint64_t)batch;
+  init_zero_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(state), nvec,
+                                                             total);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// dense k-qubit gate, one thread per group of 2^K amplitudes
+struct BitList {
+  int pos[8];     // gate qubit i -> flat bit position (qubit 0 = matrix MSB)
+  int sorted[8];  // ascending
+};
+
+template <int K>
+__global__ void __launch_bounds__(256)
+dense_kernel(float2* state, int nbits, uint64_t groups_per_state, BitList bl,
+             const float2* __restrict__ mat, long long mat_bstride) {
+  __shared__ float2 sm[(1 << K) * (1 << K)];
+  const unsigned b = blockIdx.y;
+  for (int e = threadIdx.x; e < (1 << K) * (1 << K); e += blockDim.x)
+    sm[e] = mat[(size_t)b * mat_bstride + e];
+  __syncthreads();
+  float2* st = state + ((size_t)b << nbits);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < groups_per_state;
+       gi += stride) {
+    uint64_t base = gi;
+#pragma unroll
+    for (int i = 0; i < K; ++i) base = insert_zero(base, bl.sorted[i]);
+    float2 v[1 << K];
+    uint64_t off[1 << K];
+#pragma unroll
+    for (int c = 0; c < (1 << K); ++c) {
+      uint64_t o = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if ((c >> (K - 1 - i)) & 1) o |= 1ull << bl.pos[i];
+      off[c] = o;
+      v[c] = st[base | o];
+    }
+#pragma unroll
+    for (int r = 0; r < (1 << K); ++r) {
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < (1 << K); ++c) acc = cfma(sm[r * (1 << K) + c], v[c], acc);
+      st[base | off[r]] = acc;
+    }
+  }
+}
+
+int launch_dense(void* state, int nbits, int64_t batch, const int* bitpos, int k, const void* mat,
+                 int64_t mat_bstride, cudaStream_t stream) {
+  TCB_REQUIRE(k >= 1 && k <= 5, "tcb_sv_apply_dense: k=%d unsupported (1..5)", k);
+  TCB_REQUIRE(nbits >= k && nbits <= 40, "tcb_sv_apply_dense: nbits=%d", nbits);
+  TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_apply_dense: batch=%lld", (long long)batch);
+  BitList bl;
+  for (int i = 0; i < k; ++i) {
+    TCB_REQUIRE(bitpos[i] >= 0 && bitpos[i] < nbits, "tcb_sv_apply_dense: bit %d out of range",
+                bitpos[i]);
+    for (int j = 0; j < i; ++j)
+      TCB_REQUIRE(bitpos[i] != bitpos[j], "tcb_sv_apply_dense: duplicate bit %d", bitpos[i]);
+    bl.pos[i] = bitpos[i];
+    bl.sorted[i] = bitpos[i];
+  }
+  for (int i = 1; i < k; ++i)
+    for (int j = i; j > 0 && bl.sorted[j - 1] > bl.sorted[j]; --j) {
+      int t = bl.sorted[j];
+      bl.sorted[j] = bl.sorted[j - 1];
+      bl.sorted[j - 1] = t;
+    }
+  const uint64_t gps = 1ull << (nbits - k);
+  dim3 grid(grid_for(gps, 256), (unsigned)batch);
+  float2* st = reinterpret_cast<float2*>(state);
+  const float2* m = reinterpret_cast<const float2*>(mat);
+  switch (k) {
+    case 1: dense_kernel<1><<<grid, 256, 0, stream>>>(st, nbits, gps, bl, m, mat_bstride); break;
+    case 2: dense_kernel<2><<<grid, 256, 0, stream>>>(st, nbits, gps, bl, m, mat_bstride); break;
+    case 3: dense_kernel<3><<<grid, 256, 0, stream>>>(st, nbits, gps, bl, m, mat_bstride); break;
+    case 4: dense_kernel<4><<<grid, 256, 0, stream>>>(st, nbits, gps, bl, m, mat_bstride); break;
+    case 5: dense_kernel<5><<<grid, 256, 0, stream>>>(st, nbits, gps, bl, m, mat_bstride); break;
+  }
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// diagonal k-qubit gate: one thread per amplitude pair (float4)
+struct DiagBits {
+  int pos[8];
+  int k;
+};
+
+__global__ void __launch_bounds__(256)
+diag_kernel(float4* state, int nbits, uint64_t nvec_per_state, uint64_t nvec_total, DiagBits db,
+            const float2* __restrict__ diag, long long dstride, long long mat_bstride,
+            unsigned long long index_base) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_total; i += stride) {
+    const uint64_t b = i / nvec_per_state;
+    const uint64_t x0 = ((i % nvec_per_state) << 1) | index_base;
+    const float2* d = diag + (size_t)b * mat_bstride;
+    int i0 = 0, i1 = 0;
+    for (int q = 0; q < db.k; ++q) {
+      const int p = db.pos[q];
+      const int b0 = (int)((x0 >> p) & 1ull);
+      const int b1 = (p == 0) ? 1 : b0;
+      i0 = (i0 << 1) | b0;
+      i1 = (i1 << 1) | b1;
+    }
+    const float2 d0 = d[(size_t)i0 * dstride], d1 = d[(size_t)i1 * dstride];
+    float4 v = state[i];
+    const float2 a = cmul(make_float2(v.x, v.y), d0), c = cmul(make_float2(v.z, v.w), d1);
+    state[i] = make_float4(a.x, a.y, c.x, c.y);
+  }
+}
+
+int launch_diag(void* state, int nbits, int64_t batch, const int* bitpos, int k, const void* diag,
+                int64_t dstride, int64_t mat_bstride, uint64_t index_base, cudaStream_t stream) {
+  TCB_REQUIRE(k >= 1 && k <= 8, "tcb_sv_apply_diag: k=%d unsupported (1..8)", k);
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_apply_diag: nbits=%d", nbits);
+  DiagBits db;
+  db.k = k;
+  for (int i = 0; i < k; ++i) {
+    TCB_REQUIRE(bitpos[i] >= 0 && bitpos[i] < 64, "tcb_sv_apply_diag: bit %d out of range", bitpos[i]);
+    db.pos[i] = bitpos[i];
+  }
+  const uint64_t nvec = 1ull << (nbits - 1);
+  const uint64_t total = nvec * (uint64_t)batch;
+  diag_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(state), nbits, nvec, total, db, reinterpret_cast<const float2*>(diag),
+      (long long)dstride, (long long)mat_bstride, (unsigned long long)index_base);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Z-string expectations: one read of the state for all terms.
+constexpr int EZ_THREADS = 256;
+constexpr int EZ_VEC = 4;  // float4 loads per thread per iteration (8 amplitudes)
+constexpr int EZ_MAX_TERMS = 512;
+
+__global__ void __launch_bounds__(EZ_THREADS)
+expect_z_kernel(const float4* __restrict__ state, uint64_t nvec_per_state,
+                const unsigned long long* __restrict__ zmasks, int nterms,
+                unsigned long long index_base, double* out) {
+  extern __shared__ double acc[];  // [warps][nterms]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = EZ_THREADS / 32;
+  for (int e = threadIdx.x; e < nwarps * nterms; e += EZ_THREADS) acc[e] = 0.0;
+  __syncthreads();
+  const unsigned b = blockIdx.y;
+  const float4* st = state + (size_t)b * nvec_per_state;
+  double* my = acc + warp * nterms;
+  const uint64_t chunk = (uint64_t)EZ_THREADS * EZ_VEC;
+  for (uint64_t v0 = (uint64_t)blockIdx.x * chunk; v0 < nvec_per_state;
+       v0 += (uint64_t)gridDim.x * chunk) {
+    float p[2 * EZ_VEC];
+    unsigned long long x[EZ_VEC];
+#pragma unroll
+    for (int u = 0; u < EZ_VEC; ++u) {
+      const uint64_t v = v0 + (uint64_t)u * EZ_THREADS + threadIdx.x;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < nvec_per_state) a = ldg_stream(st + v);
+      p[2 * u] = a.x * a.x + a.y * a.y;
+      p[2 * u + 1] = a.z * a.z + a.w * a.w;
+      x[u] = (v << 1) | index_base;
+    }
+    for (int t = 0; t < nterms; ++t) {
+      const unsigned long long m = zmasks[t];
+      const bool m0 = m & 1ull;  // the pair's second element differs in bit 0 only
+      float s = 0.f;
+#pragma unroll
+      for (int u = 0; u < EZ_VEC; ++u) {
+        const bool odd = __popcll(x[u] & m) & 1;
+        const float s0 = odd ? -p[2 * u] : p[2 * u];
+        const float s1 = (odd != m0) ? -p[2 * u + 1] : p[2 * u + 1];
+        s += s0 + s1;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) my[t] += (double)s;
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < nterms; t += EZ_THREADS) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += acc[w * nterms + t];
+    atomicAdd(out + (size_t)b * nterms + t, s);
+  }
+}
+
+int launch_expect_z(const void* state, int nbits, int64_t batch, const uint64_t* zmasks, int nterms,
+                    uint64_t index_base, double* out, cudaStream_t stream) {
+  TCB_REQUIRE(nterms >= 1 && nterms <= EZ_MAX_TERMS, "tcb_sv_expect_z: nterms=%d out of range", nterms);
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_expect_z: nbits=%d", nbits);
+  TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_expect_z: batch=%lld", (long long)batch);
+  const uint64_t nvec = 1ull << (nbits - 1);
+  const uint64_t chunk = (uint64_t)EZ_THREADS * EZ_VEC;
+  uint64_t gx = (nvec + chunk - 1) / chunk;
+  const uint64_t cap = (uint64_t)sm_count() * 8;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)batch);
+  const size_t smem = sizeof(double) * (EZ_THREADS / 32) * nterms;
+  expect_z_kernel<<<grid, EZ_THREADS, smem, stream>>>(
+      reinterpret_cast<const float4*>(state), nvec,
+      reinterpret_cast<const unsigned long long*>(zmasks), nterms, (unsigned long long)index_base, out);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// block-level complex reduction into double atomics
+__device__ __forceinline__ void block_reduce_add2(double re, double im, double* out) {
+  __shared__ double sre[32], sim[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sre[warp] = re;
+    sim[warp] = im;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    re = lane < nw ? sre[lane] : 0.0;
+    im = lane < nw ? sim[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      re += __shfl_xor_sync(0xffffffffu, re, o);
+      im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if (lane == 0) {
+      atomicAdd(out, re);
+      atomicAdd(out + 1, im);
+    }
+  }
+}
+
+// general Pauli string: sum_x conj(psi[x ^ xm]) * i^ny * (-1)^popc(x & zm) * psi[x]
+__global__ void __launch_bounds__(256)
+expect_pauli_kernel(const float2* __restrict__ state, uint64_t n_per_state, unsigned long long xmask,
+                    unsigned long long zmask, int ny, unsigned long long index_base, double* out) {
+  const unsigned b = blockIdx.y;
+  const float2* st = state + (size_t)b * n_per_state;
+  float re = 0.f, im = 0.f;
+  double dre = 0.0, dim_ = 0.0;
+  int cnt = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_per_state; x += stride) {
+    const float2 a = st[x];
+    const float2 c = st[x ^ xmask];
+    const bool odd = __popcll((x | index_base) & zmask) & 1;
+    // conj(c) * a
+    float pr = c.x * a.x + c.y * a.y;
+    float pi = c.x * a.y - c.y * a.x;
+    if (odd) {
+      pr = -pr;
+      pi = -pi;
+    }
+    re += pr;
+    im += pi;
+    if (++cnt == 64) {
+      dre += re;
+      dim_ += im;
+      re = im = 0.f;
+      cnt = 0;
+    }
+  }
+  dre += re;
+  dim_ += im;
+  // multiply by i^ny
+  double rr = dre, ii = dim_;
+  switch (ny & 3) {
+    case 1: rr = -dim_; ii = dre; break;
+    case 2: rr = -dre; ii = -dim_; break;
+    case 3: rr = dim_; ii = -dre; break;
+    default: break;
+  }
+  block_reduce_add2(rr, ii, out + 2 * (size_t)b);
+}
+
+int launch_expect_pauli(const void* state, int nbits, int64_t batch, uint64_t xmask, uint64_t zmask,
+                        int ny, uint64_t index_base, double* out, cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_expect_pauli: nbits=%d", nbits);
+  TCB_REQUIRE(xmask < (1ull << nbits), "tcb_sv_expect_pauli: xmask touches non-local bits");
+  TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_expect_pauli: batch=%lld", (long long)batch);
+  const uint64_t n = 1ull << nbits;
+  dim3 grid(grid_for(n, 256), (unsigned)batch);
+  expect_pauli_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float2*>(state), n, xmask, zmask,
+                                                ny, index_base, out);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// <a|b>
+__global__ void __launch_bounds__(256)
+inner_kernel(const float4* __restrict__ a, const float4* __restrict__ bb, uint64_t nvec_per_state,
+             double* out) {
+  const unsigned b = blockIdx.y;
+  const float4* pa = a + (size_t)b * nvec_per_state;
+  const float4* pb = bb + (size_t)b * nvec_per_state;
+  float re = 0.f, im = 0.f;
+  double dre = 0.0, dim_ = 0.0;
+  int cnt = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_per_state; i += stride) {
+    const float4 u = ldg_stream(pa + i), v = ldg_stream(pb + i);
+    re += u.x * v.x + u.y * v.y + u.z * v.z + u.w * v.w;
+    im += u.x * v.y - u.y * v.x + u.z * v.w - u.w * v.z;
+    if (++cnt == 32) {
+      dre += re;
+      dim_ += im;
+      re = im = 0.f;
+      cnt = 0;
+    }
+  }
+  dre += re;
+  dim_ += im;
+  block_reduce_add2(dre, dim_, out + 2 * (size_t)b);
+}
+
+int launch_inner(const void* a, const void* b, int nbits, int64_t batch, double* out,
+                 cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_inner: nbits=%d", nbits);
+  TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_inner: batch=%lld", (long long)batch);
+  const uint64_t nvec = 1ull << (nbits - 1);
+  dim3 grid(grid_for(nvec, 256), (unsigned)batch);
+  inner_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(a),
+                                         reinterpret_cast<const float4*>(b), nvec, out);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// adjoint-mode gate gradient: G[r][c] = sum_rest lam[rest,r] * conj(psi[rest,c])
+template <int K>
+__global__ void __launch_bounds__(256)
+gate_grad_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi, int nbits,
+                 uint64_t groups_per_state, BitList bl, double* grad, long long grad_bstride) {
+  constexpr int D = 1 << K;
+  const unsigned b = blockIdx.y;
+  const float2* pl = lam + ((size_t)b << nbits);
+  const float2* pp = psi + ((size_t)b << nbits);
+  float2 acc[D * D];
+#pragma unroll
+  for (int e = 0; e < D * D; ++e) acc[e] = make_float2(0.f, 0.f);
+  double2 dacc[D * D];
+#pragma unroll
+  for (int e = 0; e < D * D; ++e) dacc[e] = make_double2(0.0, 0.0);
+  int cnt = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups_per_state; g += stride) {
+    uint64_t base = g;
+#pragma unroll
+    for (int i = 0; i < K; ++i) base = insert_zero(base, bl.sorted[i]);
+    float2 l[D], p[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      uint64_t o = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if ((c >> (K - 1 - i)) & 1) o |= 1ull << bl.pos[i];
+      l[c] = pl[base | o];
+      p[c] = pp[base | o];
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        // l[r] * conj(p[c])
+        acc[r * D + c].x += l[r].x * p[c].x + l[r].y * p[c].y;
+        acc[r * D + c].y += l[r].y * p[c].x - l[r].x * p[c].y;
+      }
+    if (++cnt == 32) {
+#pragma unroll
+      for (int e = 0; e < D * D; ++e) {
+        dacc[e].x += acc[e].x;
+        dacc[e].y += acc[e].y;
+        acc[e] = make_float2(0.f, 0.f);
+      }
+      cnt = 0;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < D * D; ++e) {
+    dacc[e].x += acc[e].x;
+    dacc[e].y += acc[e].y;
+  }
+  double* gout = grad + (size_t)b * grad_bstride * 2;
+#pragma unroll
+  for (int e = 0; e < D * D; ++e) {
+    block_reduce_add2(dacc[e].x, dacc[e].y, gout + 2 * e);
+    __syncthreads();
+  }
+}
+
+int launch_gate_grad(const void* lam, const void* psi, int nbits, int64_t batch, const int* bitpos,
+                     int k, void* grad, int64_t grad_bstride, cudaStream_t stream) {
+  TCB_REQUIRE(k >= 1 && k <= 2, "tcb_sv_gate_grad: k=%d unsupported (1..2)", k);
+  TCB_REQUIRE(nbits >= k && nbits <= 40, "tcb_sv_gate_grad: nbits=%d", nbits);
+  TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_gate_grad: batch=%lld", (long long)batch);
+  BitList bl;
+  for (int i = 0; i < k; ++i) {
+    TCB_REQUIRE(bitpos[i] >= 0 && bitpos[i] < nbits, "tcb_sv_gate_grad: bit %d out of range", bitpos[i]);
+    bl.pos[i] = bitpos[i];
+    bl.sorted[i] = bitpos[i];
+  }
+  if (k == 2 && bl.sorted[0] > bl.sorted[1]) {
+    int t = bl.sorted[0];
+    bl.sorted[0] = bl.sorted[1];
+    bl.sorted[1] = t;
+  }
+  const uint64_t gps = 1ull << (nbits - k);
+  dim3 grid(grid_for(gps, 256, 4), (unsigned)batch);
+  const float2* l = reinterpret_cast<const float2*>(lam);
+  const float2* p = reinterpret_cast<const float2*>(psi);
+  double* g = reinterpret_cast<double*>(grad);
+  if (k == 1)
+    gate_grad_kernel<1><<<grid, 256, 0, stream>>>(l, p, nbits, gps, bl, g, grad_bstride);
+  else
+    gate_grad_kernel<2><<<grid, 256, 0, stream>>>(l, p, nbits, gps, bl, g, grad_bstride);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// pack / unpack the half of the state with local bit == want (global<->local qubit swap)
+__global__ void __launch_bounds__(256)
+pack_half_kernel(const float2* __restrict__ state, float2* __restrict__ buf, uint64_t nhalf, int bit,
+                 int want, int unpack, float2* state_w) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nhalf; i += stride) {
+    const uint64_t x = insert_zero(i, bit) | ((uint64_t)want << bit);
+    if (unpack)
+      state_w[x] = buf[i];
+    else
+      buf[i] = state[x];
+  }
+}
+
+int launch_pack_half(const void* state, void* buf, int nbits, int bit, int want, int unpack,
+                     cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40 && bit >= 0 && bit < nbits, "tcb_sv_pack_half: bad bit %d", bit);
+  const uint64_t nhalf = 1ull << (nbits - 1);
+  pack_half_kernel<<<grid_for(nhalf, 256), 256, 0, stream>>>(
+      reinterpret_cast<const float2*>(state), reinterpret_cast<float2*>(buf), nhalf, bit, want & 1,
+      unpack, reinterpret_cast<float2*>(const_cast<void*>(state)));
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tcb

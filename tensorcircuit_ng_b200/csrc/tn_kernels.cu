@@ -1,0 +1,164 @@
+// tn_kernels.cu — pairwise tensor-network contraction with bit-scattered addressing
+// (no transposed copies: K2 of SURVEY §2.3 is folded into the addressing).
+// Replaces tn.contract_between -> backend.tensordot (tensorcircuit/cons.py:948) and
+// cotengra's contract_core steps (tensorcircuit/experimental.py:1008).
+//
+// All modes have extent 2, so "permute + reshape + GEMM" is a GEMM whose row / column /
+// reduction indices are *bit-deposited* into the operands' flat addresses.
+//
+// v1 (this file): SIMT FP32 kernel, shared-memory tiled:  C[b, m, n] = sum_k A[b,m,k] B[b,k,n]
+//   CTA tile 64 (m) x 64 (n) outputs, K chunks of 16, 256 threads, 4x4 micro-tile per thread.
+#include "common.cuh"
+#include "pass_core.cuh"
+#include "../../include/tcb200.h"
+
+namespace tcb {
+
+struct ContractParams {
+  int nb, nm, nn, nk;
+  int8_t batch_a[32], batch_b[32], batch_c[32];
+  int8_t m_a[32], m_c[32];
+  int8_t n_b[32], n_c[32];
+  int8_t k_a[32], k_b[32];
+  int conj_a, conj_b, accumulate;
+};
+
+__device__ __forceinline__ uint64_t deposit(uint64_t v, const int8_t* pos, int n) {
+  uint64_t r = 0;
+  for (int i = 0; i < n; ++i) r |= ((v >> i) & 1ull) << pos[i];
+  return r;
+}
+
+constexpr int TM = 64, TN = 64, TK = 16, CT_THREADS = 256;
+
+// logical index convention: bit i of m <-> m_a[i]/m_c[i], etc. (host lists modes in any order)
+__global__ void __launch_bounds__(CT_THREADS)
+contract_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float2* C,
+                ContractParams p) {
+  __shared__ float2 sA[TK][TM + 1];
+  __shared__ float2 sB[TK][TN + 1];
+  __shared__ uint64_t offAm[TM], offBn[TN], offCm[TM], offCn[TN];
+
+  const uint64_t Mtot = 1ull << p.nm, Ntot = 1ull << p.nn, Ktot = 1ull << p.nk;
+  const uint64_t tiles_m = (Mtot + TM - 1) / TM, tiles_n = (Ntot + TN - 1) / TN;
+  const uint64_t tiles_per_batch = tiles_m * tiles_n;
+  const uint64_t total_tiles = tiles_per_batch << p.nb;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads, each 4 (m) x 4 (n)
+
+  for (uint64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint64_t bt = tile / tiles_per_batch;
+    const uint64_t tr = tile % tiles_per_batch;
+    const uint64_t m0 = (tr / tiles_n) * TM, n0 = (tr % tiles_n) * TN;
+    const uint64_t a_b = deposit(bt, p.batch_a, p.nb), b_b = deposit(bt, p.batch_b, p.nb),
+                   c_b = deposit(bt, p.batch_c, p.nb);
+    __syncthreads();
+    if (tid < TM) {
+      offAm[tid] = deposit(m0 + tid, p.m_a, p.nm);
+      offCm[tid] = deposit(m0 + tid, p.m_c, p.nm);
+    } else if (tid < TM + TN) {
+      const int j = tid - TM;
+      offBn[j] = deposit(n0 + j, p.n_b, p.nn);
+      offCn[j] = deposit(n0 + j, p.n_c, p.nn);
+    }
+    __syncthreads();
+
+    float2 acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+    for (uint64_t k0 = 0; k0 < Ktot; k0 += TK) {
+      // stage A tile: TK x TM, B tile: TK x TN
+      for (int e = tid; e < TK * TM; e += CT_THREADS) {
+        const int kk = e / TM, mm = e % TM;
+        float2 v = make_float2(0.f, 0.f);
+        if (k0 + kk < Ktot && m0 + mm < Mtot) {
+          v = A[a_b | offAm[mm] | deposit(k0 + kk, p.k_a, p.nk)];
+          if (p.conj_a) v.y = -v.y;
+        }
+        sA[kk][mm] = v;
+      }
+      for (int e = tid; e < TK * TN; e += CT_THREADS) {
+        const int kk = e / TN, nn = e % TN;
+        float2 v = make_float2(0.f, 0.f);
+        if (k0 + kk < Ktot && n0 + nn < Ntot) {
+          v = B[b_b | offBn[nn] | deposit(k0 + kk, p.k_b, p.nk)];
+          if (p.conj_b) v.y = -v.y;
+        }
+        sB[kk][nn] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < TK; ++kk) {
+        float2 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty + 16 * i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = cfma(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int mm = ty + 16 * i, nn = tx + 16 * j;
+        if (m0 + mm < Mtot && n0 + nn < Ntot) {
+          const uint64_t addr = c_b | offCm[mm] | offCn[nn];
+          float2 v = acc[i][j];
+          if (p.accumulate) {
+            const float2 old = C[addr];
+            v.x += old.x;
+            v.y += old.y;
+          }
+          C[addr] = v;
+        }
+      }
+  }
+}
+
+int launch_contract(const void* a, int64_t a_offset, const void* b, int64_t b_offset, void* c,
+                    const tcb_contract_desc* d, int accumulate, cudaStream_t stream) {
+  TCB_REQUIRE(d != nullptr, "tcb_tn_contract: null descriptor");
+  TCB_REQUIRE(d->n_batch >= 0 && d->n_m >= 0 && d->n_n >= 0 && d->n_k >= 0 && d->n_batch <= 32 &&
+                  d->n_m <= 32 && d->n_n <= 32 && d->n_k <= 32,
+              "tcb_tn_contract: mode counts out of range");
+  TCB_REQUIRE(d->n_batch + d->n_m + d->n_n <= 34, "tcb_tn_contract: output too large");
+  ContractParams p;
+  p.nb = d->n_batch;
+  p.nm = d->n_m;
+  p.nn = d->n_n;
+  p.nk = d->n_k;
+  for (int i = 0; i < 32; ++i) {
+    p.batch_a[i] = d->batch_a[i];
+    p.batch_b[i] = d->batch_b[i];
+    p.batch_c[i] = d->batch_c[i];
+    p.m_a[i] = d->m_a[i];
+    p.m_c[i] = d->m_c[i];
+    p.n_b[i] = d->n_b[i];
+    p.n_c[i] = d->n_c[i];
+    p.k_a[i] = d->k_a[i];
+    p.k_b[i] = d->k_b[i];
+  }
+  p.conj_a = d->conj_a;
+  p.conj_b = d->conj_b;
+  p.accumulate = accumulate;
+  const uint64_t Mtot = 1ull << p.nm, Ntot = 1ull << p.nn;
+  const uint64_t tiles = (((Mtot + TM - 1) / TM) * ((Ntot + TN - 1) / TN)) << p.nb;
+  uint64_t grid = tiles;
+  const uint64_t cap = (uint64_t)sm_count() * 4;
+  if (grid > cap) grid = cap;
+  contract_kernel<<<(unsigned)grid, CT_THREADS, 0, stream>>>(
+      reinterpret_cast<const float2*>(a) + a_offset, reinterpret_cast<const float2*>(b) + b_offset,
+      reinterpret_cast<float2*>(c), p);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tcb

@@ -1,0 +1,378 @@
+"""
+Gate tensors on the torch backend — same names, argument meaning and tensor
+layout as the reference's `tensorcircuit/gates.py` (each factory cites its lines).
+
+Layout: a k-qubit gate is a rank-2k complex64 tensor [out_0..out_{k-1},
+in_0..in_{k-1}] (gates.py:497-516).  On top of the reference semantics every
+`Gate` carries a structural hint `_b200_kind` that the pass planner uses to pick
+the diagonal / controlled fast paths without reading values back from the GPU:
+
+    ("dense",)                generic 2^k x 2^k
+    ("diag",)                 dense tensor whose matrix is diagonal (rz, rzz, cz, phase, ...)
+    ("diagvec",)              packed diagonal of length 2^k (`diagonal` gate, gates.py:1059)
+    ("ctrl", nctrl, pol)      first `nctrl` qubits are controls (bit i of pol = required value),
+                              last qubit is the target of a 2x2 block
+
+The hint is derived from the *factory* (never from the user-overridable node
+name, tensorcircuit/basecircuit.py:278).
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, Dict, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import tn
+
+Tensor = Any
+dtype = torch.complex64
+rdtype = torch.float32
+
+
+class Gate(tn.Node):  # gates.py:185-224
+    def copy(self, conjugate: bool = False) -> "Gate":
+        r = super().copy(conjugate)
+        r.__class__ = Gate
+        return r  # type: ignore[return-value]
+
+
+# ---- constant matrices (gates.py:33-174) ----------------------------------------
+_i00 = np.array([[1.0, 0.0], [0.0, 0.0]])
+_i01 = np.array([[0.0, 1.0], [0.0, 0.0]])
+_i10 = np.array([[0.0, 0.0], [1.0, 0.0]])
+_i11 = np.array([[0.0, 0.0], [0.0, 1.0]])
+_h_matrix = 1 / np.sqrt(2) * np.array([[1.0, 1.0], [1.0, -1.0]])
+_i_matrix = np.array([[1.0, 0.0], [0.0, 1.0]])
+_x_matrix = np.array([[0.0, 1.0], [1.0, 0.0]])
+_y_matrix = np.array([[0.0, -1j], [1j, 0.0]])
+_z_matrix = np.array([[1.0, 0.0], [0.0, -1.0]])
+_s_matrix = np.array([[1.0, 0.0], [0.0, 1j]])
+_t_matrix = np.array([[1.0, 0.0], [0.0, np.exp(np.pi / 4 * 1j)]])
+_wroot_matrix = (
+    1 / np.sqrt(2) * np.array([[1, -1 / np.sqrt(2) * (1 + 1.0j)], [1 / np.sqrt(2) * (1 - 1.0j), 1]])
+)
+_ii_matrix = np.kron(_i_matrix, _i_matrix)
+_xx_matrix = np.kron(_x_matrix, _x_matrix)
+_yy_matrix = np.kron(_y_matrix, _y_matrix)
+_zz_matrix = np.kron(_z_matrix, _z_matrix)
+_cnot_matrix = np.array([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 0, 1.0], [0, 0, 1.0, 0]])
+_cz_matrix = np.array([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 0], [0, 0, 0, -1.0]])
+_cy_matrix = np.array([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 0, -1.0j], [0, 0, 1.0j, 0]])
+_swap_matrix = np.array([[1.0, 0, 0, 0], [0, 0, 1.0, 0], [0, 1.0, 0, 0], [0, 0, 0, 1.0]])
+_iswap_d1_matrix = np.diag([1.0, 0, 0, 1.0])
+_iswap_d2_matrix = np.diag([0, 1.0, 1.0, 0])
+_iswap_od_matrix = np.array([[0, 0, 0, 0], [0, 0, 1.0, 0], [0, 1.0, 0, 0], [0, 0, 0, 0]])
+_toffoli_matrix = np.eye(8)[[0, 1, 2, 3, 4, 5, 7, 6]]
+_fredkin_matrix = np.eye(8)[[0, 1, 2, 3, 4, 6, 5, 7]]
+
+_const_cache: Dict[Any, torch.Tensor] = {}
+
+
+def _device() -> torch.device:
+    return torch.get_default_device() if hasattr(torch, "get_default_device") else torch.device("cpu")
+
+
+def _const(m: np.ndarray, dev: Optional[torch.device] = None) -> torch.Tensor:
+    """Cached complex64 copy of a host constant on the working device."""
+    dev = dev or _device()
+    m = np.asarray(m)
+    key = (m.shape, m.dtype.str, m.tobytes(), str(dev))
+    t = _const_cache.get(key)
+    if t is None:
+        t = torch.as_tensor(m.astype(np.complex64), device=dev)
+        _const_cache[key] = t
+    return t
+
+
+def num_to_tensor(*num: Any, dtype_: Any = None) -> Any:  # gates.py:227-286
+    """Cast numbers / arrays / tensors to complex64 torch tensors (gradients flow through the cast)."""
+    dt = dtype if dtype_ is None else dtype_
+    out = []
+    for n in num:
+        if isinstance(n, torch.Tensor):
+            out.append(n.to(dt) if n.dtype != dt else n)
+        else:
+            out.append(torch.as_tensor(np.asarray(n), device=_device()).to(dt))
+    return out[0] if len(out) == 1 else out
+
+
+array_to_tensor = num_to_tensor
+
+
+def _reshape2(t: torch.Tensor) -> torch.Tensor:
+    n = int(round(math.log2(t.numel())))
+    return t.reshape([2] * n)
+
+
+def _is_diag_host(m: np.ndarray) -> bool:
+    d = int(round(math.sqrt(m.size)))
+    mm = np.reshape(np.asarray(m), [d, d])
+    return bool(np.count_nonzero(mm - np.diag(np.diagonal(mm))) == 0)
+
+
+def _mk(t: torch.Tensor, kind: Tuple[Any, ...], name: Optional[str] = None) -> Gate:
+    g = Gate(t, name=name)
+    g._b200_kind = kind  # type: ignore[attr-defined]
+    return g
+
+
+class GateF:  # gates.py:298-380
+    def __init__(self, m: np.ndarray, n: str, kind: Tuple[Any, ...]):
+        self.m, self.n, self.kind = m, n, kind
+
+    def __call__(self) -> Gate:
+        return _mk(_reshape2(_const(self.m)), self.kind, name=self.n)
+
+    def __str__(self) -> str:
+        return self.n
+
+    __repr__ = __str__
+
+
+def _fixed(m: np.ndarray, name: str, kind: Optional[Tuple[Any, ...]] = None) -> GateF:
+    if kind is None:
+        kind = ("diag",) if _is_diag_host(m) else ("dense",)
+    return GateF(m, name, kind)
+
+
+i = _fixed(_i_matrix, "i")
+x = _fixed(_x_matrix, "x")
+y = _fixed(_y_matrix, "y")
+z = _fixed(_z_matrix, "z")
+h = _fixed(_h_matrix, "h")
+s = _fixed(_s_matrix, "s")
+t = _fixed(_t_matrix, "t")
+_sd_matrix = np.conj(_s_matrix).T
+_td_matrix = np.conj(_t_matrix).T
+sd = _fixed(_sd_matrix, "sd")  # gates.py:1217-1219
+td = _fixed(_td_matrix, "td")
+wroot = _fixed(_wroot_matrix, "wroot")
+cnot = _fixed(_cnot_matrix, "cnot", ("ctrl", 1, 1))
+cz = _fixed(_cz_matrix, "cz")
+cy = _fixed(_cy_matrix, "cy", ("ctrl", 1, 1))
+swap = _fixed(_swap_matrix, "swap")
+toffoli = _fixed(_toffoli_matrix, "toffoli", ("ctrl", 2, 3))
+fredkin = _fixed(_fredkin_matrix, "fredkin")
+_ox_matrix = np.kron(_i00, _x_matrix) + np.kron(_i11, _i_matrix)  # gates.py:362-380
+_oy_matrix = np.kron(_i00, _y_matrix) + np.kron(_i11, _i_matrix)
+_oz_matrix = np.kron(_i00, _z_matrix) + np.kron(_i11, _i_matrix)
+ox = _fixed(_ox_matrix, "ox", ("ctrl", 1, 0))
+oy = _fixed(_oy_matrix, "oy", ("ctrl", 1, 0))
+oz = _fixed(_oz_matrix, "oz")
+
+
+def _dev(th: torch.Tensor) -> torch.device:
+    return th.device if th.is_cuda else _device()
+
+
+def _scalar(theta: Any) -> torch.Tensor:
+    th = num_to_tensor(theta)
+    return th.reshape(()) if th.numel() == 1 else th
+
+
+def phase_gate(theta: float = 0) -> Gate:  # gates.py:584-603
+    th = _scalar(theta)
+    unitary = _const(_i00, _dev(th)) + torch.exp(1.0j * th) * _const(_i11, _dev(th))
+    return _mk(unitary, ("diag",))
+
+
+def u_gate(theta: float = 0.0, phi: float = 0.0, lbd: float = 0.0) -> Gate:  # gates.py:630-658
+    th, ph, lb = _scalar(theta), _scalar(phi), _scalar(lbd)
+    unitary = (
+        torch.cos(th / 2) * _const(_i00, _dev(th))
+        - torch.exp(1.0j * lb) * torch.sin(th / 2) * _const(_i01, _dev(th))
+        + torch.exp(1.0j * ph) * torch.sin(th / 2) * _const(_i10, _dev(th))
+        + torch.exp(1.0j * (ph + lb)) * torch.cos(th / 2) * _const(_i11, _dev(th))
+    )
+    return _mk(unitary, ("dense",))
+
+
+def r_gate(theta: float = 0.0, alpha: float = 0.0, phi: float = 0.0) -> Gate:  # gates.py:661-689
+    th, ph, al = _scalar(theta), _scalar(phi), _scalar(alpha)
+    unitary = (
+        torch.cos(th) * _const(_i_matrix, _dev(th))
+        - 1.0j * torch.cos(ph) * torch.sin(al) * torch.sin(th) * _const(_x_matrix, _dev(th))
+        - 1.0j * torch.sin(ph) * torch.sin(al) * torch.sin(th) * _const(_y_matrix, _dev(th))
+        - 1.0j * torch.sin(th) * torch.cos(al) * _const(_z_matrix, _dev(th))
+    )
+    return _mk(unitary, ("dense",))
+
+
+def rx_gate(theta: float = 0.0) -> Gate:  # gates.py:692-707
+    th = _scalar(theta)
+    unitary = torch.cos(th / 2.0) * _const(_i_matrix, _dev(th)) - 1.0j * torch.sin(th / 2.0) * _const(_x_matrix, _dev(th))
+    return _mk(unitary, ("dense",))
+
+
+def ry_gate(theta: float = 0.0) -> Gate:  # gates.py:710-725
+    th = _scalar(theta)
+    unitary = torch.cos(th / 2.0) * _const(_i_matrix, _dev(th)) - 1.0j * torch.sin(th / 2.0) * _const(_y_matrix, _dev(th))
+    return _mk(unitary, ("dense",))
+
+
+def rz_gate(theta: float = 0.0) -> Gate:  # gates.py:728-743
+    th = _scalar(theta)
+    unitary = torch.cos(th / 2.0) * _const(_i_matrix, _dev(th)) - 1.0j * torch.sin(th / 2.0) * _const(_z_matrix, _dev(th))
+    return _mk(unitary, ("diag",))
+
+
+def iswap_gate(theta: float = 1.0) -> Gate:  # gates.py:788-814
+    th = _scalar(theta)
+    unitary = (
+        _const(_iswap_d1_matrix, _dev(th))
+        + torch.cos(th * np.pi / 2) * _const(_iswap_d2_matrix, _dev(th))
+        + 1.0j * torch.sin(th * np.pi / 2) * _const(_iswap_od_matrix, _dev(th))
+    )
+    return _mk(unitary.reshape(2, 2, 2, 2), ("dense",))
+
+
+_cr_j = np.kron(_i00, _i_matrix)
+_cr_i = np.kron(_i11, _i_matrix)
+_cr_x = np.kron(_i11, _x_matrix)
+_cr_y = np.kron(_i11, _y_matrix)
+_cr_z = np.kron(_i11, _z_matrix)
+
+
+def cr_gate(theta: float = 0.0, alpha: float = 0.0, phi: float = 0.0) -> Gate:  # gates.py:817-849
+    th, ph, al = _scalar(theta), _scalar(phi), _scalar(alpha)
+    unitary = (
+        _const(_cr_j, _dev(th))
+        + torch.cos(th) * _const(_cr_i, _dev(th))
+        - 1.0j * torch.cos(ph) * torch.sin(al) * torch.sin(th) * _const(_cr_x, _dev(th))
+        - 1.0j * torch.sin(ph) * torch.sin(al) * torch.sin(th) * _const(_cr_y, _dev(th))
+        - 1.0j * torch.sin(th) * torch.cos(al) * _const(_cr_z, _dev(th))
+    )
+    return _mk(unitary.reshape(2, 2, 2, 2), ("ctrl", 1, 1))
+
+
+def _probe_kind(unitary: Any) -> Tuple[Any, ...]:
+    """Structure of a user-supplied matrix, decided on the host when the values are host data."""
+    if isinstance(unitary, np.ndarray) or isinstance(unitary, (list, tuple)):
+        return ("diag",) if _is_diag_host(np.asarray(unitary)) else ("dense",)
+    if isinstance(unitary, torch.Tensor) and not unitary.is_cuda and not unitary.requires_grad:
+        try:
+            return ("diag",) if _is_diag_host(unitary.detach().numpy()) else ("dense",)
+        except Exception:  # pylint: disable=broad-except  (functorch wrappers etc.)
+            return ("dense",)
+    return ("dense",)
+
+
+def any_gate(unitary: Any, name: str = "any") -> Gate:  # gates.py:866-890
+    if isinstance(unitary, tn.Node):
+        unitary.tensor = unitary.tensor.to(dtype)
+        if not isinstance(unitary, Gate):
+            unitary.__class__ = Gate
+        if not hasattr(unitary, "_b200_kind"):
+            unitary._b200_kind = ("dense",)  # type: ignore[attr-defined]
+        return unitary  # type: ignore[return-value]
+    kind = _probe_kind(unitary)
+    return _mk(_reshape2(num_to_tensor(unitary)), kind, name=name)
+
+
+def exponential_gate(unitary: Any, theta: float, name: str = "none") -> Gate:  # gates.py:893-914
+    kind = _probe_kind(unitary)
+    th, u = _scalar(theta), num_to_tensor(unitary)
+    d = int(round(math.sqrt(u.numel())))
+    mat = torch.linalg.matrix_exp(-1.0j * th * u.reshape(d, d))
+    return _mk(_reshape2(mat), kind, name="exp-" + name)
+
+
+def exponential_gate_unity(unitary: Any, theta: float, half: bool = False, name: str = "none") -> Gate:
+    """cos(theta) I - i sin(theta) U for U^2 = I (gates.py:920-953)."""
+    kind = _probe_kind(unitary)
+    th = _scalar(theta)
+    u = _const(unitary, _dev(th)) if isinstance(unitary, np.ndarray) else num_to_tensor(unitary)
+    n = int(round(math.log2(u.numel())))
+    it = _const(_eye_for(n), _dev(th))
+    u = u.reshape([2] * n)
+    if half is True:
+        th = th / 2.0
+    mat = torch.cos(th) * it - 1.0j * torch.sin(th) * u
+    return _mk(mat, kind, name="exp1-" + name)
+
+
+_eyes: Dict[int, np.ndarray] = {}
+
+
+def _eye_for(n: int) -> np.ndarray:
+    if n not in _eyes:
+        _eyes[n] = np.eye(2 ** (n // 2)).reshape([2] * n)
+    return _eyes[n]
+
+
+exp_gate = exponential_gate
+exp1_gate = exponential_gate_unity
+
+
+def rzz_gate(theta: float = 0.0, **kws: Any) -> Gate:  # gates.py:976
+    return exp1_gate(_zz_matrix, theta, half=True)
+
+
+def rxx_gate(theta: float = 0.0, **kws: Any) -> Gate:  # gates.py:977
+    return exp1_gate(_xx_matrix, theta, half=True)
+
+
+def ryy_gate(theta: float = 0.0, **kws: Any) -> Gate:  # gates.py:978
+    return exp1_gate(_yy_matrix, theta, half=True)
+
+
+def _controlled(f: Callable[..., Gate], name: str, on: int) -> Callable[..., Gate]:
+    """gates.py:343-380 controlled()/ocontrolled(): block matrix [[I,0],[0,U]] / [[U,0],[0,I]]."""
+
+    def g(**kws: Any) -> Gate:
+        base = f(**kws)
+        u = base.tensor
+        d = int(round(math.sqrt(u.numel())))
+        u = u.reshape(d, d)
+        eye = torch.eye(d, dtype=dtype, device=u.device)
+        zero = torch.zeros(d, d, dtype=dtype, device=u.device)
+        if on == 1:
+            cu = torch.cat([torch.cat([eye, zero], dim=1), torch.cat([zero, u], dim=1)], dim=0)
+        else:
+            cu = torch.cat([torch.cat([u, zero], dim=1), torch.cat([zero, eye], dim=1)], dim=0)
+        bk = getattr(base, "_b200_kind", ("dense",))
+        if bk[0] in ("diag",):
+            kind: Tuple[Any, ...] = ("diag",)
+        elif d == 2:
+            kind = ("ctrl", 1, on)
+        else:
+            kind = ("dense",)
+        return _mk(_reshape2(cu), kind, name=name)
+
+    return g
+
+
+cu_gate = _controlled(u_gate, "cu", 1)
+crx_gate = _controlled(rx_gate, "crx", 1)
+cry_gate = _controlled(ry_gate, "cry", 1)
+crz_gate = _controlled(rz_gate, "crz", 1)
+cphase_gate = _controlled(phase_gate, "cphase", 1)
+orx_gate = _controlled(rx_gate, "orx", 0)
+ory_gate = _controlled(ry_gate, "ory", 0)
+orz_gate = _controlled(rz_gate, "orz", 0)
+
+
+def diagonal_gate(diag: Any, dim: int = 2, name: str = "diagonal") -> Gate:  # gates.py:1059-1078
+    d = num_to_tensor(diag)
+    noe = int(round(math.log(d.numel()) / math.log(dim)))
+    return _mk(d.reshape([dim] * noe), ("diagvec",), name=name)
+
+
+def matrix_for_gate(g: Gate) -> np.ndarray:
+    t_ = g.tensor
+    d = int(round(math.sqrt(t_.numel())))
+    return t_.reshape(d, d).detach().cpu().numpy()
+
+
+# aliases the reference exposes (gates.py:1186-1232 meta_vgate)
+r, u, rx, ry, rz, phase, iswap, any, exp, exp1, cr = (  # noqa: A001
+    r_gate, u_gate, rx_gate, ry_gate, rz_gate, phase_gate, iswap_gate, any_gate, exp_gate, exp1_gate,
+    cr_gate,
+)  # fmt: skip
+rzz, rxx, ryy = rzz_gate, rxx_gate, ryy_gate
+cu, crx, cry, crz, cphase, orx, ory, orz = (
+    cu_gate, crx_gate, cry_gate, crz_gate, cphase_gate, orx_gate, ory_gate, orz_gate,
+)  # fmt: skip

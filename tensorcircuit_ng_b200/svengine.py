@@ -1,0 +1,289 @@
+"""
+Statevector engine: recognises a circuit-shaped tensor network at the contractor
+boundary, compiles it into fused HBM passes (passplan.py) and runs them through the
+C ABI (`tcb_sv_*`, include/tcb200.h).
+
+What it replaces in the reference: the `for (a, b) in path: tn.contract_between(...)`
+loop plus the final `reorder_edges` of tensorcircuit/cons.py:937-960 when the network
+handed to the contractor is `Circuit._copy()` (tensorcircuit/circuit.py:711-712) —
+i.e. `wavefunction()` / the cached state of `expectation*()`.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, passplan
+from .passplan import GateOp, GlobalStep, PassStep, Plan
+
+_MAX_STATE_QUBITS = 34  # 2^34 complex64 = 128 GiB: upper bound for one B200
+
+
+class NotCircuitShaped(Exception):
+    """The network is not `inputs -> gates -> dangling outputs`; use the TN path."""
+
+
+# ---------------------------------------------------------------------------------------
+def _is_copynode(node: Any) -> bool:
+    return type(node).__name__ == "CopyNode"
+
+
+def _is_input_node(node: Any) -> bool:
+    flag = getattr(node, "flag", "")
+    if isinstance(flag, str) and flag.startswith("inputs"):
+        return True
+    return node.get_rank() == 1 and str(getattr(node, "name", "")).startswith("qb-")
+
+
+def _other_end(edge: Any, node: Any, axis: int) -> Tuple[Any, int]:
+    if edge.node1 is node and edge.axis1 == axis:
+        return edge.node2, edge.axis2
+    return edge.node1, edge.axis1
+
+
+def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any]):
+    """Walk every output wire back to its input; returns (n, init_node or None, gate list).
+
+    gate list entries: (node, qubits tuple, packed_diagonal flag) sorted by creation order
+    (`_stable_id_`, tensorcircuit/cons.py:28-53 — the only record of program order the
+    contractor sees).  Raises NotCircuitShaped on anything else (expectation sandwiches,
+    amplitude networks, MPS inputs, ...).
+    """
+    n = len(output_edge_order)
+    if n == 0 or n > _MAX_STATE_QUBITS:
+        raise NotCircuitShaped("no dangling outputs" if n == 0 else "too many qubits for a statevector")
+    node_ids = {id(x) for x in nodes}
+    legs: Dict[int, List[Optional[int]]] = {}
+    gate_nodes: Dict[int, Any] = {}
+    diag_legs: Dict[int, List[Optional[int]]] = {}
+    init_node = None
+    n_zero_inputs = 0
+    visited_inputs = set()
+    for q, e in enumerate(output_edge_order):
+        if not e.is_dangling():
+            raise NotCircuitShaped("output edge is not dangling")
+        node, axis = e.node1, e.axis1
+        steps = 0
+        while True:
+            steps += 1
+            if steps > 1_000_000:
+                raise NotCircuitShaped("wire walk did not terminate")
+            if id(node) not in node_ids:
+                raise NotCircuitShaped("wire leaves the node set")
+            if _is_copynode(node):
+                # diagonal gate in hyperedge form (tensorcircuit/basecircuit.py:343-355):
+                # cn[0] <- previous front, cn[1] <-> coefficient leg, cn[2] -> next
+                if node.get_rank() != 3 or axis != 2:
+                    raise NotCircuitShaped("unsupported CopyNode wiring")
+                coef, cax = _other_end(node.edges[1], node, 1)
+                if coef is None or _is_copynode(coef):
+                    raise NotCircuitShaped("CopyNode without coefficient node")
+                dl = diag_legs.setdefault(id(coef), [None] * coef.get_rank())
+                gate_nodes[id(coef)] = coef
+                if dl[cax] is not None:
+                    raise NotCircuitShaped("coefficient leg used twice")
+                dl[cax] = q
+                prev = node.edges[0]
+                if prev.is_dangling():
+                    raise NotCircuitShaped("dangling CopyNode input")
+                node, axis = _other_end(prev, node, 0)
+                continue
+            if _is_input_node(node):
+                if node.get_rank() == 1:
+                    n_zero_inputs += 1
+                else:
+                    if init_node is not None and init_node is not node:
+                        raise NotCircuitShaped("several multi-leg input nodes")
+                    if axis != q:
+                        raise NotCircuitShaped("input legs are permuted")
+                    init_node = node
+                if (id(node), axis) in visited_inputs:
+                    raise NotCircuitShaped("input leg reached twice")
+                visited_inputs.add((id(node), axis))
+                break
+            r = node.get_rank()
+            if r % 2:
+                raise NotCircuitShaped("odd-rank node on a wire")
+            k = r // 2
+            if axis >= k:
+                raise NotCircuitShaped("wire enters a gate through an input leg")
+            lg = legs.setdefault(id(node), [None] * k)
+            gate_nodes[id(node)] = node
+            if lg[axis] is not None:
+                raise NotCircuitShaped("gate output leg used twice")
+            lg[axis] = q
+            ine = node.edges[axis + k]
+            if ine.is_dangling():
+                raise NotCircuitShaped("dangling gate input")
+            node, axis = _other_end(ine, node, axis + k)
+    if init_node is not None and n_zero_inputs:
+        raise NotCircuitShaped("mixed input kinds")
+    if init_node is not None and init_node.get_rank() != n:
+        raise NotCircuitShaped("input node rank mismatch")
+    # every node must have been accounted for
+    seen = set(legs) | set(diag_legs)
+    gates: List[Tuple[Any, Tuple[int, ...], bool]] = []
+    for x in nodes:
+        if _is_copynode(x) or _is_input_node(x):
+            continue
+        if id(x) not in seen:
+            raise NotCircuitShaped("node not on any wire")
+        if id(x) in legs:
+            lg = legs[id(x)]
+            if any(v is None for v in lg):
+                raise NotCircuitShaped("gate with unvisited legs")
+            gates.append((x, tuple(int(v) for v in lg), False))  # type: ignore[arg-type]
+        else:
+            dl = diag_legs[id(x)]
+            if any(v is None for v in dl):
+                raise NotCircuitShaped("diagonal gate with unvisited legs")
+            gates.append((x, tuple(int(v) for v in dl), True))  # type: ignore[arg-type]
+    gates.sort(key=lambda g: getattr(g[0], "_stable_id_", -1))
+    return n, init_node, gates
+
+
+# names whose matrices are structurally diagonal / controlled in the reference's gates.py; used
+# only for nodes that do not carry our own `_b200_kind` hint (a real TensorCircuit-NG install).
+_NAME_KINDS: Dict[str, Tuple[Any, ...]] = {
+    "z": ("diag",), "s": ("diag",), "t": ("diag",), "sd": ("diag",), "td": ("diag",), "i": ("diag",),
+    "rz": ("diag",), "phase": ("diag",), "cz": ("diag",), "rzz": ("diag",), "cphase": ("diag",),
+    "crz": ("diag",), "oz": ("diag",), "orz": ("diag",),
+    "cnot": ("ctrl", 1, 1), "cx": ("ctrl", 1, 1), "cy": ("ctrl", 1, 1), "crx": ("ctrl", 1, 1),
+    "cry": ("ctrl", 1, 1), "cu": ("ctrl", 1, 1), "cr": ("ctrl", 1, 1), "toffoli": ("ctrl", 2, 3),
+    "ox": ("ctrl", 1, 0), "oy": ("ctrl", 1, 0), "orx": ("ctrl", 1, 0), "ory": ("ctrl", 1, 0),
+}  # fmt: skip
+
+trust_gate_names = False  # opt-in: node names are user-overridable in the reference
+
+
+def gate_kind(node: Any, packed_diag: bool) -> Tuple[Any, ...]:
+    if packed_diag:
+        return ("diagvec",)
+    kind = getattr(node, "_b200_kind", None)
+    if kind is not None:
+        return tuple(kind) if kind[0] != "diagvec" else ("dense",)
+    if trust_gate_names:
+        return _NAME_KINDS.get(str(getattr(node, "name", "")), ("dense",))
+    return ("dense",)
+
+
+# ---------------------------------------------------------------------------------------
+class CompiledCircuit:
+    """A plan plus its device-resident programs (uploaded once, reused every step)."""
+
+    def __init__(self, plan: Plan, ops: List[GateOp], device: torch.device) -> None:
+        self.plan = plan
+        self.ops = ops
+        self.device = device
+        chunks = [s.program for s in plan.steps if isinstance(s, PassStep)]
+        self.offsets: List[int] = []
+        off = 0
+        for c in chunks:
+            self.offsets.append(off)
+            off += len(c)
+        if chunks:
+            host = np.concatenate(chunks).astype(np.int32)
+            self.programs = torch.from_numpy(host).to(device)
+        else:
+            self.programs = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def run(self, state: torch.Tensor, gatebuf: torch.Tensor, batch: int = 1, gate_batch_stride: int = 0,
+            index_base: int = 0) -> None:  # fmt: skip
+        """Apply the circuit IN PLACE to `state` ([batch * 2^nbits] complex64 on the GPU)."""
+        _lib.require_cuda(state, "state")
+        _lib.require_cuda(gatebuf, "gate buffer")
+        nbits = self.plan.nbits
+        stream = _lib.stream_ptr()
+        sp = state.data_ptr()
+        gp = gatebuf.data_ptr()
+        pi = 0
+        for step in self.plan.steps:
+            if isinstance(step, PassStep):
+                prog_ptr = self.programs.data_ptr() + 4 * self.offsets[pi]
+                pi += 1
+                _lib.call("tcb_sv_run_pass", sp, nbits, batch, prog_ptr, len(step.program), step.tile_bits,
+                          step.low_bits, gp, gate_batch_stride, index_base, stream)  # fmt: skip
+            else:
+                g = step.gate
+                bp = _lib.int_array(step.bitpos)
+                mp = gp + 8 * g.mat_off
+                if g.is_diag:
+                    stride = 1 if g.kind[0] == "diagvec" else (1 << g.k) + 1
+                    _lib.call("tcb_sv_apply_diag", sp, nbits, batch, bp, g.k, mp, stride, gate_batch_stride,
+                              index_base, stream)  # fmt: skip
+                else:
+                    _lib.call("tcb_sv_apply_dense", sp, nbits, batch, bp, g.k, mp, gate_batch_stride, stream)
+
+
+_plan_cache: Dict[Any, CompiledCircuit] = {}
+plan_options: Dict[str, Any] = {"tile_bits": passplan.PASS_MAX_T, "low_bits": 4}
+
+
+def compile_circuit(nq: int, structure: Sequence[Tuple[Tuple[int, ...], Tuple[Any, ...], int]],
+                    device: torch.device, nbits_local: Optional[int] = None) -> CompiledCircuit:  # fmt: skip
+    """structure: per gate (qubits, kind, numel of its tensor). Cached by structure."""
+    key = (nq, nbits_local, tuple(structure), str(device), tuple(sorted(plan_options.items())))
+    cc = _plan_cache.get(key)
+    if cc is None:
+        ops: List[GateOp] = []
+        off = 0
+        for gi, (qubits, kind, numel) in enumerate(structure):
+            ops.append(GateOp(tuple(qubits), tuple(kind), off, gi))
+            off += numel
+        plan = passplan.compile_plan(ops, nq, nbits_local=nbits_local, **plan_options)
+        cc = CompiledCircuit(plan, ops, device)
+        if len(_plan_cache) > 256:
+            _plan_cache.clear()
+        _plan_cache[key] = cc
+    return cc
+
+
+def new_zero_state(nbits: int, batch: int, device: torch.device) -> torch.Tensor:
+    state = torch.empty(batch << nbits, dtype=torch.complex64, device=device)
+    _lib.require_cuda(state, "state")
+    _lib.call("tcb_sv_init_zero", state.data_ptr(), nbits, batch, _lib.stream_ptr())
+    return state
+
+
+def pick_device(tensors: Sequence[torch.Tensor]) -> torch.device:
+    for t in tensors:
+        if t.is_cuda:
+            return t.device
+    if torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    raise _lib.EngineError(
+        "no CUDA device: the B200 engine has no CPU fallback (the numpy oracle under oracle/ is test "
+        "infrastructure and is never used by the product path)"
+    )
+
+
+def build_gatebuf(tensors: Sequence[torch.Tensor], device: torch.device) -> torch.Tensor:
+    flat = []
+    for t in tensors:
+        if t.dtype != torch.complex64:
+            t = t.to(torch.complex64)
+        if t.device != device:
+            t = t.to(device)
+        flat.append(t.reshape(-1))
+    return torch.cat(flat) if flat else torch.zeros(1, dtype=torch.complex64, device=device)
+
+
+def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) -> torch.Tensor:
+    """Forward statevector for a circuit-shaped network; returns a [2]*n tensor."""
+    from . import autograd  # local import (autograd imports this module)
+
+    n, init_node, gates = extract_gate_stream(nodes, output_edge_order)
+    tensors = [g[0].tensor for g in gates]
+    device = pick_device(tensors + ([init_node.tensor] if init_node is not None else []))
+    structure = [(g[1], gate_kind(g[0], g[2]), int(g[0].tensor.numel())) for g in gates]
+    cc = compile_circuit(n, structure, device)
+    gatebuf = build_gatebuf(tensors, device)
+    init = None
+    if init_node is not None:
+        init = init_node.tensor.to(torch.complex64).to(device).reshape(-1)
+    state = autograd.evolve(cc, gatebuf, init)
+    return state.reshape([2] * n)
