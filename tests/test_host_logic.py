@@ -1,0 +1,307 @@
+"""CPU tier: the C-ABI library loads and exports every declared symbol; the pass planner's
+programs, executed by the kernel-logic emulator (the SAME pass_core.cuh the GPU compiles),
+reproduce the oracle; gate-stream extraction and contractor error behaviour match the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import tc_oracle
+from helpers import brickwork, build, oracle_state, qaoa, random_layers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from tensorcircuit_ng_b200 import _lib
+
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "tcb200.h")).read()
+    declared = set(re.findall(r"\b(tcb_[a-z0-9_]+)\s*\(", header))
+    declared.discard("tcb_contract_desc")
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/tcb200.h but not exported"
+        assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype"
+    assert lib.tcb_abi_version() == 1
+
+
+def test_no_cpu_fallback(built):
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200._lib import EngineError
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    c = tc.Circuit(3)
+    c.h(0)
+    with pytest.raises(EngineError, match="no CPU fallback"):
+        c.wavefunction()
+
+
+def _emu():
+    lib = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libpass_emu.so"))
+    return lib
+
+
+def _product_stream(n, ops):
+    """Build the product circuit on CPU tensors and extract (structure, gate buffer)."""
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import svengine
+
+    c = build(tc, n, ops)
+    nodes, d_edges = c._copy()
+    nq, init, gates = svengine.extract_gate_stream(nodes, d_edges)
+    assert nq == n and init is None
+    structure = [(g[1], svengine.gate_kind(g[0], g[2]), int(g[0].tensor.numel())) for g in gates]
+    buf = np.concatenate([g[0].tensor.reshape(-1).numpy() for g in gates]).astype(np.complex64)
+    return structure, buf
+
+
+def _run_emulated(n, structure, buf, **opts):
+    from tensorcircuit_ng_b200 import passplan
+
+    gops, off = [], 0
+    for gi, (qubits, kind, numel) in enumerate(structure):
+        gops.append(passplan.GateOp(tuple(qubits), tuple(kind), off, gi))
+        off += numel
+    plan = passplan.compile_plan(gops, n, **opts)
+    state = np.zeros(2**n, dtype=np.complex64)
+    state[0] = 1
+    emu = _emu()
+    for st in plan.steps:
+        if isinstance(st, passplan.PassStep):
+            prog = np.ascontiguousarray(st.program)
+            rc = emu.emu_run_pass(
+                state.ctypes.data_as(ctypes.c_void_p), n, ctypes.c_longlong(1),
+                prog.ctypes.data_as(ctypes.c_void_p), len(prog), st.tile_bits, st.low_bits,
+                buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(0), ctypes.c_ulonglong(0),
+            )  # fmt: skip
+            assert rc == 0
+        else:
+            g = st.gate
+            k = g.k
+            if g.is_diag:
+                d = buf[g.mat_off : g.mat_off + (2**k if g.kind[0] == "diagvec" else 4**k)]
+                if g.kind[0] != "diagvec":
+                    d = np.diag(d.reshape(2**k, 2**k))
+                m = np.diag(d).reshape([2] * (2 * k))
+            else:
+                m = buf[g.mat_off : g.mat_off + 4**k].reshape([2] * (2 * k))
+            psi = np.tensordot(m, state.reshape([2] * n), axes=[list(range(k, 2 * k)), list(g.qubits)])
+            state = np.ascontiguousarray(np.moveaxis(psi, list(range(k)), list(g.qubits))).reshape(-1)
+    return state, plan
+
+
+@pytest.mark.parametrize("n,depth,seed", [(4, 3, 0), (9, 3, 1), (10, 3, 2), (12, 4, 3), (14, 3, 4), (16, 2, 5)])
+def test_planner_and_kernel_logic_match_oracle(built, n, depth, seed):
+    ops = random_layers(n, depth, seed)
+    ref = oracle_state(n, ops)
+    structure, buf = _product_stream(n, ops)
+    out, plan = _run_emulated(n, structure, buf)
+    assert plan.n_gates == len(ops)
+    np.testing.assert_allclose(out, ref, atol=1e-5)
+
+
+@pytest.mark.parametrize("tile_bits,low_bits", [(10, 4), (11, 3), (12, 5), (13, 4)])
+def test_tile_geometries(built, tile_bits, low_bits):
+    n = 15
+    ops = random_layers(n, 2, 11)
+    ref = oracle_state(n, ops)
+    structure, buf = _product_stream(n, ops)
+    out, plan = _run_emulated(n, structure, buf, tile_bits=tile_bits, low_bits=low_bits)
+    np.testing.assert_allclose(out, ref, atol=1e-5)
+
+
+def test_config1_brickwork_plan(built):
+    """BASELINE.json config 1 (20-qubit brickwork, depth 10): plan fuses 295 gates into few passes."""
+    n = 20
+    ops = brickwork(n, 10)
+    structure, buf = _product_stream(n, ops)
+    out, plan = _run_emulated(n, structure, buf)
+    ref = oracle_state(n, ops)
+    np.testing.assert_allclose(out, ref, atol=1e-5)
+    assert plan.n_gates == 295
+    assert plan.n_passes <= 12
+
+
+def test_qaoa_plan_fusion(built):
+    """BASELINE.json config 3 at reduced width: every ZZ layer rides along a dense pass."""
+    n, p = 16, 3
+    ops, edges = qaoa(n, p)
+    structure, buf = _product_stream(n, ops)
+    assert all(kind == ("diag",) for (q, kind, _) in structure if len(q) == 2)
+    out, plan = _run_emulated(n, structure, buf)
+    ref = oracle_state(n, ops)
+    np.testing.assert_allclose(out, ref, atol=1e-5)
+    assert plan.n_passes <= 2 * p + 2
+
+
+def test_plan_is_deterministic_and_cached(built):
+    from tensorcircuit_ng_b200 import passplan
+
+    n = 14
+    structure, _ = _product_stream(n, random_layers(n, 3, 7))
+    progs = []
+    for _ in range(2):
+        gops, off = [], 0
+        for gi, (qubits, kind, numel) in enumerate(structure):
+            gops.append(passplan.GateOp(tuple(qubits), tuple(kind), off, gi))
+            off += numel
+        plan = passplan.compile_plan(gops, n)
+        progs.append([s.program.tobytes() for s in plan.steps if isinstance(s, passplan.PassStep)])
+    assert progs[0] == progs[1]
+
+
+def test_extract_rejects_non_circuit_networks(built):
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import svengine
+
+    c = tc.Circuit(3)
+    c.h(0)
+    c.cnot(0, 1)
+    nodes = c.amplitude_before("010")
+    with pytest.raises(svengine.NotCircuitShaped):
+        svengine.extract_gate_stream(nodes, [])
+    nodes = c.expectation_before([tc.gates.z(), [0]], reuse=False)
+    with pytest.raises(svengine.NotCircuitShaped):
+        svengine.extract_gate_stream(nodes, [])
+
+
+def test_contractor_edge_order_errors(built):
+    """Same ValueErrors as the reference (tensorcircuit/cons.py:886-896) — raised before any GPU work."""
+    import tensorcircuit_ng_b200 as tc
+
+    c = tc.Circuit(2)
+    c.h(0)
+    nodes, d_edges = c._copy()
+    with pytest.raises(ValueError, match="more than one remaining edge"):
+        tc.cons.contractor(nodes)
+    nodes, d_edges = c._copy()
+    with pytest.raises(ValueError, match="output edges are not equal"):
+        tc.cons.contractor(nodes, output_edge_order=d_edges[:1])
+    with pytest.raises(ValueError, match="duplicate qubits"):
+        c.cnot(1, 1)
+    with pytest.raises(ValueError, match="Cannot measure two operators in one index"):
+        c.expectation_before([tc.gates.z(), [0]], [tc.gates.x(), [0]], reuse=False)
+
+
+def test_node_capture_counts(built):
+    """tests/test_miscs.py:307-324 of the reference: 7 and 9 nodes."""
+    import tensorcircuit_ng_b200 as tc
+
+    with tc.cons.runtime_nodes_capture() as captured:
+        c = tc.Circuit(3)
+        c.h(0)
+        c.amplitude("010")
+    assert len(captured["nodes"]) == 7
+
+    @tc.cons.function_nodes_capture
+    def exp(theta):
+        c = tc.Circuit(3)
+        c.h(0)
+        return c.expectation_ps(z=[-3], reuse=False)
+
+    assert len(exp(0.3)) == 9
+
+
+def test_contractor_scoping(built):
+    """tests/test_backends.py:1342-1358 of the reference: with-level and function-level contractor scoping."""
+    import tensorcircuit_ng_b200 as tc
+
+    base = tc.cons.contractor
+    with tc.runtime_contractor("plain") as cf:
+        assert tc.cons.contractor is cf and tc.circuit.contractor is cf
+    assert tc.cons.contractor is base and tc.circuit.contractor is base
+
+    @tc.set_function_contractor("plain")
+    def f():
+        return tc.circuit.contractor
+
+    assert f() is tc.cons.plain_contractor
+    assert tc.circuit.contractor is base
+
+
+def test_gate_tensors_match_oracle(built):
+    """Every gate factory of the product equals the oracle's (reference gates.py) tensor."""
+    import tensorcircuit_ng_b200 as tc
+    from tc_oracle import gates as og
+
+    pg = tc.gates
+    for name in ["i", "x", "y", "z", "h", "s", "t", "sd", "td", "wroot", "cnot", "cz", "cy", "swap", "toffoli",
+                 "fredkin", "ox", "oy", "oz"]:  # fmt: skip
+        np.testing.assert_allclose(getattr(pg, name)().tensor.numpy(), getattr(og, name)().tensor, atol=1e-7, err_msg=name)
+    th = 0.37
+    for name in ["rx", "ry", "rz", "phase", "iswap", "rzz", "rxx", "ryy", "crx", "cry", "crz", "cphase", "orx", "ory", "orz"]:
+        a = getattr(pg, name + "_gate")(theta=th).tensor.numpy()
+        b = getattr(og, name + "_gate")(theta=th).tensor
+        np.testing.assert_allclose(a, b, atol=1e-6, err_msg=name)
+    np.testing.assert_allclose(pg.u_gate(theta=0.3, phi=0.2, lbd=-0.4).tensor.numpy(), og.u_gate(0.3, 0.2, -0.4).tensor, atol=1e-6)
+    np.testing.assert_allclose(pg.r_gate(theta=0.3, alpha=0.2, phi=-0.4).tensor.numpy(), og.r_gate(0.3, 0.2, -0.4).tensor, atol=1e-6)
+    np.testing.assert_allclose(pg.cr_gate(theta=0.3, alpha=0.2, phi=-0.4).tensor.numpy(), og.cr_gate(0.3, 0.2, -0.4).tensor, atol=1e-6)
+    np.testing.assert_allclose(pg.cu_gate(theta=0.3, phi=0.2, lbd=-0.4).tensor.numpy(), og.cu_gate(theta=0.3, phi=0.2, lbd=-0.4).tensor, atol=1e-6)
+    np.testing.assert_allclose(pg.exp1_gate(og._xx_matrix, 0.3).tensor.numpy(), og.exp1_gate(og._xx_matrix, 0.3).tensor, atol=1e-6)
+    np.testing.assert_allclose(pg.exp_gate(np.diag([1.0, -1, -1, 1]), 0.3).tensor.numpy(), og.exp_gate(np.diag([1.0, -1, -1, 1]), 0.3).tensor, atol=5e-6)  # complex64 matrix_exp
+
+
+def test_gate_kind_hints_are_sound(built):
+    """A `diag` / `ctrl` hint must be structurally true for the tensor it is attached to."""
+    import tensorcircuit_ng_b200 as tc
+
+    pg = tc.gates
+    th = 1.234
+    gates = [getattr(pg, n)() for n in ["i", "x", "y", "z", "h", "s", "t", "sd", "td", "cnot", "cz", "cy", "swap",
+                                         "toffoli", "fredkin", "ox", "oy", "oz"]]  # fmt: skip
+    gates += [getattr(pg, n + "_gate")(theta=th) for n in ["rx", "ry", "rz", "phase", "rzz", "rxx", "crx", "cry", "crz",
+                                                            "cphase", "orx", "ory", "orz", "iswap"]]  # fmt: skip
+    gates += [pg.cr_gate(theta=th, alpha=0.3, phi=0.2), pg.cu_gate(theta=th, phi=0.3, lbd=0.1),
+              pg.exp1_gate(pg._zz_matrix, th), pg.exp1_gate(pg._xx_matrix, th), pg.any_gate(np.diag([1, 1j])),
+              pg.any_gate(np.array([[0, 1], [1, 0]]))]  # fmt: skip
+    for g in gates:
+        kind = g._b200_kind
+        d = int(round(np.sqrt(g.tensor.numel())))
+        m = g.tensor.reshape(d, d).numpy()
+        if kind[0] == "diag":
+            assert np.allclose(m, np.diag(np.diag(m))), g.name
+        elif kind[0] == "ctrl":
+            nctrl, pol = kind[1], kind[2]
+            polval = 0
+            for i in range(nctrl):
+                polval = (polval << 1) | ((pol >> i) & 1)
+            rest = m.copy()
+            rest[2 * polval : 2 * polval + 2, 2 * polval : 2 * polval + 2] = np.eye(2)
+            assert np.allclose(rest, np.eye(d)), g.name
+
+
+def test_planner_greedy_path_is_valid_and_competitive(built):
+    from tc_oracle import cons as ocons
+    from tc_oracle import paths
+    from tensorcircuit_ng_b200 import planner
+
+    n, d = 10, 4
+    ops = [("h", [i], {}) for i in range(n)]
+    from tc_oracle import gates as og
+
+    for j in range(d):
+        ops += [("exp1", [i, i + 1], {"unitary": og._zz_matrix, "theta": 1.0}) for i in range(n - 1)]
+        ops += [("rx", [i], {"theta": 1.0}) for i in range(n)]
+    c = build(tc_oracle, n, ops)
+    nodes, _ = c._copy()
+    (inp, out, sd), sorted_nodes = ocons.get_tn_info(nodes)
+    path = planner.greedy(inp, out, sd)
+    res = ocons.contract_path_einsum([x.tensor for x in sorted_nodes], ["".join(i) for i in inp], "".join(out), path)
+    np.testing.assert_allclose(res.reshape(-1), c.wavefunction(), atol=1e-5)
+    ours = planner.path_stats(inp, out, sd, path)
+    ref = paths.path_cost(inp, out, sd, paths.greedy(inp, out, sd))
+    assert ours["flops"] <= 1.5 * ref["flops"]
+    # sliced search honours the size bound on a scalar network
+    c2 = build(tc_oracle, n, ops)
+    nodes = c2.amplitude_before("0" * n)
+    (inp, out, sd), _ = ocons.get_tn_info(nodes)
+    td = planner.search(inp, out, sd, target_size=2**4)
+    st = planner.path_stats(inp, out, sd, td["path"], list(td["sliced_inds"]))
+    assert st["size"] <= 2**4 and len(td["sliced_inds"]) >= 1
+    vals = planner.slice_values(5, list(td["sliced_inds"]), sd)
+    assert set(vals) == set(td["sliced_inds"])
