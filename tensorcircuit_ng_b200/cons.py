@@ -217,15 +217,18 @@ def _recognize_expectation(nodes: Sequence[Any]):
     """Returns (ket tensor, n, [(op node, qubit axes)]) for <psi|ops|psi>, else None."""
     if len(nodes) < 2 or _subgraph_dangling(nodes):
         return None
-    big = [x for x in nodes if not _is_copynode(x)]
-    if len(big) != len(nodes):
+    if any(_is_copynode(x) for x in nodes):
         return None
-    ranks = sorted(((x.get_rank(), i) for i, x in enumerate(nodes)), reverse=True)
-    a, b = nodes[ranks[0][1]], nodes[ranks[1][1]]
-    n = a.get_rank()
-    if n < 1 or b.get_rank() != n or not _same_storage_conj(a.tensor, b.tensor):
+    # the bra is the lazily conjugated view of the ket's storage (tn.Node.copy(conjugate=True))
+    bra = next((x for x in nodes if x.tensor.is_conj()), None)
+    if bra is None:
         return None
-    ket, bra = (a, b) if b.tensor.is_conj() else (b, a)
+    ket = next((x for x in nodes if x is not bra and _same_storage_conj(x.tensor, bra.tensor)), None)
+    if ket is None:
+        return None
+    n = ket.get_rank()
+    if n < 1:
+        return None
     ops = [x for x in nodes if x is not ket and x is not bra]
     covered: Set[int] = set()
     found = []

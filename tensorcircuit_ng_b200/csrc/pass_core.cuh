@@ -109,31 +109,28 @@ TCB_DEV uint64_t tile_base(uint64_t tile, const int32_t* hdr) {
 }
 
 // ---- register sub-pass -------------------------------------------------------------
-template <int R, int J>
-TCB_DEV void apply_1q(float2 (&a)[1 << R], float2 m00, float2 m01, float2 m10, float2 m11) {
+// 2x2 complex matrix on register bit J of the 2^R amplitudes held by this thread.  Controls that
+// live in registers are given as (cmask, cwant) over the register index (0,0 = uncontrolled); the
+// test is on compile-time indices, so uncontrolled gates pay nothing for it after unrolling only
+// when the compiler can see cmask == 0 — hence the two instantiations below.
+template <int R, int J, bool CTRL>
+TCB_DEV void apply_1q(float2 (&a)[1 << R], float2 m00, float2 m01, float2 m10, float2 m11,
+                      int cmask, int cwant) {
   TCB_UNROLL
   for (int p = 0; p < (1 << (R - 1)); ++p) {
     const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
     const int i1 = i0 | (1 << J);
     const float2 x = a[i0], y = a[i1];
-    a[i0] = cfma(m01, y, cmul(m00, x));
-    a[i1] = cfma(m11, y, cmul(m10, x));
-  }
-}
-
-// controlled variant: register-resident controls are given as (mask, want) over the
-// register index; pairs whose index does not match keep their value.
-template <int R, int J>
-TCB_DEV void apply_c1q(float2 (&a)[1 << R], float2 m00, float2 m01, float2 m10, float2 m11,
-                       int cmask, int cwant) {
-  TCB_UNROLL
-  for (int p = 0; p < (1 << (R - 1)); ++p) {
-    const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
-    const int i1 = i0 | (1 << J);
-    const bool on = ((i0 & cmask) == cwant);
-    const float2 x = a[i0], y = a[i1];
-    a[i0] = csel(on, cfma(m01, y, cmul(m00, x)), x);
-    a[i1] = csel(on, cfma(m11, y, cmul(m10, x)), y);
+    const float2 b0 = cfma(m01, y, cmul(m00, x));
+    const float2 b1 = cfma(m11, y, cmul(m10, x));
+    if (CTRL) {
+      const bool on = ((i0 & cmask) == cwant);
+      a[i0] = csel(on, b0, x);
+      a[i1] = csel(on, b1, y);
+    } else {
+      a[i0] = b0;
+      a[i1] = b1;
+    }
   }
 }
 
@@ -144,20 +141,14 @@ TCB_DEV void apply_bitdiag(float2 (&a)[1 << R], float2 u0, float2 u1) {
   for (int i = 0; i < (1 << R); ++i) a[i] = cmul(a[i], ((i >> J) & 1) ? u1 : u0);
 }
 
-// diagonal on two register bits J (static) and k (runtime): d[xj][xk]
+// diagonal on two register bits J (static, first gate qubit) and k (runtime): d[xj][xk]
 template <int R, int J>
 TCB_DEV void apply_pairdiag(float2 (&a)[1 << R], int k, float2 d00, float2 d01, float2 d10,
-                            float2 d11, bool j_is_first) {
+                            float2 d11) {
   TCB_UNROLL
   for (int i = 0; i < (1 << R); ++i) {
-    const int xj = (i >> J) & 1;
     const bool xk = (i >> k) & 1;
-    // d[first][second]
-    float2 f;
-    if (j_is_first)
-      f = xj ? csel(xk, d11, d10) : csel(xk, d01, d00);
-    else
-      f = xj ? csel(xk, d11, d01) : csel(xk, d10, d00);
+    const float2 f = ((i >> J) & 1) ? csel(xk, d11, d10) : csel(xk, d01, d00);
     a[i] = cmul(a[i], f);
   }
 }
@@ -180,34 +171,25 @@ struct RegState {
     default: break;                                                             \
   }
 
-// apply (and clear) the pending diagonal factor of register bit j, folding in c
+// take (and clear) the pending diagonal factor of register bit j, with c folded in
 template <int R>
-TCB_DEV void flush_bit(RegState<R>& s, int j) {
-  if (!((s.dirty >> j) & 1u)) return;
-  TCB_SWITCH_J(R, j, {
-    float2 f0 = s.u0[J], f1 = s.u1[J];
-    if (s.dirty >> 31) {
-      f0 = cmul(f0, s.c);
-      f1 = cmul(f1, s.c);
-      s.c = make_float2(1.f, 0.f);
-      s.dirty &= 0x7fffffffu;
-    }
-    apply_bitdiag<R, J>(s.a, f0, f1);
-    s.u0[J] = make_float2(1.f, 0.f);
-    s.u1[J] = make_float2(1.f, 0.f);
-  })
-  s.dirty &= ~(1u << j);
-}
-
-template <int R>
-TCB_DEV void flush_all(RegState<R>& s) {
-  TCB_UNROLL
-  for (int j = 0; j < R; ++j) flush_bit<R>(s, j);
+TCB_DEV void take_pending(RegState<R>& s, int j, float2& f0, float2& f1) {
+  f0 = make_float2(1.f, 0.f);
+  f1 = make_float2(1.f, 0.f);
+  if ((s.dirty >> j) & 1u) {
+    TCB_SWITCH_J(R, j, {
+      f0 = s.u0[J];
+      f1 = s.u1[J];
+      s.u0[J] = make_float2(1.f, 0.f);
+      s.u1[J] = make_float2(1.f, 0.f);
+    })
+    s.dirty &= ~(1u << j);
+  }
   if (s.dirty >> 31) {
-    TCB_UNROLL
-    for (int i = 0; i < (1 << R); ++i) s.a[i] = cmul(s.a[i], s.c);
+    f0 = cmul(f0, s.c);
+    f1 = cmul(f1, s.c);
     s.c = make_float2(1.f, 0.f);
-    s.dirty = 0;
+    s.dirty &= 0x7fffffffu;
   }
 }
 
@@ -220,29 +202,48 @@ TCB_DEV void mul_u(RegState<R>& s, int j, float2 d0, float2 d1) {
   s.dirty |= (1u << j);
 }
 
+// XOR-fold of the bits above the low nibble (linear over GF(2)): swz(t) = (t & ~15) | ((t ^ fold_hi(t)) & 15)
+TCB_DEV int fold_hi(int t) { return ((t >> 4) ^ (t >> 8) ^ (t >> 12)) & 15; }
+
 // one thread's share of a register sub-pass.
 //   tile : shared-memory tile (swizzled), sp : sub-pass header, gates : gate buffer of this
 //   batch element, group : which 2^R-amplitude group this thread owns, cta_base : CTA-constant
-//   flat-index bits (already OR-ed with index_base)
+//   flat-index bits (already OR-ed with index_base), hi_flat : optional table of tile_to_flat(h<<L)
 template <int R>
 TCB_DEV void run_reg_subpass(float2* tile, const int32_t* hdr, const int32_t* sp,
-                             const float2* __restrict__ gates, int group, uint64_t cta_base) {
+                             const float2* __restrict__ gates, int group, uint64_t cta_base,
+                             const uint64_t* hi_flat = nullptr) {
   const int T = hdr[H_T];
   int tbase = 0;
   for (int b = 0; b < T - R; ++b) tbase |= ((group >> b) & 1) << sp[S_GRPBITS + b];
-  int rb[R];
+  uint64_t gidx;
+  if (hi_flat != nullptr) {
+    const int L = hdr[H_L];
+    gidx = cta_base | hi_flat[tbase >> L] | (uint64_t)(tbase & ((1 << L) - 1));
+  } else {
+    gidx = cta_base | tile_to_flat(tbase, hdr);
+  }
+
+  // shared-memory address of amplitude i:  tbase and the register offsets have disjoint bits, and
+  // the swizzle is linear, so   swz(tbase | off_i) = base_hi | off_i(hi part) | (low ^ fold) & 15
+  int rb[R];   // register bit j -> tile bit mask
+  int rsw[R];  // its contribution to the swizzled address: mask with the low nibble replaced by the fold
   TCB_UNROLL
-  for (int j = 0; j < R; ++j) rb[j] = 1 << sp[S_REGBITS + j];
-  const uint64_t gidx = cta_base | tile_to_flat(tbase, hdr);
+  for (int j = 0; j < R; ++j) {
+    const int m = 1 << sp[S_REGBITS + j];
+    rb[j] = m;
+    rsw[j] = (m & ~15) | ((m ^ fold_hi(m)) & 15);
+  }
+  const int sbase = (tbase & ~15) | ((tbase ^ fold_hi(tbase)) & 15);
 
   RegState<R> s;
   TCB_UNROLL
   for (int i = 0; i < (1 << R); ++i) {
-    int off = 0;
+    int ad = sbase;
     TCB_UNROLL
     for (int j = 0; j < R; ++j)
-      if ((i >> j) & 1) off |= rb[j];
-    s.a[i] = tile[swz(tbase | off)];
+      if ((i >> j) & 1) ad ^= rsw[j];
+    s.a[i] = tile[ad];
   }
   TCB_UNROLL
   for (int j = 0; j < R; ++j) {
@@ -258,12 +259,63 @@ TCB_DEV void run_reg_subpass(float2* tile, const int32_t* hdr, const int32_t* sp
   for (int o = 0; o < nops; ++o, op += OP_WORDS) {
     const int code = op[O_CODE];
     const float2* m = gates + op[O_MAT];
-    if (code == OP_1Q) {
-      const int j = op[O_A];
+    if (code == OP_1Q || code == OP_C1Q) {
+      // dense (optionally controlled) 2x2 on register bit j.  Pending diagonal factors on that bit
+      // (and the thread-constant factor) are folded into the matrix columns:  M' = M diag(f0, f1).
       const int rs = op[O_AUX1];
-      const float2 m00 = m[0], m01 = m[1], m10 = m[rs], m11 = m[rs + 1];
-      flush_bit<R>(s, j);
-      TCB_SWITCH_J(R, j, (apply_1q<R, J>(s.a, m00, m01, m10, m11)))
+      int j, cmask = 0, cwant = 0;
+      bool active = true;
+      if (code == OP_1Q) {
+        j = op[O_A];
+      } else {
+        j = op[O_B];
+        const int pol = op[O_AUX0];
+        const int qc[2] = {op[O_A], op[O_AUX2]};
+        TCB_UNROLL
+        for (int c = 0; c < 2; ++c) {
+          const int q = qc[c];
+          if (q < 0) continue;
+          const int want = (pol >> c) & 1;
+          if (q >= QREF_BIT) {
+            active = active && ((int)((gidx >> (q - QREF_BIT)) & 1ull) == want);
+          } else {
+            cmask |= 1 << q;
+            cwant |= want << q;
+          }
+        }
+      }
+      float2 m00 = make_float2(1.f, 0.f), m01 = make_float2(0.f, 0.f), m10 = m01, m11 = m00;
+      if (active) {
+        m00 = m[0];
+        m01 = m[1];
+        m10 = m[rs];
+        m11 = m[rs + 1];
+      }
+      if (cmask == 0) {
+        // (for an inactive thread-level control the matrix is the identity, so this still applies
+        //  the pending diagonal — correct, and keeps one code path)
+        const bool pend = ((s.dirty >> j) & 1u) || (s.dirty >> 31);
+        if (pend || active) {
+          float2 f0, f1;
+          take_pending<R>(s, j, f0, f1);
+          m00 = cmul(m00, f0);
+          m10 = cmul(m10, f0);
+          m01 = cmul(m01, f1);
+          m11 = cmul(m11, f1);
+          TCB_SWITCH_J(R, j, (apply_1q<R, J, false>(s.a, m00, m01, m10, m11, 0, 0)))
+        }
+      } else {
+        // register-resident controls: the pending factor of bit j applies to every pair, the gate
+        // only to the selected ones -> flush the factor first, then apply the masked gate
+        if (((s.dirty >> j) & 1u) || (s.dirty >> 31)) {
+          float2 f0, f1;
+          take_pending<R>(s, j, f0, f1);
+          TCB_SWITCH_J(R, j, (apply_bitdiag<R, J>(s.a, f0, f1)))
+        }
+        if (active) {
+          TCB_SWITCH_J(R, j, (apply_1q<R, J, true>(s.a, m00, m01, m10, m11, cmask, cwant)))
+        }
+      }
     } else if (code == OP_DIAG1) {
       const int q = op[O_A];
       const int st = op[O_AUX1];
@@ -278,62 +330,48 @@ TCB_DEV void run_reg_subpass(float2* tile, const int32_t* hdr, const int32_t* sp
     } else if (code == OP_DIAG2) {
       const int qa = op[O_A], qb = op[O_B];
       const int st = op[O_AUX1];
-      const float2 d00 = m[0], d01 = m[st], d10 = m[2 * st], d11 = m[3 * st];
       const bool a_bit = qa >= QREF_BIT, b_bit = qb >= QREF_BIT;
-      if (a_bit && b_bit) {
-        const bool xa = (gidx >> (qa - QREF_BIT)) & 1ull;
-        const bool xb = (gidx >> (qb - QREF_BIT)) & 1ull;
-        s.c = cmul(s.c, xa ? (xb ? d11 : d10) : (xb ? d01 : d00));
-        s.dirty |= 0x80000000u;
-      } else if (!a_bit && b_bit) {
-        const bool xb = (gidx >> (qb - QREF_BIT)) & 1ull;
-        mul_u<R>(s, qa, xb ? d01 : d00, xb ? d11 : d10);
-      } else if (a_bit && !b_bit) {
-        const bool xa = (gidx >> (qa - QREF_BIT)) & 1ull;
-        mul_u<R>(s, qb, xa ? d10 : d00, xa ? d11 : d01);
+      if (a_bit || b_bit) {
+        // resolve the thread-constant qubit(s): the gate collapses to a 1q diagonal or a scalar
+        const bool xa = a_bit ? (bool)((gidx >> (qa - QREF_BIT)) & 1ull) : false;
+        const bool xb = b_bit ? (bool)((gidx >> (qb - QREF_BIT)) & 1ull) : false;
+        if (a_bit && b_bit) {
+          s.c = cmul(s.c, m[(2 * (int)xa + (int)xb) * st]);
+          s.dirty |= 0x80000000u;
+        } else if (b_bit) {
+          mul_u<R>(s, qa, m[(int)xb * st], m[(2 + (int)xb) * st]);
+        } else {
+          mul_u<R>(s, qb, m[(2 * (int)xa) * st], m[(2 * (int)xa + 1) * st]);
+        }
       } else {
         // both register bits: apply directly (commutes with every pending diagonal factor)
-        TCB_SWITCH_J(R, qa, (apply_pairdiag<R, J>(s.a, qb, d00, d01, d10, d11, true)))
-      }
-    } else if (code == OP_C1Q) {
-      const int j = op[O_B];
-      const int rs = op[O_AUX1];
-      const int pol = op[O_AUX0];
-      const int qc[2] = {op[O_A], op[O_AUX2]};
-      bool active = true;
-      int cmask = 0, cwant = 0;
-      TCB_UNROLL
-      for (int c = 0; c < 2; ++c) {
-        const int q = qc[c];
-        if (q < 0) continue;
-        const int want = (pol >> c) & 1;
-        if (q >= QREF_BIT) {
-          active = active && ((int)((gidx >> (q - QREF_BIT)) & 1ull) == want);
-        } else {
-          cmask |= 1 << q;
-          cwant |= want << q;
-        }
-      }
-      flush_bit<R>(s, j);
-      if (active) {
-        const float2 m00 = m[0], m01 = m[1], m10 = m[rs], m11 = m[rs + 1];
-        if (cmask == 0) {
-          TCB_SWITCH_J(R, j, (apply_1q<R, J>(s.a, m00, m01, m10, m11)))
-        } else {
-          TCB_SWITCH_J(R, j, (apply_c1q<R, J>(s.a, m00, m01, m10, m11, cmask, cwant)))
-        }
+        const float2 d00 = m[0], d01 = m[st], d10 = m[2 * st], d11 = m[3 * st];
+        TCB_SWITCH_J(R, qa, (apply_pairdiag<R, J>(s.a, qb, d00, d01, d10, d11)))
       }
     }
   }
-  flush_all<R>(s);
+  // flush what is still pending
+  TCB_NOUNROLL
+  for (int j = 0; j < R; ++j) {
+    if ((s.dirty >> j) & 1u) {
+      float2 f0, f1;
+      take_pending<R>(s, j, f0, f1);
+      TCB_SWITCH_J(R, j, (apply_bitdiag<R, J>(s.a, f0, f1)))
+    }
+  }
+  if (s.dirty >> 31) {
+    float2 f0, f1;
+    take_pending<R>(s, 0, f0, f1);
+    apply_bitdiag<R, 0>(s.a, f0, f1);
+  }
 
   TCB_UNROLL
   for (int i = 0; i < (1 << R); ++i) {
-    int off = 0;
+    int ad = sbase;
     TCB_UNROLL
     for (int j = 0; j < R; ++j)
-      if ((i >> j) & 1) off |= rb[j];
-    tile[swz(tbase | off)] = s.a[i];
+      if ((i >> j) & 1) ad ^= rsw[j];
+    tile[ad] = s.a[i];
   }
 }
 

@@ -72,7 +72,7 @@ pass_kernel(const float2* src, float2* dst, int nbits, const int32_t* __restrict
     if (sp[S_KIND] == SUB_REG) {
       const int ngroups = 1 << (T - R);
       for (int g = tid; g < ngroups; g += PASS_THREADS)
-        run_reg_subpass<R>(tile, hdr, sp, gates, g, cta_base);
+        run_reg_subpass<R>(tile, hdr, sp, gates, g, cta_base, hi_flat);
     } else {
       run_smem_dense(tile, hdr, sp, gates, tid, PASS_THREADS);
     }

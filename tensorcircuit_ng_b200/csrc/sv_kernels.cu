@@ -166,57 +166,75 @@ int launch_diag(void* state, int nbits, int64_t batch, const int* bitpos, int k,
 
 // ---------------------------------------------------------------------------------
 // Z-string expectations: one read of the state for all terms.
+//
+// <Z_S> = sum_x (-1)^{popc(x & m)} |psi_x|^2 is a Walsh-Hadamard coefficient of the probability
+// vector.  Each thread holds 32 probabilities whose indices differ in 5 known bits (bit 0 and
+// bits 9..12 of x); one in-register WHT (80 adds) turns them into the 32 possible signed sums,
+// so every term costs ONE coefficient lookup + the sign of the remaining bits per 32 amplitudes
+// instead of 32 sign evaluations.  Warp-shuffle reduction per term, double accumulation.
 constexpr int EZ_THREADS = 256;
-constexpr int EZ_VEC = 4;  // float4 loads per thread per iteration (8 amplitudes)
-constexpr int EZ_MAX_TERMS = 512;
+constexpr int EZ_VEC = 16;  // float4 loads per thread per iteration (32 amplitudes)
+constexpr int EZ_MAX_TERMS = 1024;
 
 __global__ void __launch_bounds__(EZ_THREADS)
 expect_z_kernel(const float4* __restrict__ state, uint64_t nvec_per_state,
                 const unsigned long long* __restrict__ zmasks, int nterms,
                 unsigned long long index_base, double* out) {
-  extern __shared__ double acc[];  // [warps][nterms]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) unsigned char ez_smem[];
+  float* coef = reinterpret_cast<float*>(ez_smem);                               // [32][EZ_THREADS]
+  double* acc = reinterpret_cast<double*>(ez_smem + 32 * EZ_THREADS * sizeof(float));  // [warps][nterms]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarps = EZ_THREADS / 32;
-  for (int e = threadIdx.x; e < nwarps * nterms; e += EZ_THREADS) acc[e] = 0.0;
+  for (int e = tid; e < nwarps * nterms; e += EZ_THREADS) acc[e] = 0.0;
   __syncthreads();
   const unsigned b = blockIdx.y;
   const float4* st = state + (size_t)b * nvec_per_state;
   double* my = acc + warp * nterms;
   const uint64_t chunk = (uint64_t)EZ_THREADS * EZ_VEC;
+  // group bits of x: bit 0 (pair inside a float4) and bits 9..12 (u); everything else is "rest"
   for (uint64_t v0 = (uint64_t)blockIdx.x * chunk; v0 < nvec_per_state;
        v0 += (uint64_t)gridDim.x * chunk) {
     float p[2 * EZ_VEC];
-    unsigned long long x[EZ_VEC];
 #pragma unroll
     for (int u = 0; u < EZ_VEC; ++u) {
-      const uint64_t v = v0 + (uint64_t)u * EZ_THREADS + threadIdx.x;
+      const uint64_t v = v0 + (uint64_t)u * EZ_THREADS + tid;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (v < nvec_per_state) a = ldg_stream(st + v);
       p[2 * u] = a.x * a.x + a.y * a.y;
       p[2 * u + 1] = a.z * a.z + a.w * a.w;
-      x[u] = (v << 1) | index_base;
     }
+    // in-register Walsh-Hadamard transform over the 5 group bits (w = e | u << 1)
+#pragma unroll
+    for (int sft = 0; sft < 5; ++sft) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (!((i >> sft) & 1)) {
+          const float x = p[i], y = p[i | (1 << sft)];
+          p[i] = x + y;
+          p[i | (1 << sft)] = x - y;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) coef[i * EZ_THREADS + tid] = p[i];
+    // (each thread only reads back its own column: no barrier needed)
+    const unsigned long long xrest = ((v0 + (uint64_t)tid) << 1) | index_base;
     for (int t = 0; t < nterms; ++t) {
       const unsigned long long m = zmasks[t];
-      const bool m0 = m & 1ull;  // the pair's second element differs in bit 0 only
-      float s = 0.f;
+      const int c = (int)(m & 1ull) | (int)(((m >> 9) & 15ull) << 1);
+      float val = coef[c * EZ_THREADS + tid];
+      // xrest has zeros at the 5 group bits, so they are not counted twice
+      if (__popcll(xrest & m) & 1) val = -val;
 #pragma unroll
-      for (int u = 0; u < EZ_VEC; ++u) {
-        const bool odd = __popcll(x[u] & m) & 1;
-        const float s0 = odd ? -p[2 * u] : p[2 * u];
-        const float s1 = (odd != m0) ? -p[2 * u + 1] : p[2 * u + 1];
-        s += s0 + s1;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) my[t] += (double)s;
+      for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+      if (lane == 0) my[t] += (double)val;
     }
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < nterms; t += EZ_THREADS) {
-    double s = 0.0;
-    for (int w = 0; w < nwarps; ++w) s += acc[w * nterms + t];
-    atomicAdd(out + (size_t)b * nterms + t, s);
+  for (int t = tid; t < nterms; t += EZ_THREADS) {
+    double sum = 0.0;
+    for (int w = 0; w < nwarps; ++w) sum += acc[w * nterms + t];
+    atomicAdd(out + (size_t)b * nterms + t, sum);
   }
 }
 
@@ -225,13 +243,20 @@ int launch_expect_z(const void* state, int nbits, int64_t batch, const uint64_t*
   TCB_REQUIRE(nterms >= 1 && nterms <= EZ_MAX_TERMS, "tcb_sv_expect_z: nterms=%d out of range", nterms);
   TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_expect_z: nbits=%d", nbits);
   TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_expect_z: batch=%lld", (long long)batch);
+  TCB_REQUIRE((index_base & ((1ull << nbits) - 1ull)) == 0, "tcb_sv_expect_z: index_base overlaps local bits");
   const uint64_t nvec = 1ull << (nbits - 1);
   const uint64_t chunk = (uint64_t)EZ_THREADS * EZ_VEC;
   uint64_t gx = (nvec + chunk - 1) / chunk;
-  const uint64_t cap = (uint64_t)sm_count() * 8;
+  const uint64_t cap = (uint64_t)sm_count() * 4;
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, (unsigned)batch);
-  const size_t smem = sizeof(double) * (EZ_THREADS / 32) * nterms;
+  const size_t smem = 32 * EZ_THREADS * sizeof(float) + sizeof(double) * (EZ_THREADS / 32) * nterms;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TCB_CHECK_CUDA(cudaFuncSetAttribute(expect_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        100 * 1024));
+    attr_set = true;
+  }
   expect_z_kernel<<<grid, EZ_THREADS, smem, stream>>>(
       reinterpret_cast<const float4*>(state), nvec,
       reinterpret_cast<const unsigned long long*>(zmasks), nterms, (unsigned long long)index_base, out);

@@ -93,8 +93,8 @@ def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any]):
                 node, axis = _other_end(prev, node, 0)
                 continue
             if _is_input_node(node):
-                if node.get_rank() == 1:
-                    n_zero_inputs += 1
+                if node.get_rank() == 1 and str(getattr(node, "name", "")).startswith("qb-"):
+                    n_zero_inputs += 1  # |0> leaf of all_zero_nodes (basecircuit.py:52-66)
                 else:
                     if init_node is not None and init_node is not node:
                         raise NotCircuitShaped("several multi-leg input nodes")
