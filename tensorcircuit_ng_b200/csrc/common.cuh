@@ -34,9 +34,10 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return r;
 }
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) {
+  // (no "memory" clobber: callers never read the stored location again before a barrier, and a
+  //  clobber would serialise the independent LDS -> STG chains of the streaming loops)
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
-               "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
+               "f"(v.y), "f"(v.z), "f"(v.w));
 }
 
 // insert a zero bit at position p of x

@@ -32,18 +32,26 @@ from typing import Any, Dict, List, Optional, Sequence, Set, Tuple
 import numpy as np
 
 # ---- word layout: keep in sync with csrc/pass_core.cuh -------------------------------
-PASS_MAGIC = 0x7CB20001
+PASS_MAGIC = 0x7CB20003
 PASS_MAX_T = 13
-PASS_R = 5
-PASS_MAX_WORDS = 3072
-H_MAGIC, H_T, H_L, H_NSUB, H_WORDS, H_NNONTILE, H_R = 0, 1, 2, 3, 4, 5, 6
+PASS_R = 4
+PASS_MAX_WORDS = 6144
+H_MAGIC, H_T, H_L, H_NSUB, H_WORDS, H_NNONTILE, H_R, H_NFILL = 0, 1, 2, 3, 4, 5, 6, 7
+H_NPOOL, H_POOLSIZE, H_NFILL_STATIC = 64, 65, 66
+PASS_MAX_POOL = 1536
 H_TILEPOS, H_NONTILEPOS, HDR_WORDS = 8, 24, 80
-S_NOPS, S_KIND, S_REGBITS, S_GRPBITS, S_WORDS, SUB_HDR_WORDS = 0, 1, 2, 10, 22, 24
+S_NROUNDS, S_KIND, S_REGBITS, S_GRPBITS, S_WORDS, SUB_HDR_WORDS = 0, 1, 2, 10, 22, 24
 SUB_REG, SUB_SMEM_DENSE = 0, 1
-OP_WORDS = 8
-OP_1Q, OP_C1Q, OP_DIAG1, OP_DIAG2, OP_DENSE = 1, 2, 3, 4, 5
-QREF_BIT = 32
+RD_FLAGS, RD_FMASK, RD_NNN, RD_NRR, RD_NRJ, RD_WORDS, RD_CTRL, RD_M, RD_C, RD_F, RD_FIXED = (
+    0, 1, 2, 3, 4, 9, 10, 20, 60, 64, 120,
+)  # fmt: skip
+TT_A, TT_B, TT_W, TT_WORDS = 0, 1, 4, 12
+OP_WORDS = 16
+OP_DENSE = 5
+FK_SCALAR, FK_PAIR, FK_TABLE, FK_MATRIX = 0, 1, 2, 3
+FF_D1, FF_D2_FIRST, FF_D2_SECOND, FF_S1, FF_S2, FF_T, FF_T_SWAP, FF_M, FF_MD = range(9)
 MIN_PASS_BITS = PASS_R + 5  # smallest state the tile kernel accepts
+_ONE = int(np.float32(1.0).view(np.int32))
 
 
 @dataclass
@@ -229,44 +237,12 @@ def _order_group_bits(nonreg: List[int]) -> List[int]:
     return first + tail
 
 
-def _encode_pass(nbits: int, tile_pos: List[int], L: int, subpasses: List[Dict[str, Any]]) -> np.ndarray:
-    T = len(tile_pos)
-    words: List[int] = [0] * HDR_WORDS
-    words[H_MAGIC] = PASS_MAGIC
-    words[H_T] = T
-    words[H_L] = L
-    words[H_NSUB] = len(subpasses)
-    words[H_R] = PASS_R
-    nontile = [p for p in range(nbits) if p not in set(tile_pos)]
-    words[H_NNONTILE] = len(nontile)
-    assert len(nontile) <= 56 and T <= 16
-    for i, p in enumerate(tile_pos):
-        words[H_TILEPOS + i] = p
-    for i, p in enumerate(nontile):
-        words[H_NONTILEPOS + i] = p
-    for sp in subpasses:
-        hdr = [0] * SUB_HDR_WORDS
-        hdr[S_NOPS] = len(sp["ops"])
-        hdr[S_KIND] = sp["kind"]
-        for j, b in enumerate(sp.get("reg", [])):
-            hdr[S_REGBITS + j] = b
-        for j, b in enumerate(sp.get("grp", [])):
-            hdr[S_GRPBITS + j] = b
-        hdr[S_WORDS] = SUB_HDR_WORDS + OP_WORDS * len(sp["ops"])
-        words.extend(hdr)
-        for op in sp["ops"]:
-            assert len(op) == OP_WORDS
-            words.extend(op)
-    words[H_WORDS] = len(words)
-    return np.asarray(words, dtype=np.int32)
-
-
 def _dense_dim(g: GateOp) -> int:
     return 1 << g.k
 
 
 def compile_plan(gates: Sequence[GateOp], nqubits: int, *, nbits_local: Optional[int] = None,
-                 tile_bits: int = PASS_MAX_T, low_bits: int = 4, max_ops_per_pass: int = 300,
+                 tile_bits: int = PASS_MAX_T, low_bits: int = 4, max_ops_per_pass: int = 200,
                  lookahead: int = 512) -> Plan:  # fmt: skip
     """Compile a gate stream.  `nbits_local` < nqubits describes a sharded state whose top
     (nqubits - nbits_local) qubits are global: only diagonal gates / controls may touch them."""
@@ -319,9 +295,204 @@ def compile_plan(gates: Sequence[GateOp], nqubits: int, *, nbits_local: Optional
                 continue
             if not sched:
                 raise RuntimeError("pass planner stalled")  # pragma: no cover
-        sched = front.simulate(inside, pos_of, 4, max_ops_per_pass, commit=True)
-        steps.append(_build_pass(gates, sched, nbits, pos_of, sorted(inside), L))
+        # the program must fit the kernel's shared-memory budget: shrink the pass until it does
+        limit = max_ops_per_pass
+        while True:
+            sched = front.simulate(inside, pos_of, 4, limit)
+            try:
+                step = _build_pass(gates, sched, nbits, pos_of, sorted(inside), L)
+                break
+            except _ProgramTooLarge:
+                limit = max(1, int(len(sched) * 0.7))
+        front.simulate(inside, pos_of, 4, len(sched), commit=True)
+        steps.append(step)
     return Plan(nbits=nbits, steps=steps, n_gates=len(gates))
+
+
+class _ProgramTooLarge(RuntimeError):
+    pass
+
+
+class _Pool:
+    """Gate tensors a pass needs, packed for the CTA's shared-memory pool (pass_kernel.cu)."""
+
+    def __init__(self) -> None:
+        self.entries: Dict[int, Tuple[int, int]] = {}  # gate mat_off -> (numel, pool offset)
+        self.size = 0
+
+    def ref(self, g: GateOp, delta: int = 0) -> int:
+        if g.mat_off not in self.entries:
+            numel = (1 << g.k) if g.kind[0] == "diagvec" else (1 << (2 * g.k))
+            self.entries[g.mat_off] = (numel, self.size)
+            self.size += numel
+        return self.entries[g.mat_off][1] + delta
+
+    def table(self) -> List[int]:
+        out: List[int] = []
+        for mat_off, (numel, poff) in self.entries.items():
+            out += [mat_off, numel, poff]
+        return out
+
+
+class _Round:
+    def __init__(self) -> None:
+        self.gate: List[Optional[Dict[str, Any]]] = [None] * PASS_R
+        self.ctrl_regs: Set[int] = set()
+        self.diag: List[GateOp] = []
+
+
+def _diag_stride(g: GateOp) -> int:
+    return 1 if g.kind[0] == "diagvec" else (1 << g.k) + 1
+
+
+def _build_rounds(sub_gates: Sequence[GateOp], run: List[Tuple[int, str]], pos_of: Sequence[int],
+                  reg_idx: Dict[int, int]) -> List[_Round]:  # fmt: skip
+    """Cut the ordered gate list of one register sub-pass into rounds (pass_core.cuh: a round is a
+    diagonal part followed by at most one fused 2x2 per register bit)."""
+    rounds: List[_Round] = [_Round()]
+    for gi, how in run:
+        g = sub_gates[gi]
+        cur = rounds[-1]
+        if how == "diag":
+            touches = [reg_idx[pos_of[q]] for q in g.qubits if pos_of[q] in reg_idx]
+            if g.k == 1 and touches and cur.gate[touches[0]] is not None and cur.gate[touches[0]]["ctrl"] is None \
+                    and touches[0] not in cur.ctrl_regs:
+                # 1q diagonal right after dense gate(s) on the same register bit: same 2x2 product
+                cur.gate[touches[0]]["fusion"].append((g, 0, FF_MD, _diag_stride(g)))
+                continue
+            if any(cur.gate[j] is not None for j in touches):
+                cur = _Round()
+                rounds.append(cur)
+            cur.diag.append(g)
+        elif how == "1q":
+            j = reg_idx[pos_of[g.qubits[0]]]
+            if (cur.gate[j] is not None and cur.gate[j]["ctrl"] is not None) or j in cur.ctrl_regs:
+                cur = _Round()
+                rounds.append(cur)
+            if cur.gate[j] is None:
+                cur.gate[j] = {"fusion": [], "ctrl": None}
+            cur.gate[j]["fusion"].append((g, 0, FF_M, 2))
+        elif how == "c1q":
+            nctrl, pol = g.kind[1], g.kind[2]
+            j = reg_idx[pos_of[g.qubits[-1]]]
+            cmask = cwant = 0
+            tcs: List[Tuple[int, int]] = []
+            regs: Set[int] = set()
+            for ci in range(nctrl):
+                want = (pol >> ci) & 1
+                p = pos_of[g.qubits[ci]]
+                if p in reg_idx:
+                    k = reg_idx[p]
+                    cmask |= 1 << k
+                    cwant |= want << k
+                    regs.add(k)
+                else:
+                    tcs.append((p, want))
+            if cur.gate[j] is not None or j in cur.ctrl_regs or any(cur.gate[k] is not None for k in regs):
+                cur = _Round()
+                rounds.append(cur)
+            D = 1 << g.k
+            polval = 0
+            for ci in range(nctrl):
+                polval = (polval << 1) | ((pol >> ci) & 1)
+            delta = (polval * 2) * D + polval * 2  # top-left of the active 2x2 block
+            cur.gate[j] = {"fusion": [(g, delta, FF_M, D)], "ctrl": {"cmask": cmask, "cwant": cwant, "tcs": tcs}}
+            cur.ctrl_regs |= regs
+        else:  # pragma: no cover
+            raise AssertionError(how)
+    return [r for r in rounds if r.diag or any(x is not None for x in r.gate)]
+
+
+def _emit_round(words: List[int], fills: List[List[int]], rnd: _Round, pos_of: Sequence[int],
+                reg_idx: Dict[int, int], tbit_of_pos: Dict[int, int], pool: _Pool) -> None:  # fmt: skip
+    base = len(words)
+    rec = [0] * RD_FIXED
+    flags = 0
+    for j in range(PASS_R):
+        rec[RD_M + 8 * j] = _ONE  # identity defaults (overwritten by the device prologue)
+        rec[RD_M + 8 * j + 6] = _ONE
+    rec[RD_C] = _ONE
+    for b in range(13):
+        rec[RD_F + 4 * b] = _ONE
+        rec[RD_F + 4 * b + 2] = _ONE
+    for j, gt in enumerate(rnd.gate):
+        if gt is None:
+            continue
+        flags |= 1 << j
+        fills.append([base + RD_M + 8 * j, FK_MATRIX, len(gt["fusion"]), 0]
+                     + [w for (fg, delta, form, st) in gt["fusion"]
+                        for w in (pool.ref(fg, delta), form | (st << 8), 0, 0)])  # fmt: skip
+        c = gt["ctrl"]
+        if c is not None:
+            if c["cmask"]:
+                flags |= 1 << (8 + j)
+            tcs = c["tcs"]
+            w0 = c["cmask"] | (c["cwant"] << 8) | (len(tcs) << 16)
+            w1 = 0
+            if len(tcs) > 0:
+                w1 |= tcs[0][0] | (tcs[0][1] << 7)
+            if len(tcs) > 1:
+                w1 |= (tcs[1][0] << 8) | (tcs[1][1] << 15)
+            rec[RD_CTRL + 2 * j] = w0
+            rec[RD_CTRL + 2 * j + 1] = w1
+    # diagonal part: classify every gate against (non-tile | thread-constant tile | register) bits
+    scalar_src: List[int] = []
+    pair_src: Dict[int, List[int]] = {}
+    nn: List[Tuple[int, int, GateOp, int]] = []
+    rj: List[List[Tuple[int, int, GateOp, int]]] = [[] for _ in range(PASS_R)]
+    rr: List[Tuple[int, int, GateOp, int]] = []
+    for g in rnd.diag:
+        st = _diag_stride(g)
+        ps = [pos_of[q] for q in g.qubits]
+        in_tile = [p in tbit_of_pos for p in ps]
+        if g.k == 1:
+            if in_tile[0]:
+                pair_src.setdefault(tbit_of_pos[ps[0]], []).extend([pool.ref(g), FF_D1 | (st << 8), 0, 0])
+            else:
+                scalar_src.extend([pool.ref(g), FF_S1 | (st << 8), ps[0], 0])
+            continue
+        if not in_tile[0] and not in_tile[1]:
+            scalar_src.extend([pool.ref(g), FF_S2 | (st << 8), ps[0], ps[1]])
+        elif in_tile[0] and not in_tile[1]:
+            pair_src.setdefault(tbit_of_pos[ps[0]], []).extend([pool.ref(g), FF_D2_FIRST | (st << 8), ps[1], 0])
+        elif in_tile[1] and not in_tile[0]:
+            pair_src.setdefault(tbit_of_pos[ps[1]], []).extend([pool.ref(g), FF_D2_SECOND | (st << 8), ps[0], 0])
+        else:
+            ra, rb = ps[0] in reg_idx, ps[1] in reg_idx
+            if ra and rb:
+                rr.append((reg_idx[ps[0]], reg_idx[ps[1]], g, FF_T))
+            elif ra:
+                rj[reg_idx[ps[0]]].append((reg_idx[ps[0]], tbit_of_pos[ps[1]], g, FF_T))
+            elif rb:
+                rj[reg_idx[ps[1]]].append((reg_idx[ps[1]], tbit_of_pos[ps[0]], g, FF_T_SWAP))
+            else:
+                nn.append((tbit_of_pos[ps[0]], tbit_of_pos[ps[1]], g, FF_T))
+    if rnd.diag:
+        flags |= 1 << 16
+    if scalar_src:
+        fills.append([base + RD_C, FK_SCALAR, len(scalar_src) // 4, 0] + scalar_src)
+    fmask = 0
+    for b, src in sorted(pair_src.items()):
+        fmask |= 1 << b
+        fills.append([base + RD_F + 4 * b, FK_PAIR, len(src) // 4, 0] + src)
+    rec[RD_FLAGS] = flags
+    rec[RD_FMASK] = fmask
+    rec[RD_NNN] = len(nn)
+    rec[RD_NRR] = len(rr)
+    tables = list(nn)
+    for j in range(PASS_R):
+        rec[RD_NRJ + j] = len(rj[j])
+        tables += rj[j]
+    tables += rr
+    rec[RD_WORDS] = RD_FIXED + TT_WORDS * len(tables)
+    words.extend(rec)
+    for a, b, g, form in tables:
+        ent = [0] * TT_WORDS
+        ent[TT_A], ent[TT_B] = a, b
+        ent[TT_W], ent[TT_W + 6] = _ONE, _ONE
+        ent[TT_W + 2], ent[TT_W + 4] = _ONE, _ONE
+        fills.append([len(words) + TT_W, FK_TABLE, 1, 0, pool.ref(g), form | (_diag_stride(g) << 8), 0, 0])
+        words.extend(ent)
 
 
 def _build_pass(gates: Sequence[GateOp], sched: List[Tuple[int, str]], nbits: int, pos_of: Sequence[int],
@@ -330,27 +501,39 @@ def _build_pass(gates: Sequence[GateOp], sched: List[Tuple[int, str]], nbits: in
     tbit_of_pos = {p: i for i, p in enumerate(tile_pos)}
     nq = len(pos_of)
     sub_gates = [gates[gi] for gi, _ in sched]
-    allow = {i for i in range(len(sub_gates))}
-    # local frontier over the scheduled gates only (indices into sub_gates)
-    local = _Frontier(sub_gates, nq)
-    subpasses: List[Dict[str, Any]] = []
+    local = _Frontier(sub_gates, nq)  # frontier over the scheduled gates only
     tile_set = set(tile_pos)
+
+    words: List[int] = [0] * HDR_WORDS
+    words[H_MAGIC] = PASS_MAGIC
+    words[H_T] = T
+    words[H_L] = L
+    words[H_R] = PASS_R
+    nontile = [p for p in range(nbits) if p not in tile_set]
+    words[H_NNONTILE] = len(nontile)
+    assert len(nontile) <= 40 and T <= 16
+    for i, p in enumerate(tile_pos):
+        words[H_TILEPOS + i] = p
+    for i, p in enumerate(nontile):
+        words[H_NONTILEPOS + i] = p
+    fills: List[List[int]] = []
+    pool = _Pool()
+    nsub = 0
     while local.remaining > 0:
-        # is the next ready gate a dense k>=2 gate?  then it is its own shared-memory sub-pass
         inside = _grow(local, pos_of, set(), PASS_R, tile_pos, 1, 1 << 30)
         run = local.simulate(inside, pos_of, 1, 1 << 30)
         if not run:
-            # only dense multi-qubit gates are ready
-            cand = [
-                local.queues[q][local.ptr[q]] for q in range(nq) if local.ptr[q] < len(local.queues[q])
-            ]
+            # only dense multi-qubit gates are ready: one shared-memory sub-pass each
+            cand = [local.queues[q][local.ptr[q]] for q in range(nq) if local.ptr[q] < len(local.queues[q])]
             cand = sorted({gi for gi in cand if local.ready(gi, local.ptr)})
-            gi = cand[0]
-            g = sub_gates[gi]
+            g = sub_gates[cand[0]]
             assert g.k >= 2 and all(pos_of[q] in tile_set for q in g.qubits), "planner invariant"
-            tb = [tbit_of_pos[pos_of[q]] for q in g.qubits] + [0] * 5
-            op = [OP_DENSE, tb[0], tb[1], g.mat_off, g.k, tb[2], tb[3], tb[4]]
-            subpasses.append({"kind": SUB_SMEM_DENSE, "ops": [op]})
+            tb = [tbit_of_pos[pos_of[q]] for q in g.qubits] + [0] * 4
+            hdr = [0] * SUB_HDR_WORDS
+            hdr[S_NROUNDS], hdr[S_KIND], hdr[S_WORDS] = 1, SUB_SMEM_DENSE, SUB_HDR_WORDS + OP_WORDS
+            words.extend(hdr)
+            words.extend([OP_DENSE, tb[0], tb[1], g.mat_off, g.k, tb[2], tb[3], 0] + [0] * 8)
+            nsub += 1
             for q in g.qubits:
                 local.ptr[q] += 1
             local.remaining -= 1
@@ -360,41 +543,39 @@ def _build_pass(gates: Sequence[GateOp], sched: List[Tuple[int, str]], nbits: in
         reg_tb = [tbit_of_pos[p] for p in reg_pos]
         reg_idx = {p: j for j, p in enumerate(reg_pos)}
         grp = _order_group_bits([t for t in range(T) if t not in set(reg_tb)])
+        rounds = _build_rounds(sub_gates, run, pos_of, reg_idx)
+        hdr_at = len(words)
+        hdr = [0] * SUB_HDR_WORDS
+        hdr[S_NROUNDS], hdr[S_KIND] = len(rounds), SUB_REG
+        for j, b in enumerate(reg_tb):
+            hdr[S_REGBITS + j] = b
+        for j, b in enumerate(grp):
+            hdr[S_GRPBITS + j] = b
+        words.extend(hdr)
+        for rnd in rounds:
+            _emit_round(words, fills, rnd, pos_of, reg_idx, tbit_of_pos, pool)
+        words[hdr_at + S_WORDS] = len(words) - hdr_at
+        nsub += 1
+    words[H_NSUB] = nsub
+    # fill records, then the table of their offsets (last H_NFILL words)
+    def _is_static(f: List[int]) -> bool:  # no source looks at tile-constant bits
+        return all((f[4 + 4 * i + 1] & 0xFF) not in (FF_D2_FIRST, FF_D2_SECOND, FF_S1, FF_S2) for i in range(f[2]))
 
-        def qref(q: int) -> int:
-            p = pos_of[q]
-            return reg_idx[p] if p in reg_idx else QREF_BIT + p
-
-        ops: List[List[int]] = []
-        for gi, how in run:
-            g = sub_gates[gi]
-            D = _dense_dim(g)
-            if how == "1q":
-                ops.append([OP_1Q, reg_idx[pos_of[g.qubits[0]]], 0, g.mat_off, 0, 2, 0, 0])
-            elif how == "c1q":
-                nctrl, pol = g.kind[1], g.kind[2]
-                wants = [(pol >> i) & 1 for i in range(nctrl)]
-                polval = 0
-                for w in wants:
-                    polval = (polval << 1) | w
-                mat = g.mat_off + (polval * 2) * D + polval * 2
-                qc0 = qref(g.qubits[0])
-                qc1 = qref(g.qubits[1]) if nctrl == 2 else -1
-                polbits = wants[0] | ((wants[1] << 1) if nctrl == 2 else 0)
-                ops.append([OP_C1Q, qc0, reg_idx[pos_of[g.qubits[-1]]], mat, polbits, D, qc1, 0])
-            elif how == "diag":
-                packed = g.kind[0] == "diagvec"
-                if g.k == 1:
-                    ops.append([OP_DIAG1, qref(g.qubits[0]), 0, g.mat_off, 0, 1 if packed else 3, 0, 0])
-                else:
-                    ops.append(
-                        [OP_DIAG2, qref(g.qubits[0]), qref(g.qubits[1]), g.mat_off, 0, 1 if packed else 5, 0, 0]
-                    )
-            else:  # pragma: no cover
-                raise AssertionError(how)
-        subpasses.append({"kind": SUB_REG, "reg": reg_tb, "grp": grp, "ops": ops})
-    program = _encode_pass(nbits, tile_pos, L, subpasses)
-    if len(program) > PASS_MAX_WORDS:
-        raise RuntimeError(f"pass program too large ({len(program)} words)")
+    fills = [f for f in fills if _is_static(f)] + [f for f in fills if not _is_static(f)]
+    words[H_NFILL_STATIC] = sum(1 for f in fills if _is_static(f))
+    offs = []
+    for f in fills:
+        offs.append(len(words))
+        words.extend(f)
+    words[H_NFILL] = len(offs)
+    ptab = pool.table()
+    words[H_NPOOL] = len(ptab) // 3
+    words[H_POOLSIZE] = pool.size
+    words.extend(ptab)  # pool table sits right before the fill-offset table
+    words.extend(offs)
+    words[H_WORDS] = len(words)
+    program = np.asarray(words, dtype=np.int64).astype(np.int32)
+    if len(program) > PASS_MAX_WORDS or pool.size > PASS_MAX_POOL:
+        raise _ProgramTooLarge(f"pass program too large ({len(program)} words)")
     return PassStep(program=program, tile_bits=T, low_bits=L, gate_ids=[gates[gi].gid for gi, _ in sched],
-                    n_subpasses=len(subpasses))  # fmt: skip
+                    n_subpasses=nsub)  # fmt: skip

@@ -85,7 +85,7 @@ def test_random_circuit_state(cuda, n, depth, seed):
     assert np.abs(psi - ref).max() <= ATOL_PSI
 
 
-@pytest.mark.parametrize("tile_bits,low_bits", [(10, 4), (11, 3), (12, 5), (13, 4), (13, 6)])
+@pytest.mark.parametrize("tile_bits,low_bits", [(10, 4), (11, 3), (12, 5), (13, 4), (13, 5)])
 def test_tile_geometries(cuda, tile_bits, low_bits):
     tc = _tc()
     n = 16
