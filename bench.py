@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""
+bench.py — the driver's measurement contract for the statevector hot path.
+
+Workload at N = 1 (BASELINE.json configs[2], the configuration the gates/s + HBM GB/s metric is
+quoted on): 30-qubit QAOA MaxCut, p = 8, random 3-regular graph (networkx seed 0, 45 edges),
+630 gates, followed by the 45 <Z_i Z_j> cost terms.  One "step" = |0..0> -> evolve -> 45
+expectations.  
+
+Workload at N > 1: the same circuit family on n = 30 + log2(N) qubits, amplitudes sharded over
+the N GPUs (top log2 N qubits global, NCCL all-to-all qubit swaps; sharded.py) — per-GPU state
+stays 8 GiB, so scaling is weak.
+
+Lines printed (ONE JSON line, rank 0):
+    value   : gates/s with every input resident in HBM (compiled plan, gate matrices on device)
+    e2e     : gates/s through the public API (Circuit(...).rx/.exp1/.expectation_ps) from HOST
+              parameters in pinned memory, result read back to the host, every step
+    roofline: the fused tile-pass kernel, algorithmic bytes 16 B/amplitude/launch over its
+              CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+    cpu_baseline : the numpy oracle (restated reference path, `plain` contractor order) on the
+              host cores, on a bounded sample, extrapolated as stated in `sample`
+
+`--impl reference` times the reference's CPU path (the numpy restatement under oracle/ — the
+reference package itself cannot be imported in this image) on the same
+workload family, bounded sample per step.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from typing import Any, Dict, List, Tuple
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_QUBITS_1GPU = 30
+P_LAYERS = 8
+
+
+# ----------------------------------------------------------------------------------------------
+def qaoa_problem(n: int, p: int) -> Tuple[List[Tuple[int, int]], np.ndarray, np.ndarray]:
+    import networkx as nx
+
+    g = nx.random_regular_graph(3, n, seed=0)
+    rng = np.random.default_rng(0)
+    gam = rng.uniform(0, np.pi, p).astype(np.float32)
+    bet = rng.uniform(0, np.pi, p).astype(np.float32)
+    edges = [(int(a), int(b)) for a, b in g.edges]
+    return edges, gam, bet
+
+
+def build_qaoa(mod: Any, n: int, edges: List[Tuple[int, int]], gam: Any, bet: Any, zz: Any) -> Any:
+    """The same source for the engine (`mod` = tensorcircuit_ng_b200) and the oracle (tc_oracle):
+    tensorcircuit/templates/blocks.py:99-143 QAOA_block = exp1(ZZ, gamma) on edges, rx(beta) on nodes."""
+    c = mod.Circuit(n)
+    for q in range(n):
+        c.h(q)
+    for l in range(len(gam)):
+        for a, b in edges:
+            c.exp1(a, b, unitary=zz, theta=gam[l])
+        for q in range(n):
+            c.rx(q, theta=bet[l])
+    return c
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, index: int) -> None:
+        self.index = index
+        self.rows: List[List[str]] = []
+        self.proc: Any = None
+        self.thread: Any = None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+        except OSError:
+            self.proc = None
+            return
+
+        def pump() -> None:
+            assert self.proc is not None and self.proc.stdout is not None
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> Dict[str, Any]:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_s: int, repeats: int = 1) -> Tuple[float, int, float]:
+    """Oracle (numpy restatement of the reference CPU path, `plain` statevector contraction order,
+    tensorcircuit/cons.py:429-463) on the QAOA family at n_s qubits, first layer only.
+    Returns (seconds, gates, gates/s at n_s)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tc_oracle
+
+    edges, gam, bet = qaoa_problem(n_s, 1)
+    zz = np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0])).astype(np.complex64)
+    tc_oracle.set_contractor("plain")
+    best = float("inf")
+    ng = n_s + len(edges) + n_s
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        c = build_qaoa(tc_oracle, n_s, edges, [float(gam[0])], [float(bet[0])], zz)
+        psi = c.wavefunction()
+        _ = float(np.vdot(psi, psi).real)
+        best = min(best, time.perf_counter() - t0)
+    return best, ng, ng / best
+
+
+def run_reference(args: argparse.Namespace) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_target = N_QUBITS_1GPU + max(0, int(np.log2(max(1, args.gpus))))
+    n_s = args.ref_qubits
+    cores = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(n_s)
+    times = []
+    ng = 0
+    for _ in range(args.steps):
+        t, ng, _ = cpu_reference_sample(n_s)
+        times.append(t)
+    per_step = sum(times) / len(times)
+    # time per gate of the statevector path is proportional to 2^n (every gate is one pass over the state)
+    gps = ng / per_step / (2.0 ** (n_target - n_s))
+    sample = (f"oracle (numpy restatement, plain contractor) on the QAOA family at n={n_s}, layer 1 only "
+              f"({ng} gates, {per_step:.2f} s/step); gates/s scaled by 2^-({n_target}-{n_s}) to n={n_target} "
+              "(per-gate time is one pass over 2^n amplitudes)")  # fmt: skip
+    line = {
+        "impl": "reference",
+        "metric": "gates/s",
+        "value": gps,
+        "unit": "gates/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": per_step * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "complex64",
+        "data": "synthetic",
+        "config": {"workload": f"qaoa_maxcut_3regular_n{n_target}_p{P_LAYERS}", "measured_on": f"n={n_s}, p=1 sample, extrapolated"},
+        "cpu_baseline": {"value": gps, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": gps, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_b200(args: argparse.Namespace) -> None:
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import _lib, expect, passplan, svengine
+
+    torch.set_default_device(dev)
+    n = args.qubits
+    p = P_LAYERS
+    edges, gam, bet = qaoa_problem(n, p)
+    n_gates = n + p * (len(edges) + n)
+    zz_host = np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0])).astype(np.complex64)
+    zz = zz_host  # host constant, like tc.gates._zz_matrix in the reference's QAOA examples
+
+    # ---- device-resident path: plan + gate buffer built once (what a training loop reuses) ----
+    c = build_qaoa(tc, n, edges, [float(x) for x in gam], [float(x) for x in bet], zz)
+    nodes, d_edges = c._copy()
+    nq, init, gates = svengine.extract_gate_stream(nodes, d_edges)
+    structure = [(g[1], svengine.gate_kind(g[0], g[2]), int(g[0].tensor.numel())) for g in gates]
+    cc = svengine.compile_circuit(n, structure, dev)
+    gatebuf = svengine.build_gatebuf([g[0].tensor for g in gates], dev)
+    plan = cc.plan
+    state = svengine.new_zero_state(n, 1, dev)
+    stream = torch.cuda.current_stream()
+
+    def step_resident() -> "torch.Tensor":
+        _lib.call("tcb_sv_init_zero", state.data_ptr(), n, 1, _lib.stream_ptr())
+        cc.run(state, gatebuf)
+        return expect.z_expectations(state, n, [[a, b] for a, b in edges])
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        zzv = step_resident()
+    e1.record(stream)
+    barrier()
+    launches = _lib.launch_count - l0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    cost = float((0.5 * (1.0 - zzv)).sum().item())
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events around every tile pass ------
+    pass_ms: List[float] = []
+    evs = []
+    _lib.call("tcb_sv_init_zero", state.data_ptr(), n, 1, _lib.stream_ptr())
+    pi = 0
+    for st in plan.steps:
+        if isinstance(st, passplan.PassStep):
+            prog_ptr = cc.programs.data_ptr() + 4 * cc.offsets[pi]
+            pi += 1
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            _lib.call("tcb_sv_run_pass", state.data_ptr(), n, 1, prog_ptr, len(st.program), st.tile_bits,
+                      st.low_bits, st.pool_elems, gatebuf.data_ptr(), 0, 0, _lib.stream_ptr())  # fmt: skip
+            b.record(stream)
+            evs.append((a, b))
+    torch.cuda.synchronize()
+    pass_ms = [a.elapsed_time(b) for a, b in evs]
+    alg_bytes = 16.0 * (2.0**n)  # one read + one write of 2^n complex64 per launch
+    avg_pass_ms = sum(pass_ms) / max(1, len(pass_ms))
+    achieved = alg_bytes / (avg_pass_ms * 1e-3) / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "pass_kernel_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- e2e: public API from HOST parameters, every step ------------------------------------
+    gam_pin = torch.from_numpy(gam).pin_memory()
+    bet_pin = torch.from_numpy(bet).pin_memory()
+
+    def step_e2e() -> float:
+        g_d = gam_pin.to(dev, non_blocking=True)
+        b_d = bet_pin.to(dev, non_blocking=True)
+        cq = build_qaoa(tc, n, edges, g_d, b_d, zz)
+        total = None
+        for a, b in edges:
+            v = cq.expectation_ps(z=[a, b])
+            total = v if total is None else total + v
+        return float((0.5 * (len(edges) - total.real)).cpu())
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        cost_e2e = step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    # ---- max over ranks --------------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    units = n_gates * world  # replicas until the sharded state lands: every rank runs the workload
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_s = args.ref_qubits
+        tsec, ng, gps_s = cpu_reference_sample(n_s)
+        cpu_baseline = {
+            "value": gps_s / (2.0 ** (n - n_s)),
+            "unit": "gates/s",
+            "cores": os.cpu_count() or 1,
+            "kind": "port",
+            "sample": (f"oracle (numpy restatement of the reference CPU path, plain contractor) on the same QAOA "
+                       f"family at n={n_s}, layer 1 ({ng} gates in {tsec:.1f} s = {gps_s:.1f} gates/s), scaled by "
+                       f"2^-({n}-{n_s}) to n={n}"),  # fmt: skip
+        }
+
+    if rank == 0:
+        line = {
+            "metric": "gates/s",
+            "value": units / (ms_per_step * 1e-3),
+            "unit": "gates/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "complex64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"qaoa_maxcut_3regular_n{n}_p{p}",
+                "gates": n_gates,
+                "expectation_terms": len(edges),
+                "state_bytes": 8 * 2**n,
+                "l2": "inputs larger than L2 (8 GiB state)",
+                "multi_gpu": "single" if world == 1 else "replicas",
+                "hbm_passes": plan.n_passes,
+                "state_gbs": plan.n_passes * alg_bytes / (sum(pass_ms) * 1e-3) / 1e9 if pass_ms else None,
+                "equivalent_unfused_gbs": n_gates * alg_bytes / (ms_per_step * 1e-3) / 1e9,
+                "cost": cost,
+            },
+            "roofline": {
+                "kernel": "tcb::pass_kernel (fused tile pass)",
+                "bound": "hbm",
+                "achieved": achieved,
+                "peak": peak,
+                "peak_source": peak_src,
+                "unit": "GB/s",
+                "frac": achieved / peak,
+                "traffic": traffic,
+                "alg_bytes_per_launch": alg_bytes,
+                "avg_launch_ms": avg_pass_ms,
+                "launches_per_step": len(pass_ms),
+            },
+            "cpu_baseline": cpu_baseline,
+            "e2e": {
+                "value": units / e2e_s,
+                "unit": "gates/s",
+                "h2d_bytes_per_step": int(gam.nbytes + bet.nbytes),
+                "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_s * 1e3,
+                "steps": e2e_steps,
+                "cost": cost_e2e,
+            },
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--qubits", type=int, default=N_QUBITS_1GPU)
+    ap.add_argument("--ref-qubits", type=int, default=24, help="size of the bounded CPU sample (even: 3-regular graph)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -67,14 +67,14 @@ int tcb_sv_apply_diag(void* state, int nbits, int64_t batch, const int* bitpos_h
  * program ops address it by element offset.  Replaces the tensordot+permute
  * loop of tensorcircuit/cons.py:937-953 for circuit-shaped networks.          */
 int tcb_sv_run_pass(void* state, int nbits, int64_t batch, const int32_t* program,
-                    int32_t program_words, int tile_bits, int low_bits, const void* gatebuf,
+                    int32_t program_words, int tile_bits, int low_bits, int pool_elems, const void* gatebuf,
                     int64_t gate_batch_stride, uint64_t index_base, void* stream);
 /* same kernel reading `src` and writing `dst` (out-of-place; src may equal dst).
- * tile_bits / low_bits repeat the program header's T / L (the host needs them to size the
- * launch without reading device memory).                                                  */
+ * tile_bits / low_bits / pool_elems repeat the program header's T / L / gate-pool size (the
+ * host needs them to size the launch without reading device memory).                      */
 int tcb_sv_run_pass_oop(const void* src, void* dst, int nbits, int64_t batch,
                         const int32_t* program, int32_t program_words, int tile_bits,
-                        int low_bits, const void* gatebuf, int64_t gate_batch_stride,
+                        int low_bits, int pool_elems, const void* gatebuf, int64_t gate_batch_stride,
                         uint64_t index_base, void* stream);
 
 /* ---- statevector: reductions (K3/K4 without materialising the bra) --------

@@ -69,11 +69,12 @@ SYMBOLS = {
     ),
     "tcb_sv_run_pass": (
         c_int,
-        [c_void_p, c_int, c_int64, c_void_p, c_int32, c_int, c_int, c_void_p, c_int64, c_uint64, c_void_p],
+        [c_void_p, c_int, c_int64, c_void_p, c_int32, c_int, c_int, c_int, c_void_p, c_int64, c_uint64,
+         c_void_p],
     ),
     "tcb_sv_run_pass_oop": (
         c_int,
-        [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int32, c_int, c_int, c_void_p, c_int64,
+        [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int32, c_int, c_int, c_int, c_void_p, c_int64,
          c_uint64, c_void_p],
     ),  # fmt: skip
     "tcb_sv_expect_z": (

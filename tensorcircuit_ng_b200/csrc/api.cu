@@ -33,7 +33,7 @@ int launch_init_zero(void*, int, int64_t, cudaStream_t);
 int launch_dense(void*, int, int64_t, const int*, int, const void*, int64_t, cudaStream_t);
 int launch_diag(void*, int, int64_t, const int*, int, const void*, int64_t, int64_t, uint64_t,
                 cudaStream_t);
-int launch_pass(const void*, void*, int, int64_t, const int32_t*, int32_t, int, int, const void*,
+int launch_pass(const void*, void*, int, int64_t, const int32_t*, int32_t, int, int, int, const void*,
                 int64_t, uint64_t, cudaStream_t);
 int launch_expect_z(const void*, int, int64_t, const uint64_t*, int, uint64_t, double*, cudaStream_t);
 int launch_expect_pauli(const void*, int, int64_t, uint64_t, uint64_t, int, uint64_t, double*,
@@ -92,24 +92,25 @@ int tcb_sv_apply_diag(void* state, int nbits, int64_t batch, const int* bitpos, 
 }
 
 int tcb_sv_run_pass(void* state, int nbits, int64_t batch, const int32_t* program,
-                    int32_t program_words, int tile_bits, int low_bits, const void* gatebuf,
-                    int64_t gate_batch_stride, uint64_t index_base, void* stream) {
+                    int32_t program_words, int tile_bits, int low_bits, int pool_elems,
+                    const void* gatebuf, int64_t gate_batch_stride, uint64_t index_base, void* stream) {
   NOTNULL(state, "tcb_sv_run_pass");
   NOTNULL(program, "tcb_sv_run_pass");
   NOTNULL(gatebuf, "tcb_sv_run_pass");
-  return launch_pass(state, state, nbits, batch, program, program_words, tile_bits, low_bits, gatebuf,
-                     gate_batch_stride, index_base, S(stream));
+  return launch_pass(state, state, nbits, batch, program, program_words, tile_bits, low_bits, pool_elems,
+                     gatebuf, gate_batch_stride, index_base, S(stream));
 }
 
 int tcb_sv_run_pass_oop(const void* src, void* dst, int nbits, int64_t batch, const int32_t* program,
-                        int32_t program_words, int tile_bits, int low_bits, const void* gatebuf,
-                        int64_t gate_batch_stride, uint64_t index_base, void* stream) {
+                        int32_t program_words, int tile_bits, int low_bits, int pool_elems,
+                        const void* gatebuf, int64_t gate_batch_stride, uint64_t index_base,
+                        void* stream) {
   NOTNULL(src, "tcb_sv_run_pass_oop");
   NOTNULL(dst, "tcb_sv_run_pass_oop");
   NOTNULL(program, "tcb_sv_run_pass_oop");
   NOTNULL(gatebuf, "tcb_sv_run_pass_oop");
-  return launch_pass(src, dst, nbits, batch, program, program_words, tile_bits, low_bits, gatebuf,
-                     gate_batch_stride, index_base, S(stream));
+  return launch_pass(src, dst, nbits, batch, program, program_words, tile_bits, low_bits, pool_elems,
+                     gatebuf, gate_batch_stride, index_base, S(stream));
 }
 
 int tcb_sv_expect_z(const void* state, int nbits, int64_t batch, const uint64_t* zmasks, int nterms,

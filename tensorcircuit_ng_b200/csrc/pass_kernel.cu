@@ -1,17 +1,20 @@
 // pass_kernel.cu — CUDA shell of the fused tile pass (logic in pass_core.cuh).
 //
 // Bound: HBM (one read + one write of the state per launch, 16 B per amplitude).
-// Structure: PERSISTENT CTAs with a two-stage shared-memory pipeline.
+// Structure: PERSISTENT CTAs, several per SM, each streaming one tile at a time.
 //   * grid = (#SMs x CTAs per SM); a CTA walks tiles  blockIdx.x, + gridDim.x, ...
-//   * while tile k is being computed in buffer k&1, tile k+1 streams into the other buffer with
-//     cp.async (LDGSTS: no registers are tied up, so the 2^R amplitudes per thread and the next
-//     tile's 64 KB in flight coexist);  cp.async.wait_group + one barrier hands the buffer over.
+//   * blockDim = 2^(T-R) threads, R = 5: 128 threads for 2^12-amplitude tiles, FOUR CTAs per SM
+//     (4 x 32 KB tiles + side tables, 4 x 128 x 128 registers = the whole register file), 256 threads
+//     and two CTAs per SM for 2^13 tiles.  The register sub-passes are FP32-pipe bound (a 2x2 complex
+//     matvec per amplitude pair and gate), the streaming phases HBM bound; with four CTAs per SM in
+//     different phases the warp schedulers overlap one CTA's load / store with another's arithmetic
+//     (measured: a CTA pair with in-CTA double buffering left the FMA pipe 2/3 idle — too few warps).
+//   * load: 16-byte cp.async (LDGSTS) straight into the swizzled tile, so no registers are tied up
+//     while the tile is in flight; the per-tile fill records are resolved meanwhile.
 //   * once per CTA: the program is staged in shared memory and the gate tensors the pass needs are
-//     copied into a shared-memory pool; per tile, warps resolve the fill records (fused 1q
+//     copied into a shared-memory pool; per tile, threads resolve the fill records (fused 1q
 //     products, diagonal gates against this tile's constant bits) from the pool — no global
 //     latency on the per-tile critical path.
-//   * blockDim = 2^(T-R) threads: 256 for 2^13-amplitude tiles (1 CTA/SM, 2 x 64 KB buffers),
-//     128 for 2^12 tiles (2 CTAs/SM).
 #include "common.cuh"
 #include "pass_core.cuh"
 #include "../../include/tcb200.h"
@@ -34,9 +37,9 @@ __device__ unsigned long long g_pass_prof[16];
 #define PROF_MARK(slot)
 #endif
 
-__device__ __forceinline__ void cp_async8(float2* smem_dst, const float2* gmem_src) {
+__device__ __forceinline__ void cp_async16(float2* smem_dst, const float2* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -55,33 +58,38 @@ __device__ __forceinline__ Mat2 shfl_down_mat2(const Mat2& m, int d) {
   return r;
 }
 
-// per-tile prologue: a warp owns a fill record, lane i loads source i from the shared-memory gate
-// pool, the ordered product is a shuffle tree (after step k lane i holds sources [i, i + 2^k)).
-__device__ __forceinline__ void prologue_fill(int32_t* sprog, int prog_words, const float2* pool,
-                                              uint64_t cta_bits, int warp, int lane, int nwarps, int first,
-                                              int last) {
+// fill records [first, last) with ONE THREAD per record (short records: <= FILL_SHORT sources)
+__device__ __forceinline__ void prologue_fill_threads(int32_t* sprog, int prog_words, const float2* pool,
+                                                      uint64_t cta_bits, int tid, int nthreads, int first,
+                                                      int last) {
+  const int nfill = sprog[H_NFILL];
+  const int32_t* filltab = sprog + prog_words - nfill;
+  for (int r = first + tid; r < last; r += nthreads) run_fill_record(sprog, filltab[r], pool, cta_bits);
+}
+
+// fill records [first, last) with ONE WARP per record: lane i loads source i from the shared-memory
+// gate pool, the ordered product is a shuffle tree (after step k lane i holds sources [i, i + 2^k)).
+__device__ __forceinline__ void prologue_fill_warps(int32_t* sprog, int prog_words, const float2* pool,
+                                                    uint64_t cta_bits, int warp, int lane, int nwarps,
+                                                    int first, int last) {
   const int nfill = sprog[H_NFILL];
   const int32_t* filltab = sprog + prog_words - nfill;
   for (int r = first + warp; r < last; r += nwarps) {
     const int32_t* rec = sprog + filltab[r];
     const int kind = rec[1], count = rec[2];
-    if (count == 1) {  // nothing to multiply
-      if (lane == 0) store_fill_result(sprog, rec, load_fill_source(rec + 4, kind, pool, cta_bits));
-      continue;
-    }
-    Mat2 acc = mat2_identity();
+    Mat2 acc = fill_identity(kind);
     for (int c0 = 0; c0 < count; c0 += 32) {  // (records longer than a warp: chunks, in order)
-      Mat2 e = mat2_identity();
+      Mat2 e = fill_identity(kind);
       if (c0 + lane < count) e = load_fill_source(rec + 4 + 4 * (c0 + lane), kind, pool, cta_bits);
       const int span = count - c0;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         if (d < span) {  // warp-uniform: skip tree levels that only see identities
           const Mat2 later = shfl_down_mat2(e, d);
-          e = mat2_mul(later, e);
+          e = fill_combine(kind, later, e);
         }
       }
-      acc = mat2_mul(e, acc);  // lane 0 holds the chunk product
+      acc = fill_combine(kind, e, acc);  // lane 0 holds the chunk product
     }
     if (lane == 0) store_fill_result(sprog, rec, acc);
   }
@@ -99,71 +107,97 @@ struct PassArgs {
   int nbits, prog_words;
 };
 
-// R register bits, LT = log2(threads per CTA) (512 threads for a 2^13 tile at R = 4); tile bits T = LT + R are compile-time, so every
+// shared-memory carve-up (bytes, every region 16-byte aligned)
+constexpr int GRP_STRIDE = 40;  // per sub-pass: 32 lane parts + up to 8 warp parts
+struct PassSmem {
+  size_t tile, hi_flat, grp, pool, prog, total;
+};
+__host__ __device__ inline PassSmem pass_smem_layout(int T, int L, int prog_words, int poolsize) {
+  PassSmem s;
+  s.tile = 0;
+  s.hi_flat = (size_t)8 << T;
+  s.grp = s.hi_flat + ((((size_t)4 << (T - L)) + 15) & ~(size_t)15);
+  s.pool = s.grp + (size_t)PASS_MAX_SUB * GRP_STRIDE * 4;
+  s.prog = s.pool + (((size_t)poolsize * 8 + 15) & ~(size_t)15);
+  s.total = s.prog + (((size_t)prog_words * 4 + 15) & ~(size_t)15);
+  return s;
+}
+
+// R register bits, LT = log2(threads per CTA); tile bits T = LT + R are compile-time, so every
 // swizzle constant of the streaming phases is a literal.
-template <int R, int LT>
-__global__ void __launch_bounds__(1 << LT, 1) pass_kernel(const PassArgs A) {
+template <int R, int LT, int MINB>
+__global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
   constexpr int T = LT + R;
   constexpr int NT = 1 << LT;
-  constexpr int N_LD = (1 << T) / NT;        // 8-byte cp.async per thread
-  constexpr int N_ST = (1 << (T - 1)) / NT;  // STG.128 per thread
-  constexpr size_t TILE_BYTES = (size_t)8 << T;
+  constexpr int N_IO = (1 << (T - 1)) / NT;  // 16-byte chunks per thread (load and store)
+  constexpr int NWARPS = (NT + 31) / 32;
+  static_assert(NWARPS <= 8, "grp table holds 8 warp parts");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  constexpr int NWARPS = NT / 32;
 
-  // ---- once per CTA: carve shared memory, stage the program, build hi_flat ----
+  // ---- once per CTA: carve shared memory, stage the program, build the static tables ----
   const int L = __ldg(A.prog + H_L);
   const int poolsize = __ldg(A.prog + H_POOLSIZE);
-  uint64_t* hi_flat = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE_BYTES);
-  float2* pool = reinterpret_cast<float2*>(smem_raw + 2 * TILE_BYTES + ((size_t)8 << (T - L)));
-  int32_t* sprog = reinterpret_cast<int32_t*>(smem_raw + 2 * TILE_BYTES + ((size_t)8 << (T - L)) +
-                                              (((size_t)poolsize * 8 + 15) & ~(size_t)15));
+  const PassSmem lay = pass_smem_layout(T, L, A.prog_words, poolsize);
+  float2* tile = reinterpret_cast<float2*>(smem_raw + lay.tile);
+  uint32_t* hi_flat = reinterpret_cast<uint32_t*>(smem_raw + lay.hi_flat);  // tile_to_flat(h << L) >> L
+  int32_t* grp = reinterpret_cast<int32_t*>(smem_raw + lay.grp);
+  float2* pool = reinterpret_cast<float2*>(smem_raw + lay.pool);
+  int32_t* sprog = reinterpret_cast<int32_t*>(smem_raw + lay.prog);
   for (int w = tid; w < A.prog_words; w += NT) sprog[w] = __ldg(A.prog + w);
   __syncthreads();
   const int32_t* hdr = sprog;
-  for (int h = tid; h < (1 << (T - L)); h += NT) hi_flat[h] = tile_to_flat(h << L, hdr);
+  for (int h = tid; h < (1 << (T - L)); h += NT) hi_flat[h] = (uint32_t)(tile_to_flat(h << L, hdr) >> L);
   const int npool = hdr[H_NPOOL];
   const int nfill = hdr[H_NFILL];
   const int nstatic = hdr[H_NFILL_STATIC];
+  const int nshort_end = hdr[H_NFILL_SHORT_END];
+  const int nsub = hdr[H_NSUB];
   const int32_t* pooltab = sprog + A.prog_words - nfill - 3 * npool;
+  {
+    // tile index of a thread = lane part | warp part, per register sub-pass
+    const int32_t* sp = hdr + HDR_WORDS;
+    for (int s = 0; s < nsub; ++s) {
+      if (sp[S_KIND] == SUB_REG) {
+        for (int i = tid; i < GRP_STRIDE; i += NT) {
+          const int g = i < 32 ? i : ((i - 32) << 5);
+          grp[s * GRP_STRIDE + i] = group_to_tile(g & (NT - 1), T, R, sp);
+        }
+      }
+      sp += sp[S_WORDS];
+    }
+  }
 
-  // element mapping of the streaming phases
-  //   load : t = tid + NT*u        (8 B per lane: a warp instruction covers 256 contiguous bytes)
-  //   store: t = 2*tid + 2*NT*u    (two amplitudes -> one STG.128)
+  // element mapping of the streaming phases: chunk c = tid + NT*u holds amplitudes t = 2c, 2c+1
+  // (16 bytes per lane: a warp instruction covers 512 contiguous bytes of the tile index space).
   // tid and NT*u have disjoint bits, so swizzle and hi_flat index split into thread + literal parts.
   const int lowmask = (1 << L) - 1;
-  const int ld_s0 = swz(tid), st_s0 = swz(2 * tid);
+  const int io_s0 = swz(2 * tid);
   const unsigned long long tps_mask = (1ull << A.log_tiles_per_state) - 1ull;
+  const uint32_t* hf = hi_flat + ((2 * tid) >> L);
+  const int hstep = (2 * NT) >> L;  // hi_flat entries per u step
+  __syncthreads();                  // hi_flat and grp ready
 
   long long cur_batch = -1;
-  auto issue_load = [&](unsigned long long tile_global, int which) {
-    float2* buf = reinterpret_cast<float2*>(smem_raw + (size_t)which * TILE_BYTES);
-    const unsigned long long b = tile_global >> A.log_tiles_per_state;
-    const uint64_t base = tile_base(tile_global & tps_mask, hdr);
-    const float2* src_b = A.src + ((size_t)b << A.nbits) + (base | (uint64_t)(tid & lowmask));
-    const uint64_t* hf = hi_flat + (tid >> L);
-    const int hstep = NT >> L;  // hi_flat entries per u step
-    uint64_t off[N_LD];
-#pragma unroll
-    for (int u = 0; u < N_LD; ++u) off[u] = hf[u * hstep];
-#pragma unroll
-    for (int u = 0; u < N_LD; ++u) cp_async8(buf + (ld_s0 ^ swz(NT * u)), src_b + off[u]);
-    cp_async_commit();
-  };
-
-  unsigned long long tg = blockIdx.x;
-  __syncthreads();  // hi_flat ready
-  if (tg < A.total_tiles) issue_load(tg, 0);
-
-  for (int k = 0; tg < A.total_tiles; ++k, tg += gridDim.x) {
-    float2* tile = reinterpret_cast<float2*>(smem_raw + (size_t)(k & 1) * TILE_BYTES);
+  for (unsigned long long tg = blockIdx.x; tg < A.total_tiles; tg += gridDim.x) {
     const long long b = (long long)(tg >> A.log_tiles_per_state);
     const uint64_t base = tile_base(tg & tps_mask, hdr);
     const uint64_t cta_bits = base | A.index_base;
     const float2* gates = A.gatebuf + (size_t)b * A.gate_bstride;
     PROF_DECL
+    // ---- load: 16-byte cp.async straight into the swizzled tile (no registers held) ----
+    {
+      const float2* src_b = A.src + ((size_t)b << A.nbits) + (base | (uint64_t)((2 * tid) & lowmask));
+      uint64_t off[N_IO];
+#pragma unroll
+      for (int u = 0; u < N_IO; ++u) off[u] = (uint64_t)hf[u * hstep] << L;
+#pragma unroll
+      for (int u = 0; u < N_IO; ++u) cp_async16(tile + (io_s0 ^ swz(2 * NT * u)), src_b + off[u]);
+      cp_async_commit();
+    }
+    PROF_MARK(0);
+    // ---- while the tile streams in: resolve the fill records (shared memory only) ----
     if (b != cur_batch) {  // (re)stage the gate pool of this batch element
       for (int e = 0; e < npool; ++e) {
         const int goff = pooltab[3 * e], cnt = pooltab[3 * e + 1], poff = pooltab[3 * e + 2];
@@ -171,26 +205,22 @@ __global__ void __launch_bounds__(1 << LT, 1) pass_kernel(const PassArgs A) {
       }
       cur_batch = b;
       __syncthreads();
-      // records that do not depend on tile bits (fused 1q products, ...): once per batch element
-      prologue_fill(sprog, A.prog_words, pool, 0, warp, lane, NWARPS, 0, nstatic);
+      // records that do not depend on tile bits (fused 1q products, tables, ...): once per batch element
+      prologue_fill_warps(sprog, A.prog_words, pool, 0, warp, lane, NWARPS, 0, nstatic);
     }
-    // resolve the tile-dependent fill records (shared memory only)
-    PROF_MARK(0);
-    prologue_fill(sprog, A.prog_words, pool, cta_bits, warp, lane, NWARPS, nstatic, nfill);
+    prologue_fill_threads(sprog, A.prog_words, pool, cta_bits, tid, NT, nstatic, nshort_end);
+    prologue_fill_warps(sprog, A.prog_words, pool, cta_bits, warp, lane, NWARPS, nshort_end, nfill);
     PROF_MARK(1);
-    // tile k has landed; everybody is done with the other buffer (barrier at the end of k-1)
     cp_async_wait_all();
     __syncthreads();
     PROF_MARK(2);
-    if (tg + gridDim.x < A.total_tiles) issue_load(tg + gridDim.x, (k + 1) & 1);
-    PROF_MARK(3);
 
     // ---- sub-passes ----
-    const int nsub = hdr[H_NSUB];
     const int32_t* sp = hdr + HDR_WORDS;
     for (int s = 0; s < nsub; ++s) {
       if (sp[S_KIND] == SUB_REG) {
-        run_reg_subpass<R>(tile, hdr, sp, tid, cta_bits, hi_flat);  // 2^(T-R) groups == NT threads
+        const int tbase = grp[s * GRP_STRIDE + lane] | grp[s * GRP_STRIDE + 32 + warp];
+        run_reg_subpass<R>(tile, sp, tbase, cta_bits);  // 2^(T-R) groups == NT threads
       } else {
         run_smem_dense(tile, hdr, sp, gates, tid, NT);
       }
@@ -202,34 +232,42 @@ __global__ void __launch_bounds__(1 << LT, 1) pass_kernel(const PassArgs A) {
     // ---- store ----
     {
       float2* dst_b = A.dst + ((size_t)b << A.nbits) + (base | (uint64_t)((2 * tid) & lowmask));
-      const uint64_t* hf = hi_flat + ((2 * tid) >> L);
-      const int hstep = (2 * NT) >> L;
-      uint64_t off[N_ST];
-      float2 x[N_ST], y[N_ST];
+      uint64_t off[N_IO];
+      float4 v[N_IO];
 #pragma unroll
-      for (int u = 0; u < N_ST; ++u) {
-        const int sa = st_s0 ^ swz(2 * NT * u);
-        off[u] = hf[u * hstep];
-        x[u] = tile[sa];
-        y[u] = tile[sa ^ 1];
+      for (int u = 0; u < N_IO; ++u) {
+        off[u] = (uint64_t)hf[u * hstep] << L;
+        v[u] = *reinterpret_cast<const float4*>(tile + (io_s0 ^ swz(2 * NT * u)));
       }
 #pragma unroll
-      for (int u = 0; u < N_ST; ++u)
-        stg_stream(reinterpret_cast<float4*>(dst_b + off[u]), make_float4(x[u].x, x[u].y, y[u].x, y[u].y));
+      for (int u = 0; u < N_IO; ++u) stg_stream(reinterpret_cast<float4*>(dst_b + off[u]), v[u]);
     }
     PROF_MARK(5);
-    __syncthreads();  // the buffer and sprog may be overwritten from here on
+    __syncthreads();  // the tile and sprog may be overwritten from here on
     PROF_MARK(6);
   }
 }
 
-static size_t pass_smem_bytes(int T, int L, int prog_words, int poolsize) {
-  return ((size_t)16 << T) + ((size_t)8 << (T - L)) + (((size_t)poolsize * 8 + 15) & ~(size_t)15) +
-         (size_t)prog_words * 4;
+template <int LT>
+static int launch_pass_lt(const PassArgs& a, uint64_t tiles_total, size_t smem, cudaStream_t stream) {
+  constexpr int MINB = (512 >> LT) < 1 ? 1 : ((512 >> LT) > 8 ? 8 : (512 >> LT));  // <= 128 registers / thread
+  static bool attr_set = false;
+  if (!attr_set) {
+    TCB_CHECK_CUDA(cudaFuncSetAttribute(pass_kernel<PASS_R, LT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+    attr_set = true;
+  }
+  // persistent CTAs: as many per SM as shared memory and the register file (MINB) allow
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > MINB ? MINB : per_sm);
+  uint64_t grid = (uint64_t)sm_count() * per_sm;
+  if (grid > tiles_total) grid = tiles_total;
+  pass_kernel<PASS_R, LT, MINB><<<(unsigned)grid, 1 << LT, smem, stream>>>(a);
+  return 0;
 }
 
 int launch_pass(const void* src, void* dst, int nbits, int64_t batch, const int32_t* program,
-                int32_t program_words, int tile_bits, int low_bits, const void* gatebuf,
+                int32_t program_words, int tile_bits, int low_bits, int pool_elems, const void* gatebuf,
                 int64_t gate_batch_stride, uint64_t index_base, cudaStream_t stream) {
   TCB_REQUIRE(tile_bits >= PASS_R + 5 && tile_bits <= PASS_MAX_T && tile_bits <= nbits,
               "tcb_sv_run_pass: tile_bits=%d out of range [%d,%d] (nbits=%d)", tile_bits,
@@ -237,25 +275,15 @@ int launch_pass(const void* src, void* dst, int nbits, int64_t batch, const int3
   TCB_REQUIRE(low_bits >= 1 && low_bits <= 5, "tcb_sv_run_pass: bad low_bits=%d (1..5)", low_bits);
   TCB_REQUIRE(program_words >= HDR_WORDS && program_words <= PASS_MAX_WORDS,
               "tcb_sv_run_pass: program_words=%d out of range", program_words);
+  TCB_REQUIRE(pool_elems >= 0 && pool_elems <= PASS_MAX_POOL, "tcb_sv_run_pass: pool_elems=%d out of range",
+              pool_elems);
   TCB_REQUIRE(batch >= 1, "tcb_sv_run_pass: batch must be >= 1");
+  TCB_REQUIRE(nbits - low_bits <= 32, "tcb_sv_run_pass: nbits - low_bits must be <= 32");
   const uint64_t tiles = 1ull << (nbits - tile_bits);
   const uint64_t total = tiles * (uint64_t)batch;
   const int lt = tile_bits - PASS_R;
-  // worst-case pool (the exact size is in the program header, which lives on the device)
-  const size_t smem = pass_smem_bytes(tile_bits, low_bits, program_words, PASS_MAX_POOL);
+  const size_t smem = pass_smem_layout(tile_bits, low_bits, program_words, pool_elems).total;
   TCB_REQUIRE(smem <= 200 * 1024, "tcb_sv_run_pass: shared memory %zu too large", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TCB_CHECK_CUDA(cudaFuncSetAttribute(pass_kernel<PASS_R, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TCB_CHECK_CUDA(cudaFuncSetAttribute(pass_kernel<PASS_R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TCB_CHECK_CUDA(cudaFuncSetAttribute(pass_kernel<PASS_R, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TCB_CHECK_CUDA(cudaFuncSetAttribute(pass_kernel<PASS_R, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TCB_CHECK_CUDA(cudaFuncSetAttribute(pass_kernel<PASS_R, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  const int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
-  uint64_t grid = (uint64_t)sm_count() * (ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm));
-  if (grid > total) grid = total;
   PassArgs a;
   a.src = reinterpret_cast<const float2*>(src);
   a.dst = reinterpret_cast<float2*>(dst);
@@ -267,13 +295,14 @@ int launch_pass(const void* src, void* dst, int nbits, int64_t batch, const int3
   a.log_tiles_per_state = nbits - tile_bits;
   a.nbits = nbits;
   a.prog_words = program_words;
+  int rc = 0;
   switch (lt) {
-    case 9: pass_kernel<PASS_R, 9><<<(unsigned)grid, 512, smem, stream>>>(a); break;
-    case 8: pass_kernel<PASS_R, 8><<<(unsigned)grid, 256, smem, stream>>>(a); break;
-    case 7: pass_kernel<PASS_R, 7><<<(unsigned)grid, 128, smem, stream>>>(a); break;
-    case 6: pass_kernel<PASS_R, 6><<<(unsigned)grid, 64, smem, stream>>>(a); break;
-    default: pass_kernel<PASS_R, 5><<<(unsigned)grid, 32, smem, stream>>>(a); break;
+    case 8: rc = launch_pass_lt<8>(a, total, smem, stream); break;
+    case 7: rc = launch_pass_lt<7>(a, total, smem, stream); break;
+    case 6: rc = launch_pass_lt<6>(a, total, smem, stream); break;
+    default: rc = launch_pass_lt<5>(a, total, smem, stream); break;
   }
+  if (rc) return rc;
   TCB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

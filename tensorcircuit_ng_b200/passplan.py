@@ -13,14 +13,18 @@ gate on each of its qubits has been scheduled.  For a pass we pick T tile bits (
 lowest index bits are always in, for coalescing) so that as many ready gates as
 possible become applicable:
 
-    diagonal 1q/2q gates ........ always applicable (their non-tile bits are CTA constants)
+    diagonal 1q/2q gates ........ applicable when ONE of their qubits is a tile bit (the partner may
+                                  be a CTA constant).  They are scheduled lazily: a diagonal gate is
+                                  attached to a round in which one of its qubits is a register bit,
+                                  and otherwise left for a later pass
     dense 1q .................... its qubit must be a tile bit
     controlled-1q (1-2 ctrls) ... the *target* must be a tile bit, controls may be anywhere
     dense 2..4q ................. all qubits in the tile (shared-memory sub-pass)
     anything else ............... its own unfused launch (`GlobalStep`)
 
 Inside a pass the scheduled gates are cut into register sub-passes of R = 5 tile bits
-by the same greedy rule.  Pure host code (numpy only) — unit-tested on CPU against the
+(slot 0 is always tile bit 0, so shared memory is accessed in 16-byte amplitude pairs) by the
+same greedy rule.  Pure host code (numpy only) — unit-tested on CPU against the
 oracle through the kernel-logic emulator in tests/emu/.
 """
 
@@ -32,24 +36,24 @@ from typing import Any, Dict, List, Optional, Sequence, Set, Tuple
 import numpy as np
 
 # ---- word layout: keep in sync with csrc/pass_core.cuh -------------------------------
-PASS_MAGIC = 0x7CB20003
+PASS_MAGIC = 0x7CB20004
 PASS_MAX_T = 13
-PASS_R = 4
+PASS_R = 5
 PASS_MAX_WORDS = 6144
+PASS_MAX_SUB = 16
 H_MAGIC, H_T, H_L, H_NSUB, H_WORDS, H_NNONTILE, H_R, H_NFILL = 0, 1, 2, 3, 4, 5, 6, 7
-H_NPOOL, H_POOLSIZE, H_NFILL_STATIC = 64, 65, 66
+H_NPOOL, H_POOLSIZE, H_NFILL_STATIC, H_NFILL_SHORT_END = 64, 65, 66, 67
+FILL_SHORT = 4
 PASS_MAX_POOL = 1536
 H_TILEPOS, H_NONTILEPOS, HDR_WORDS = 8, 24, 80
 S_NROUNDS, S_KIND, S_REGBITS, S_GRPBITS, S_WORDS, SUB_HDR_WORDS = 0, 1, 2, 10, 22, 24
 SUB_REG, SUB_SMEM_DENSE = 0, 1
-RD_FLAGS, RD_FMASK, RD_NNN, RD_NRR, RD_NRJ, RD_WORDS, RD_CTRL, RD_M, RD_C, RD_F, RD_FIXED = (
-    0, 1, 2, 3, 4, 9, 10, 20, 60, 64, 120,
-)  # fmt: skip
+RD_FLAGS, RD_NRR, RD_WORDS, RD_NRJ, RD_CTRL, RD_M, RD_F, RD_FIXED = 0, 1, 2, 3, 8, 20, 60, 80
 TT_A, TT_B, TT_W, TT_WORDS = 0, 1, 4, 12
 OP_WORDS = 16
 OP_DENSE = 5
-FK_SCALAR, FK_PAIR, FK_TABLE, FK_MATRIX = 0, 1, 2, 3
-FF_D1, FF_D2_FIRST, FF_D2_SECOND, FF_S1, FF_S2, FF_T, FF_T_SWAP, FF_M, FF_MD = range(9)
+FK_PAIR, FK_TABLE, FK_MATRIX = 1, 2, 3
+FF_D1, FF_D2_FIRST, FF_D2_SECOND, FF_T, FF_T_SWAP, FF_M, FF_MD = 0, 1, 2, 5, 6, 7, 8
 MIN_PASS_BITS = PASS_R + 5  # smallest state the tile kernel accepts
 _ONE = int(np.float32(1.0).view(np.int32))
 
@@ -77,6 +81,7 @@ class PassStep:
     low_bits: int
     gate_ids: List[int]
     n_subpasses: int
+    pool_elems: int = 0  # complex elements of the shared-memory gate pool (sizes the launch)
 
 
 @dataclass
@@ -104,7 +109,13 @@ def _applicable(g: GateOp, pos_of: Sequence[int], inside: Set[int], max_dense: i
     """How gate g can run when the bit positions `inside` are resident; None if it cannot."""
     kind = g.kind[0]
     if kind in ("diag", "diagvec"):
-        return "diag" if g.k <= 2 else None
+        # lazily scheduled: one of its qubits must be resident (the gate becomes per-thread data of
+        # the round that owns that bit, pass_core.cuh); a partner outside is a CTA / thread constant
+        if g.k <= 2:
+            nin = sum(1 for q in g.qubits if pos_of[q] in inside)
+            if nin:
+                return "diag2" if nin == 2 else "diag"
+        return None
     if kind == "ctrl":
         nctrl = g.kind[1]
         if nctrl <= 2 and g.k == nctrl + 1:
@@ -139,6 +150,28 @@ class _Frontier:
                 return False
         return True
 
+    def heads(self) -> List[int]:
+        """Ready gates (head of every queue they sit in), ascending."""
+        out = set()
+        for q, qq in enumerate(self.queues):
+            if self.ptr[q] < len(qq) and self.ready(qq[self.ptr[q]], self.ptr):
+                out.add(qq[self.ptr[q]])
+        return sorted(out)
+
+    def commit(self, done: Sequence[int]) -> None:
+        """Mark `done` (a per-qubit prefix-closed set of pending gates) as executed."""
+        dset = set(done)
+        for gi in done:
+            for q in self.gates[gi].qubits:
+                assert self.queues[q][self.ptr[q]] in dset, "planner invariant: executed set is not prefix closed"
+        cnt = [0] * len(self.queues)
+        for gi in done:
+            for q in self.gates[gi].qubits:
+                cnt[q] += 1
+        for q, c in enumerate(cnt):
+            self.ptr[q] += c
+        self.remaining -= len(done)
+
     def simulate(self, inside: Set[int], pos_of: Sequence[int], max_dense: int, limit: int,
                  commit: bool = False, allow: Optional[Set[int]] = None) -> List[Tuple[int, str]]:  # fmt: skip
         """Greedily run every gate that is ready and applicable; returns [(gate index, how)]."""
@@ -170,21 +203,30 @@ class _Frontier:
         return out
 
 
-def _score(sched: List[Tuple[int, str]]) -> float:
-    # diagonal gates are (nearly) free riders; what a pass buys is dense work
-    return sum(1.0 if how != "diag" else 0.05 for _, how in sched)
+_RR_PENALTY = -0.75
+
+
+def _score(sched: List[Tuple[int, str]], rr: float = 0.05) -> float:
+    """What a resident bit set buys is dense work; diagonal gates are (nearly) free riders — except,
+    at the register level (rr < 0), a 2q diagonal with BOTH qubits in registers, which costs a
+    per-amplitude multiply instead of a per-thread one."""
+    tot = 0.0
+    for _, how in sched:
+        tot += 0.05 if how == "diag" else (rr if how == "diag2" else 1.0)
+    return tot
 
 
 def _grow(front: _Frontier, pos_of: Sequence[int], start: Set[int], size: int, candidates: Sequence[int],
-          max_dense: int, limit: int, allow: Optional[Set[int]] = None) -> Set[int]:  # fmt: skip
+          max_dense: int, limit: int, allow: Optional[Set[int]] = None, rr: float = 0.05,
+          fill: bool = True) -> Set[int]:  # fmt: skip
     """Greedy growth of the resident bit set up to `size` bits."""
     inside = set(start)
     cands = [c for c in candidates if c not in inside]
     while len(inside) < size and cands:
-        base = _score(front.simulate(inside, pos_of, max_dense, limit, allow=allow))
+        base = _score(front.simulate(inside, pos_of, max_dense, limit, allow=allow), rr)
         best, best_gain = None, 0.0
         for c in cands:
-            gain = _score(front.simulate(inside | {c}, pos_of, max_dense, limit, allow=allow)) - base
+            gain = _score(front.simulate(inside | {c}, pos_of, max_dense, limit, allow=allow), rr) - base
             if gain > best_gain + 1e-9:
                 best, best_gain = c, gain
         if best is None:
@@ -215,34 +257,52 @@ def _grow(front: _Frontier, pos_of: Sequence[int], start: Set[int], size: int, c
         else:
             inside.add(best)
             cands.remove(best)
-    # fill up with arbitrary candidates (keeps the kernel's fixed geometry)
-    for c in cands:
-        if len(inside) >= size:
-            break
-        inside.add(c)
+    # fill up with candidates that unlock nothing (keeps the kernel's fixed geometry)
+    if fill:
+        base = front.simulate(inside, pos_of, max_dense, limit, allow=allow)
+        for c in cands:
+            if len(inside) >= size:
+                break
+            if len(front.simulate(inside | {c}, pos_of, max_dense, limit, allow=allow)) == len(base):
+                inside.add(c)
+        for c in cands:
+            if len(inside) >= size:
+                break
+            inside.add(c)
     return inside
 
 
 def _order_group_bits(nonreg: List[int]) -> List[int]:
-    """Order the non-register tile bits so the 4 lowest thread-id bits land on distinct
-    residues mod 4 (conflict-free under the XOR-fold swizzle of pass_core.cuh::swz)."""
+    """Order the non-register tile bits so the 3 lowest thread-id bits (a quarter warp = one
+    LDS.128 wavefront) land on the 3 distinct chunk classes of pass_core.cuh::swz, (b - 1) mod 3."""
     rest = sorted(nonreg)
     first: List[int] = []
     used = set()
     for b in rest:
-        if b % 4 not in used and len(first) < 4:
+        if (b - 1) % 3 not in used and len(first) < 3:
             first.append(b)
-            used.add(b % 4)
+            used.add((b - 1) % 3)
     tail = [b for b in rest if b not in first]
     return first + tail
 
 
-def _dense_dim(g: GateOp) -> int:
-    return 1 << g.k
+def terminal_diagonals(gates: Sequence[GateOp], nq: int) -> Set[int]:
+    """Diagonal gates with no later non-diagonal gate on any of their qubits (never worth deferring)."""
+    later_dense = [False] * nq
+    out: Set[int] = set()
+    for gi in range(len(gates) - 1, -1, -1):
+        g = gates[gi]
+        if g.is_diag:
+            if not any(later_dense[q] for q in g.qubits):
+                out.add(gi)
+        else:
+            for q in g.qubits:
+                later_dense[q] = True
+    return out
 
 
 def compile_plan(gates: Sequence[GateOp], nqubits: int, *, nbits_local: Optional[int] = None,
-                 tile_bits: int = PASS_MAX_T, low_bits: int = 4, max_ops_per_pass: int = 200,
+                 tile_bits: int = 12, low_bits: int = 4, max_ops_per_pass: int = 200,
                  lookahead: int = 512) -> Plan:  # fmt: skip
     """Compile a gate stream.  `nbits_local` < nqubits describes a sharded state whose top
     (nqubits - nbits_local) qubits are global: only diagonal gates / controls may touch them."""
@@ -253,6 +313,7 @@ def compile_plan(gates: Sequence[GateOp], nqubits: int, *, nbits_local: Optional
             g.gid = gi
     steps: List[Any] = []
     front = _Frontier(gates, nqubits)
+    terminal = terminal_diagonals(gates, nqubits)
     use_pass = nbits >= MIN_PASS_BITS
     T = min(tile_bits, nbits, PASS_MAX_T)
     L = min(low_bits, T)
@@ -267,9 +328,7 @@ def compile_plan(gates: Sequence[GateOp], nqubits: int, *, nbits_local: Optional
                 "swap it into the local register first (sharded.py)"
             )
         steps.append(GlobalStep(g, bp))
-        for q in g.qubits:
-            front.ptr[q] += 1
-        front.remaining -= 1
+        front.commit([gi])
 
     while front.remaining > 0:
         if not use_pass:
@@ -281,30 +340,33 @@ def compile_plan(gates: Sequence[GateOp], nqubits: int, *, nbits_local: Optional
         start = set(range(L))
         inside = _grow(front, pos_of, start, T, local_positions, 4, lookahead)
         sched = front.simulate(inside, pos_of, 4, max_ops_per_pass)
-        if _score(sched) < 0.5 and all(how == "diag" for _, how in sched):
-            # no dense work can be unlocked by any tile: the earliest blocked gate goes unfused
-            blocked = [
-                front.queues[q][front.ptr[q]]
-                for q in range(nqubits)
-                if front.ptr[q] < len(front.queues[q])
-            ]
-            blocked = [gi for gi in blocked if front.ready(gi, front.ptr)]
-            hard = [gi for gi in blocked if _applicable(gates[gi], pos_of, set(local_positions), 4) is None]
-            if hard and not sched:
-                emit_global(min(hard))
-                continue
-            if not sched:
+        if not sched:
+            # nothing can run inside any tile: the earliest ready gate goes unfused (k >= 5 dense
+            # gates, diagonal gates on global qubits only, k >= 3 diagonals)
+            heads = front.heads()
+            if not heads:
                 raise RuntimeError("pass planner stalled")  # pragma: no cover
+            emit_global(heads[0])
+            continue
         # the program must fit the kernel's shared-memory budget: shrink the pass until it does
         limit = max_ops_per_pass
+        step = None
         while True:
             sched = front.simulate(inside, pos_of, 4, limit)
             try:
-                step = _build_pass(gates, sched, nbits, pos_of, sorted(inside), L)
+                step, done = _build_pass(gates, sched, nbits, pos_of, sorted(inside), L, terminal)
+                if not done:  # everything was deferred: apply the diagonal gates right here
+                    step, done = _build_pass(gates, sched, nbits, pos_of, sorted(inside), L, None)
                 break
             except _ProgramTooLarge:
+                if len(sched) <= 1:
+                    raise
                 limit = max(1, int(len(sched) * 0.7))
-        front.simulate(inside, pos_of, 4, len(sched), commit=True)
+        if not done:
+            heads = front.heads()
+            emit_global(heads[0])
+            continue
+        front.commit(done)
         steps.append(step)
     return Plan(nbits=nbits, steps=steps, n_gates=len(gates))
 
@@ -338,7 +400,17 @@ class _Round:
     def __init__(self) -> None:
         self.gate: List[Optional[Dict[str, Any]]] = [None] * PASS_R
         self.ctrl_regs: Set[int] = set()
-        self.diag: List[GateOp] = []
+        # diagonal part (applied BEFORE the gates of the round)
+        self.pair_src: List[List[int]] = [[] for _ in range(PASS_R)]  # fill sources of slot J's factor
+        self.rj: List[List[Tuple[int, GateOp, int]]] = [[] for _ in range(PASS_R)]  # (partner tile bit, gate, form)
+        self.rr: List[Tuple[int, int, GateOp]] = []  # (slot of first qubit, slot of second qubit, gate)
+
+    def has_factor(self, j: int) -> bool:
+        return bool(self.pair_src[j]) or bool(self.rj[j])
+
+    def empty(self) -> bool:
+        return (all(x is None for x in self.gate) and not self.rr
+                and not any(self.has_factor(j) for j in range(PASS_R)))  # fmt: skip
 
 
 def _diag_stride(g: GateOp) -> int:
@@ -346,29 +418,57 @@ def _diag_stride(g: GateOp) -> int:
 
 
 def _build_rounds(sub_gates: Sequence[GateOp], run: List[Tuple[int, str]], pos_of: Sequence[int],
-                  reg_idx: Dict[int, int]) -> List[_Round]:  # fmt: skip
-    """Cut the ordered gate list of one register sub-pass into rounds (pass_core.cuh: a round is a
-    diagonal part followed by at most one fused 2x2 per register bit)."""
+                  reg_idx: Dict[int, int], tbit_of_pos: Dict[int, int], pool: _Pool) -> List[_Round]:  # fmt: skip
+    """Cut the ordered gate list of one register sub-pass into rounds (pass_core.cuh: a round is, per
+    register slot, an optional diagonal factor followed by at most one fused 2x2)."""
     rounds: List[_Round] = [_Round()]
+
+    def fresh() -> _Round:
+        r = _Round()
+        rounds.append(r)
+        return r
+
     for gi, how in run:
         g = sub_gates[gi]
         cur = rounds[-1]
-        if how == "diag":
-            touches = [reg_idx[pos_of[q]] for q in g.qubits if pos_of[q] in reg_idx]
-            if g.k == 1 and touches and cur.gate[touches[0]] is not None and cur.gate[touches[0]]["ctrl"] is None \
-                    and touches[0] not in cur.ctrl_regs:
-                # 1q diagonal right after dense gate(s) on the same register bit: same 2x2 product
-                cur.gate[touches[0]]["fusion"].append((g, 0, FF_MD, _diag_stride(g)))
+        if how in ("diag", "diag2"):
+            st = _diag_stride(g)
+            ps = [pos_of[q] for q in g.qubits]
+            slots = [reg_idx.get(p) for p in ps]
+            if g.k == 1:
+                j = slots[0]
+                assert j is not None
+                gt = cur.gate[j]
+                if gt is not None and gt["ctrl"] is None and j not in cur.ctrl_regs:
+                    # 1q diagonal right after dense gate(s) on the same slot: same 2x2 product
+                    gt["fusion"].append((g, 0, FF_MD, st))
+                    continue
+                if gt is not None:
+                    cur = fresh()
+                cur.pair_src[j].extend([pool.ref(g), FF_D1 | (st << 8), 0, 0])
                 continue
-            if any(cur.gate[j] is not None for j in touches):
-                cur = _Round()
-                rounds.append(cur)
-            cur.diag.append(g)
+            if slots[0] is not None and slots[1] is not None:
+                if cur.gate[slots[0]] is not None or cur.gate[slots[1]] is not None:
+                    cur = fresh()
+                cur.rr.append((slots[0], slots[1], g))
+                continue
+            own = 0 if slots[0] is not None else 1  # which gate qubit is the register bit
+            j = slots[own]
+            assert j is not None
+            if cur.gate[j] is not None:
+                cur = fresh()
+            pp = ps[1 - own]
+            if pp in tbit_of_pos:  # thread-constant partner: one LDS.128 lookup per thread
+                # W = [x_B=0: (d[x_A=0], d[x_A=1])], [x_B=1: ...]; A is the register bit
+                form = FF_T_SWAP if own == 0 else FF_T
+                cur.rj[j].append((tbit_of_pos[pp], g, form))
+            else:  # CTA-constant partner: resolved per tile by the prologue
+                form = FF_D2_FIRST if own == 0 else FF_D2_SECOND
+                cur.pair_src[j].extend([pool.ref(g), form | (st << 8), pp, 0])
         elif how == "1q":
             j = reg_idx[pos_of[g.qubits[0]]]
             if (cur.gate[j] is not None and cur.gate[j]["ctrl"] is not None) or j in cur.ctrl_regs:
-                cur = _Round()
-                rounds.append(cur)
+                cur = fresh()
             if cur.gate[j] is None:
                 cur.gate[j] = {"fusion": [], "ctrl": None}
             cur.gate[j]["fusion"].append((g, 0, FF_M, 2))
@@ -376,7 +476,7 @@ def _build_rounds(sub_gates: Sequence[GateOp], run: List[Tuple[int, str]], pos_o
             nctrl, pol = g.kind[1], g.kind[2]
             j = reg_idx[pos_of[g.qubits[-1]]]
             cmask = cwant = 0
-            tcs: List[Tuple[int, int]] = []
+            tcs: List[int] = []
             regs: Set[int] = set()
             for ci in range(nctrl):
                 want = (pol >> ci) & 1
@@ -386,11 +486,12 @@ def _build_rounds(sub_gates: Sequence[GateOp], run: List[Tuple[int, str]], pos_o
                     cmask |= 1 << k
                     cwant |= want << k
                     regs.add(k)
+                elif p in tbit_of_pos:
+                    tcs.append(tbit_of_pos[p] | 0x80 | (want << 8))
                 else:
-                    tcs.append((p, want))
+                    tcs.append(p | (want << 8))
             if cur.gate[j] is not None or j in cur.ctrl_regs or any(cur.gate[k] is not None for k in regs):
-                cur = _Round()
-                rounds.append(cur)
+                cur = fresh()
             D = 1 << g.k
             polval = 0
             for ci in range(nctrl):
@@ -400,21 +501,19 @@ def _build_rounds(sub_gates: Sequence[GateOp], run: List[Tuple[int, str]], pos_o
             cur.ctrl_regs |= regs
         else:  # pragma: no cover
             raise AssertionError(how)
-    return [r for r in rounds if r.diag or any(x is not None for x in r.gate)]
+    return [r for r in rounds if not r.empty()]
 
 
-def _emit_round(words: List[int], fills: List[List[int]], rnd: _Round, pos_of: Sequence[int],
-                reg_idx: Dict[int, int], tbit_of_pos: Dict[int, int], pool: _Pool) -> None:  # fmt: skip
+def _emit_round(words: List[int], fills: List[List[int]], rnd: _Round, pool: _Pool) -> None:
     base = len(words)
+    assert base % 4 == 0
     rec = [0] * RD_FIXED
     flags = 0
     for j in range(PASS_R):
         rec[RD_M + 8 * j] = _ONE  # identity defaults (overwritten by the device prologue)
         rec[RD_M + 8 * j + 6] = _ONE
-    rec[RD_C] = _ONE
-    for b in range(13):
-        rec[RD_F + 4 * b] = _ONE
-        rec[RD_F + 4 * b + 2] = _ONE
+        rec[RD_F + 4 * j] = _ONE
+        rec[RD_F + 4 * j + 2] = _ONE
     for j, gt in enumerate(rnd.gate):
         if gt is None:
             continue
@@ -430,79 +529,66 @@ def _emit_round(words: List[int], fills: List[List[int]], rnd: _Round, pos_of: S
             w0 = c["cmask"] | (c["cwant"] << 8) | (len(tcs) << 16)
             w1 = 0
             if len(tcs) > 0:
-                w1 |= tcs[0][0] | (tcs[0][1] << 7)
+                w1 |= tcs[0]
             if len(tcs) > 1:
-                w1 |= (tcs[1][0] << 8) | (tcs[1][1] << 15)
+                w1 |= tcs[1] << 16
             rec[RD_CTRL + 2 * j] = w0
             rec[RD_CTRL + 2 * j + 1] = w1
-    # diagonal part: classify every gate against (non-tile | thread-constant tile | register) bits
-    scalar_src: List[int] = []
-    pair_src: Dict[int, List[int]] = {}
-    nn: List[Tuple[int, int, GateOp, int]] = []
-    rj: List[List[Tuple[int, int, GateOp, int]]] = [[] for _ in range(PASS_R)]
-    rr: List[Tuple[int, int, GateOp, int]] = []
-    for g in rnd.diag:
-        st = _diag_stride(g)
-        ps = [pos_of[q] for q in g.qubits]
-        in_tile = [p in tbit_of_pos for p in ps]
-        if g.k == 1:
-            if in_tile[0]:
-                pair_src.setdefault(tbit_of_pos[ps[0]], []).extend([pool.ref(g), FF_D1 | (st << 8), 0, 0])
-            else:
-                scalar_src.extend([pool.ref(g), FF_S1 | (st << 8), ps[0], 0])
-            continue
-        if not in_tile[0] and not in_tile[1]:
-            scalar_src.extend([pool.ref(g), FF_S2 | (st << 8), ps[0], ps[1]])
-        elif in_tile[0] and not in_tile[1]:
-            pair_src.setdefault(tbit_of_pos[ps[0]], []).extend([pool.ref(g), FF_D2_FIRST | (st << 8), ps[1], 0])
-        elif in_tile[1] and not in_tile[0]:
-            pair_src.setdefault(tbit_of_pos[ps[1]], []).extend([pool.ref(g), FF_D2_SECOND | (st << 8), ps[0], 0])
-        else:
-            ra, rb = ps[0] in reg_idx, ps[1] in reg_idx
-            if ra and rb:
-                rr.append((reg_idx[ps[0]], reg_idx[ps[1]], g, FF_T))
-            elif ra:
-                rj[reg_idx[ps[0]]].append((reg_idx[ps[0]], tbit_of_pos[ps[1]], g, FF_T))
-            elif rb:
-                rj[reg_idx[ps[1]]].append((reg_idx[ps[1]], tbit_of_pos[ps[0]], g, FF_T_SWAP))
-            else:
-                nn.append((tbit_of_pos[ps[0]], tbit_of_pos[ps[1]], g, FF_T))
-    if rnd.diag:
-        flags |= 1 << 16
-    if scalar_src:
-        fills.append([base + RD_C, FK_SCALAR, len(scalar_src) // 4, 0] + scalar_src)
-    fmask = 0
-    for b, src in sorted(pair_src.items()):
-        fmask |= 1 << b
-        fills.append([base + RD_F + 4 * b, FK_PAIR, len(src) // 4, 0] + src)
-    rec[RD_FLAGS] = flags
-    rec[RD_FMASK] = fmask
-    rec[RD_NNN] = len(nn)
-    rec[RD_NRR] = len(rr)
-    tables = list(nn)
+    tables: List[Tuple[int, int, GateOp, int]] = []
     for j in range(PASS_R):
-        rec[RD_NRJ + j] = len(rj[j])
-        tables += rj[j]
-    tables += rr
+        if rnd.has_factor(j):
+            flags |= 1 << (16 + j)
+        if rnd.pair_src[j]:
+            fills.append([base + RD_F + 4 * j, FK_PAIR, len(rnd.pair_src[j]) // 4, 0] + rnd.pair_src[j])
+        rec[RD_NRJ + j] = len(rnd.rj[j])
+        for tb, g, form in rnd.rj[j]:
+            tables.append((j, tb, g, form))
+    rec[RD_NRR] = len(rnd.rr)
+    for ja, jb, g in rnd.rr:
+        tables.append((ja, jb, g, FF_T))
+    rec[RD_FLAGS] = flags
     rec[RD_WORDS] = RD_FIXED + TT_WORDS * len(tables)
     words.extend(rec)
     for a, b, g, form in tables:
         ent = [0] * TT_WORDS
         ent[TT_A], ent[TT_B] = a, b
-        ent[TT_W], ent[TT_W + 6] = _ONE, _ONE
-        ent[TT_W + 2], ent[TT_W + 4] = _ONE, _ONE
+        for i in range(4):
+            ent[TT_W + 2 * i] = _ONE
         fills.append([len(words) + TT_W, FK_TABLE, 1, 0, pool.ref(g), form | (_diag_stride(g) << 8), 0, 0])
         words.extend(ent)
 
 
+def _needed_prefix(sub_gates: Sequence[GateOp], run: List[Tuple[int, str]], keep_always: Optional[Set[int]],
+                   gids: Sequence[int]) -> List[Tuple[int, str]]:  # fmt: skip
+    """Drop the diagonal gates of `run` that nothing later in the run depends on (they stay pending
+    and ride along, for free, with the next gate on one of their qubits — possibly in a later pass).
+    The kept set is closed under "earlier gate on a shared qubit", so it is a valid schedule."""
+    if keep_always is None:
+        return run
+    needed: Set[int] = set()
+    keep = [False] * len(run)
+    for i in range(len(run) - 1, -1, -1):
+        gi, how = run[i]
+        g = sub_gates[gi]
+        if how != "diag" or gids[gi] in keep_always or any(q in needed for q in g.qubits):
+            keep[i] = True
+            needed.update(g.qubits)
+    return [x for x, k in zip(run, keep) if k]
+
+
 def _build_pass(gates: Sequence[GateOp], sched: List[Tuple[int, str]], nbits: int, pos_of: Sequence[int],
-                tile_pos: List[int], L: int) -> PassStep:  # fmt: skip
+                tile_pos: List[int], L: int, terminal: Optional[Set[int]]) -> Tuple[PassStep, List[int]]:  # fmt: skip
+    """Returns the pass and the indices (into `gates`) of the gates it executes.  `terminal` = the
+    diagonal gates that must not be deferred (None: defer nothing)."""
     T = len(tile_pos)
     tbit_of_pos = {p: i for i, p in enumerate(tile_pos)}
+    assert tile_pos[0] == 0, "tile bit 0 must be flat bit 0 (register slot 0)"
     nq = len(pos_of)
     sub_gates = [gates[gi] for gi, _ in sched]
+    gids = [gi for gi, _ in sched]
     local = _Frontier(sub_gates, nq)  # frontier over the scheduled gates only
     tile_set = set(tile_pos)
+    done_local: List[int] = []
 
     words: List[int] = [0] * HDR_WORDS
     words[H_MAGIC] = PASS_MAGIC
@@ -519,31 +605,42 @@ def _build_pass(gates: Sequence[GateOp], sched: List[Tuple[int, str]], nbits: in
     fills: List[List[int]] = []
     pool = _Pool()
     nsub = 0
-    while local.remaining > 0:
-        inside = _grow(local, pos_of, set(), PASS_R, tile_pos, 1, 1 << 30)
-        run = local.simulate(inside, pos_of, 1, 1 << 30)
+    while local.remaining > 0 and nsub < PASS_MAX_SUB:
+        inside = _grow(local, pos_of, {0}, PASS_R, tile_pos, 1, 1 << 30, rr=_RR_PENALTY)
+        run = _needed_prefix(sub_gates, local.simulate(inside, pos_of, 1, 1 << 30), terminal, gids)
         if not run:
-            # only dense multi-qubit gates are ready: one shared-memory sub-pass each
-            cand = [local.queues[q][local.ptr[q]] for q in range(nq) if local.ptr[q] < len(local.queues[q])]
-            cand = sorted({gi for gi in cand if local.ready(gi, local.ptr)})
-            g = sub_gates[cand[0]]
-            assert g.k >= 2 and all(pos_of[q] in tile_set for q in g.qubits), "planner invariant"
-            tb = [tbit_of_pos[pos_of[q]] for q in g.qubits] + [0] * 4
-            hdr = [0] * SUB_HDR_WORDS
-            hdr[S_NROUNDS], hdr[S_KIND], hdr[S_WORDS] = 1, SUB_SMEM_DENSE, SUB_HDR_WORDS + OP_WORDS
-            words.extend(hdr)
-            words.extend([OP_DENSE, tb[0], tb[1], g.mat_off, g.k, tb[2], tb[3], 0] + [0] * 8)
-            nsub += 1
-            for q in g.qubits:
-                local.ptr[q] += 1
-            local.remaining -= 1
-            continue
-        run = local.simulate(inside, pos_of, 1, 1 << 30, commit=True)
-        reg_pos = sorted(inside)  # flat bit positions held in registers
+            # no register work is due: a dense multi-qubit gate, if one is ready, takes a
+            # shared-memory sub-pass; diagonal gates that block one are applied right away
+            heads = local.heads()
+            dense = [gi for gi in heads if not sub_gates[gi].is_diag]
+            if dense:
+                g = sub_gates[dense[0]]
+                assert g.k >= 2 and all(pos_of[q] in tile_set for q in g.qubits), "planner invariant"
+                tb = [tbit_of_pos[pos_of[q]] for q in g.qubits] + [0] * 4
+                hdr = [0] * SUB_HDR_WORDS
+                hdr[S_NROUNDS], hdr[S_KIND], hdr[S_WORDS] = 1, SUB_SMEM_DENSE, SUB_HDR_WORDS + OP_WORDS
+                words.extend(hdr)
+                words.extend([OP_DENSE, tb[0], tb[1], g.mat_off, g.k, tb[2], tb[3], 0] + [0] * 8)
+                nsub += 1
+                local.commit([dense[0]])
+                done_local.append(dense[0])
+                continue
+            blocking = [gi for gi in heads if any(
+                any(not sub_gates[x].is_diag for x in local.queues[q][local.ptr[q] + 1:])
+                for q in sub_gates[gi].qubits)]  # fmt: skip
+            if not blocking:
+                break  # only deferred diagonal gates are left: a later pass takes them
+            inside = _grow(local, pos_of, {0}, PASS_R, tile_pos, 1, 1 << 30, allow=set(blocking))
+            run = local.simulate(inside, pos_of, 1, 1 << 30, allow=set(blocking))
+            if not run:
+                break
+        local.commit([gi for gi, _ in run])
+        done_local.extend(gi for gi, _ in run)
+        reg_pos = [0] + sorted(p for p in inside if p != 0)  # slot 0 = flat bit 0 = tile bit 0
         reg_tb = [tbit_of_pos[p] for p in reg_pos]
         reg_idx = {p: j for j, p in enumerate(reg_pos)}
         grp = _order_group_bits([t for t in range(T) if t not in set(reg_tb)])
-        rounds = _build_rounds(sub_gates, run, pos_of, reg_idx)
+        rounds = _build_rounds(sub_gates, run, pos_of, reg_idx, tbit_of_pos, pool)
         hdr_at = len(words)
         hdr = [0] * SUB_HDR_WORDS
         hdr[S_NROUNDS], hdr[S_KIND] = len(rounds), SUB_REG
@@ -553,16 +650,20 @@ def _build_pass(gates: Sequence[GateOp], sched: List[Tuple[int, str]], nbits: in
             hdr[S_GRPBITS + j] = b
         words.extend(hdr)
         for rnd in rounds:
-            _emit_round(words, fills, rnd, pos_of, reg_idx, tbit_of_pos, pool)
+            _emit_round(words, fills, rnd, pool)
         words[hdr_at + S_WORDS] = len(words) - hdr_at
         nsub += 1
     words[H_NSUB] = nsub
-    # fill records, then the table of their offsets (last H_NFILL words)
-    def _is_static(f: List[int]) -> bool:  # no source looks at tile-constant bits
-        return all((f[4 + 4 * i + 1] & 0xFF) not in (FF_D2_FIRST, FF_D2_SECOND, FF_S1, FF_S2) for i in range(f[2]))
+    # fill records [static | dynamic short | dynamic long], then the table of their offsets
+    def _is_static(f: List[int]) -> bool:  # no source looks at CTA-constant bits
+        return all((f[4 + 4 * i + 1] & 0xFF) not in (FF_D2_FIRST, FF_D2_SECOND) for i in range(f[2]))
 
-    fills = [f for f in fills if _is_static(f)] + [f for f in fills if not _is_static(f)]
-    words[H_NFILL_STATIC] = sum(1 for f in fills if _is_static(f))
+    stat = [f for f in fills if _is_static(f)]
+    dyn_short = [f for f in fills if not _is_static(f) and f[2] <= FILL_SHORT]
+    dyn_long = [f for f in fills if not _is_static(f) and f[2] > FILL_SHORT]
+    fills = stat + dyn_short + dyn_long
+    words[H_NFILL_STATIC] = len(stat)
+    words[H_NFILL_SHORT_END] = len(stat) + len(dyn_short)
     offs = []
     for f in fills:
         offs.append(len(words))
@@ -577,5 +678,7 @@ def _build_pass(gates: Sequence[GateOp], sched: List[Tuple[int, str]], nbits: in
     program = np.asarray(words, dtype=np.int64).astype(np.int32)
     if len(program) > PASS_MAX_WORDS or pool.size > PASS_MAX_POOL:
         raise _ProgramTooLarge(f"pass program too large ({len(program)} words)")
-    return PassStep(program=program, tile_bits=T, low_bits=L, gate_ids=[gates[gi].gid for gi, _ in sched],
-                    n_subpasses=nsub)  # fmt: skip
+    done = [gids[gi] for gi in done_local]
+    step = PassStep(program=program, tile_bits=T, low_bits=L, gate_ids=[gates[gi].gid for gi in done],
+                    n_subpasses=nsub, pool_elems=pool.size)  # fmt: skip
+    return step, done

@@ -206,7 +206,7 @@ class CompiledCircuit:
                 prog_ptr = self.programs.data_ptr() + 4 * self.offsets[pi]
                 pi += 1
                 _lib.call("tcb_sv_run_pass", sp, nbits, batch, prog_ptr, len(step.program), step.tile_bits,
-                          step.low_bits, gp, gate_batch_stride, index_base, stream)  # fmt: skip
+                          step.low_bits, step.pool_elems, gp, gate_batch_stride, index_base, stream)  # fmt: skip
             else:
                 g = step.gate
                 bp = _lib.int_array(step.bitpos)
@@ -220,7 +220,7 @@ class CompiledCircuit:
 
 
 _plan_cache: Dict[Any, CompiledCircuit] = {}
-plan_options: Dict[str, Any] = {"tile_bits": passplan.PASS_MAX_T, "low_bits": 4}
+plan_options: Dict[str, Any] = {"tile_bits": 12, "low_bits": 4}
 
 
 def compile_circuit(nq: int, structure: Sequence[Tuple[Tuple[int, ...], Tuple[Any, ...], int]],

@@ -22,7 +22,8 @@ extern "C" int emu_run_pass(float* state_f, int nbits, long long batch, const in
   if (hdr[H_NNONTILE] != nbits - T) return 13;
   const int nthreads = 256;
   const uint64_t tiles = 1ull << (nbits - T);
-  std::vector<float2> tile(1u << T);
+  std::vector<float4> tile4(1u << (T - 1));  // 16-byte aligned
+  float2* tile = reinterpret_cast<float2*>(tile4.data());
   float2* state = reinterpret_cast<float2*>(state_f);
   const float2* gatebuf = reinterpret_cast<const float2*>(gatebuf_f);
   std::vector<int32_t> sprog(prog, prog + prog_words);  // per-"CTA" staged copy of the program
@@ -47,12 +48,11 @@ extern "C" int emu_run_pass(float* state_f, int nbits, long long batch, const in
       for (int s = 0; s < hdr[H_NSUB]; ++s) {
         if (sp[S_KIND] == SUB_REG) {
           const int ngroups = 1 << (T - PASS_R);
-          for (int tid = 0; tid < nthreads; ++tid)
-            for (int g = tid; g < ngroups; g += nthreads)
-              run_reg_subpass<PASS_R>(tile.data(), hdr, sp, g, base | index_base);
+          for (int g = 0; g < ngroups; ++g)
+            run_reg_subpass<PASS_R>(tile, sp, group_to_tile(g, T, PASS_R, sp), base | index_base);
         } else {
           for (int tid = 0; tid < nthreads; ++tid)
-            run_smem_dense(tile.data(), hdr, sp, gates, tid, nthreads);
+            run_smem_dense(tile, hdr, sp, gates, tid, nthreads);
         }
         sp += sp[S_WORDS];
       }

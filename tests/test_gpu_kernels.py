@@ -188,4 +188,4 @@ def test_error_reporting(cuda):
     with pytest.raises(_lib.EngineError, match="null pointer"):
         _lib.call("tcb_sv_init_zero", None, 3, 1, _lib.stream_ptr())
     with pytest.raises(_lib.EngineError, match="tile_bits"):
-        _lib.call("tcb_sv_run_pass", st.data_ptr(), 3, 1, st.data_ptr(), 100, 13, 4, st.data_ptr(), 0, 0, _lib.stream_ptr())
+        _lib.call("tcb_sv_run_pass", st.data_ptr(), 3, 1, st.data_ptr(), 100, 13, 4, 0, st.data_ptr(), 0, 0, _lib.stream_ptr())

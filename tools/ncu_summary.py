@@ -37,5 +37,6 @@ reg = []
 for b in range(0, len(data), B):
     ch = data[b:b+B]; reg.append((sum(d[2] for d in ch), sum(d[1] for d in ch), b))
 for s_, e, b in sorted(reg, reverse=True)[:8]:
-    ch = data[b:b+B]; o = collections.Counter(re.match(r'(@!?U?P\d+\s+)?([A-Z0-9_]+)', d[0]).group(2) for d in ch)
+    if tot_s == 0: break
+    ch = data[b:b+B]; o = collections.Counter((re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", d[0]) or re.match("()(.*)", "x ?")).group(2) for d in ch)
     print(f"  sass[{b:5d}:{b+B:5d}] samples {100*s_/tot_s:4.1f}% exec {100*e/tot_e:4.1f}%  {o.most_common(6)}")

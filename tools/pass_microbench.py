@@ -45,8 +45,8 @@ run("1 zz diag only", [([0, 1], ("diag",), zz(0.2))])
 run("45 zz diag only", [([int(a), int(b)], ("diag",), zz(0.2)) for a, b in (rng.permutation(n)[:2] for _ in range(45))])
 run("45 zz + 5 rx", [([int(a), int(b)], ("diag",), zz(0.2)) for a, b in (rng.permutation(n)[:2] for _ in range(45))] + [([q], ("dense",), rx(0.3)) for q in hi[:5]])
 run("45 zz + 13 rx", [([int(a), int(b)], ("diag",), zz(0.2)) for a, b in (rng.permutation(n)[:2] for _ in range(45))] + [([q], ("dense",), rx(0.3)) for q in hi + lo])
-run("13 rx, T=12", [([q], ("dense",), rx(0.3 + q)) for q in hi[:8] + lo], tile_bits=12)
-run("13 rx, T=11", [([q], ("dense",), rx(0.3 + q)) for q in hi[:7] + lo], tile_bits=11)
+run("13 rx, T=13", [([q], ("dense",), rx(0.3 + q)) for q in hi + lo], tile_bits=13)
+run("12 rx, T=12", [([q], ("dense",), rx(0.3 + q)) for q in hi[:8] + lo], tile_bits=12)
 run("5 rx, L=5", [([q], ("dense",), rx(0.3 + q)) for q in hi[:5]], low_bits=5)
 pass
 run("1 cnot high", [([0, 1], ("ctrl", 1, 1), np.array([[1,0,0,0],[0,1,0,0],[0,0,0,1],[0,0,1,0]], dtype=np.complex64))])
@@ -73,10 +73,12 @@ print(f"tcb_sv_apply_diag (global RMW): {ms:.3f} ms ({16*2**n/ms/1e6:.0f} GB/s)"
 m = torch.eye(2, dtype=torch.complex64, device=dev)
 ms = timeit(lambda: _lib.call("tcb_sv_apply_dense", state.data_ptr(), n, 1, _lib.int_array([20]), 1, m.data_ptr(), 0, _lib.stream_ptr()))
 print(f"tcb_sv_apply_dense k=1 bit 20: {ms:.3f} ms ({16*2**n/ms/1e6:.0f} GB/s)")
-for T in (13, 12, 11):
-    tile_pos = list(range(T)); pos_of = [n - 1 - q for q in range(n)]
-    step = passplan._build_pass([], [], n, pos_of, tile_pos, 4)
-    prog = torch.from_numpy(step.program).to(dev)
-    gb = torch.zeros(4, dtype=torch.complex64, device=dev)
-    ms = timeit(lambda: _lib.call("tcb_sv_run_pass", state.data_ptr(), n, 1, prog.data_ptr(), len(step.program), T, 4, gb.data_ptr(), 0, 0, _lib.stream_ptr()))
-    print(f"empty pass (load->smem->store) T={T}: {ms:.3f} ms ({16*2**n/ms/1e6:.0f} GB/s)")
+for T in (13, 12):
+    for L in (4, 3, 2):
+        for name, hi in (("contiguous", list(range(L, T))), ("scattered", [L + 1 + 2 * i for i in range(T - L)])):
+            tile_pos = list(range(L)) + hi; pos_of = [n - 1 - q for q in range(n)]
+            step, _ = passplan._build_pass([], [], n, pos_of, tile_pos, L, None)
+            prog = torch.from_numpy(step.program).to(dev)
+            gb = torch.zeros(4, dtype=torch.complex64, device=dev)
+            ms = timeit(lambda: _lib.call("tcb_sv_run_pass", state.data_ptr(), n, 1, prog.data_ptr(), len(step.program), T, L, step.pool_elems, gb.data_ptr(), 0, 0, _lib.stream_ptr()))
+            print(f"empty pass (load->smem->store) T={T} L={L} {name}: {ms:.3f} ms ({16*2**n/ms/1e6:.0f} GB/s)")

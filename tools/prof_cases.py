@@ -11,6 +11,7 @@ def rx(t):
 def zz(t): return np.diag(np.exp(-1j * t * np.array([1, -1, -1, 1]))).astype(np.complex64)
 hi = list(range(9)); lo = [n - 1, n - 2, n - 3, n - 4]
 cases = {
+    "rx12": [([q], ("dense",), rx(0.3 + q)) for q in hi[:8] + lo],
     "rx13": [([q], ("dense",), rx(0.3 + q)) for q in hi + lo],
     "rx5": [([q], ("dense",), rx(0.3 + q)) for q in hi[:5]],
     "zz45": [([int(a), int(b)], ("diag",), zz(0.2)) for a, b in (rng.permutation(n)[:2] for _ in range(45))],

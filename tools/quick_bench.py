@@ -49,7 +49,7 @@ for step in plan.steps:
         prog_ptr = cc.programs.data_ptr() + 4 * cc.offsets[pi]; pi += 1
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.call("tcb_sv_run_pass", state.data_ptr(), n, 1, prog_ptr, len(step.program), step.tile_bits, step.low_bits, gatebuf.data_ptr(), 0, 0, _lib.stream_ptr())
+        _lib.call("tcb_sv_run_pass", state.data_ptr(), n, 1, prog_ptr, len(step.program), step.tile_bits, step.low_bits, step.pool_elems, gatebuf.data_ptr(), 0, 0, _lib.stream_ptr())
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         print(f"  pass {pi}: gates {len(step.gate_ids)} subpasses {step.n_subpasses} {ms:.3f} ms  {16*2**n/ms/1e6:.0f} GB/s")
