@@ -89,7 +89,9 @@ constexpr int SUB_HDR_WORDS = 24;
 constexpr int SUB_REG = 0, SUB_SMEM_DENSE = 1;
 // round record (register sub-pass); every float block is 16-byte aligned
 constexpr int RD_FLAGS = 0;   // bit J: gate on register slot J; bit 8+J: that gate has register-resident
-                              // controls; bit 16+J: diagonal factor on slot J
+                              // controls; bit 16+J: diagonal factor on slot J; bit 30: the round needs
+                              // the general path (a controlled gate, a factor without gate, an RR table)
+constexpr int RD_GENERAL = 1 << 30;
 constexpr int RD_NRR = 1;     // # two-bit diagonal tables with both bits in registers
 constexpr int RD_WORDS = 2;   // total words of this round (fixed part + tables)
 constexpr int RD_NRJ = 3;     // [5] # tables with register slot J and a thread-constant tile bit
@@ -142,12 +144,16 @@ struct PackedM {
   float2 m00, n00, m01, n01, m10, n10, m11, n11;  // m = (re, im), n = (-im, re)
 };
 __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+// n = (-im, re) is produced by ONE packed multiply of the swapped entry with (-1, 1): a genuine
+// register pair.  (Built from two scalars, ptxas re-creates the pair with 2 MOVs in front of almost
+// every use instead of keeping it live: +50% instructions in the gate loop.)
+__device__ __forceinline__ float2 rot90(float2 m) { return __fmul2_rn(make_float2(m.y, m.x), make_float2(-1.f, 1.f)); }
 __device__ __forceinline__ PackedM pack_matrix(float2 m00, float2 m01, float2 m10, float2 m11) {
   PackedM p;
-  p.m00 = m00; p.n00 = make_float2(-m00.y, m00.x);
-  p.m01 = m01; p.n01 = make_float2(-m01.y, m01.x);
-  p.m10 = m10; p.n10 = make_float2(-m10.y, m10.x);
-  p.m11 = m11; p.n11 = make_float2(-m11.y, m11.x);
+  p.m00 = m00; p.n00 = rot90(m00);
+  p.m01 = m01; p.n01 = rot90(m01);
+  p.m10 = m10; p.n10 = rot90(m10);
+  p.m11 = m11; p.n11 = rot90(m11);
   return p;
 }
 // (b0, b1) = M (x, y)
@@ -343,7 +349,7 @@ TCB_DEV void apply_1q(float2 (&a)[1 << R], float2 m00, float2 m01, float2 m10, f
 template <int R, int J>
 TCB_DEV void apply_bitdiag(float2 (&a)[1 << R], float2 u0, float2 u1) {
 #if defined(__CUDACC__)
-  const float2 n0 = make_float2(-u0.y, u0.x), n1 = make_float2(-u1.y, u1.x);
+  const float2 n0 = rot90(u0), n1 = rot90(u1);
   TCB_UNROLL
   for (int i = 0; i < (1 << R); ++i) a[i] = ((i >> J) & 1) ? packed_cmul(a[i], u1, n1) : packed_cmul(a[i], u0, n0);
 #else
@@ -352,14 +358,42 @@ TCB_DEV void apply_bitdiag(float2 (&a)[1 << R], float2 u0, float2 u1) {
 #endif
 }
 
-// diagonal table on two register slots j, k (both runtime; rare)
+// diagonal table on two register slots JA < JB (compile-time): a[i] *= d[2 * i_JA + i_JB]
+template <int R, int JA, int JB>
+TCB_DEV void apply_pairdiag_ct(float2 (&a)[1 << R], float2 d00, float2 d01, float2 d10, float2 d11) {
+  if constexpr (JB < R) {
+#if defined(__CUDACC__)
+    const float2 n00 = rot90(d00), n01 = rot90(d01), n10 = rot90(d10), n11 = rot90(d11);
+    TCB_UNROLL
+    for (int i = 0; i < (1 << R); ++i) {
+      const int c = 2 * ((i >> JA) & 1) + ((i >> JB) & 1);
+      a[i] = c == 0 ? packed_cmul(a[i], d00, n00)
+                    : (c == 1 ? packed_cmul(a[i], d01, n01) : (c == 2 ? packed_cmul(a[i], d10, n10) : packed_cmul(a[i], d11, n11)));
+    }
+#else
+    TCB_UNROLL
+    for (int i = 0; i < (1 << R); ++i) {
+      const int c = 2 * ((i >> JA) & 1) + ((i >> JB) & 1);
+      a[i] = cmul(a[i], c == 0 ? d00 : (c == 1 ? d01 : (c == 2 ? d10 : d11)));
+    }
+#endif
+  }
+}
 template <int R>
 TCB_DEV void apply_pairdiag(float2 (&a)[1 << R], int j, int k, float2 d00, float2 d01, float2 d10,
                             float2 d11) {
-  TCB_UNROLL
-  for (int i = 0; i < (1 << R); ++i) {
-    const bool xj = (i >> j) & 1, xk = (i >> k) & 1;
-    a[i] = cmul(a[i], xj ? csel(xk, d11, d10) : csel(xk, d01, d00));
+  switch (j * 8 + k) {  // j < k (planner)
+    case 0 * 8 + 1: apply_pairdiag_ct<R, 0, 1>(a, d00, d01, d10, d11); break;
+    case 0 * 8 + 2: apply_pairdiag_ct<R, 0, 2>(a, d00, d01, d10, d11); break;
+    case 0 * 8 + 3: apply_pairdiag_ct<R, 0, 3>(a, d00, d01, d10, d11); break;
+    case 0 * 8 + 4: apply_pairdiag_ct<R, 0, 4>(a, d00, d01, d10, d11); break;
+    case 1 * 8 + 2: apply_pairdiag_ct<R, 1, 2>(a, d00, d01, d10, d11); break;
+    case 1 * 8 + 3: apply_pairdiag_ct<R, 1, 3>(a, d00, d01, d10, d11); break;
+    case 1 * 8 + 4: apply_pairdiag_ct<R, 1, 4>(a, d00, d01, d10, d11); break;
+    case 2 * 8 + 3: apply_pairdiag_ct<R, 2, 3>(a, d00, d01, d10, d11); break;
+    case 2 * 8 + 4: apply_pairdiag_ct<R, 2, 4>(a, d00, d01, d10, d11); break;
+    case 3 * 8 + 4: apply_pairdiag_ct<R, 3, 4>(a, d00, d01, d10, d11); break;
+    default: break;
   }
 }
 
@@ -441,6 +475,37 @@ TCB_DEV void round_bit(float2 (&a)[1 << R], const int32_t* rd, int flags, int tb
   }
 }
 
+// fast path of round_bit: an uncontrolled gate with an optional factor (the whole of a QAOA / VQE
+// layer).  Kept apart from the general path so that the hot loop is one compact stretch of code
+// (the general path's controlled / diagonal-only variants are 2/3 of the instructions and would
+// otherwise sit between the hot blocks: instruction-cache misses were 17% of all stall samples).
+template <int R, int J>
+TCB_DEV void round_bit_simple(float2 (&a)[1 << R], const int32_t* rd, int flags, int tbase, const int32_t*& tt) {
+  if constexpr (J < R) {
+    if (!((flags >> J) & 1)) return;
+    const float4 A = lds4(rd + RD_M + 8 * J), B = lds4(rd + RD_M + 8 * J + 4);
+    float2 m00 = make_float2(A.x, A.y), m01 = make_float2(A.z, A.w);
+    float2 m10 = make_float2(B.x, B.y), m11 = make_float2(B.z, B.w);
+    if ((flags >> (16 + J)) & 1) {
+      const float4 F = lds4(rd + RD_F + 4 * J);
+      float2 f0 = make_float2(F.x, F.y), f1 = make_float2(F.z, F.w);
+      const int nj = rd[RD_NRJ + J];
+      TCB_NOUNROLL
+      for (int e = 0; e < nj; ++e, tt += TT_WORDS) {
+        const int xb = (tbase >> tt[TT_B]) & 1;
+        const float4 W = lds4(tt + TT_W + 4 * xb);
+        f0 = cmul(f0, make_float2(W.x, W.y));
+        f1 = cmul(f1, make_float2(W.z, W.w));
+      }
+      m00 = cmul(m00, f0);
+      m10 = cmul(m10, f0);
+      m01 = cmul(m01, f1);
+      m11 = cmul(m11, f1);
+    }
+    gate_on<R, J, false>(a, m00, m01, m10, m11, 0, 0);
+  }
+}
+
 // one thread's share of a register sub-pass.
 //   tile : shared-memory tile (swizzled), sp : sub-pass header, tbase : the thread's tile index with
 //   the register bits zero, cta_bits : CTA-constant flat-index bits (tile base | index_base)
@@ -485,6 +550,15 @@ TCB_DEV void run_reg_subpass(float2* tile, const int32_t* sp, int tbase, uint64_
       for (int e = 0; e < nrr; ++e, trr += TT_WORDS)
         apply_pairdiag<R>(a, trr[TT_A], trr[TT_B], lds2(trr + TT_W), lds2(trr + TT_W + 2), lds2(trr + TT_W + 4),
                           lds2(trr + TT_W + 6));
+    }
+    if (!(flags & RD_GENERAL)) {
+      round_bit_simple<R, 0>(a, rd, flags, tbase, tt);
+      round_bit_simple<R, 1>(a, rd, flags, tbase, tt);
+      round_bit_simple<R, 2>(a, rd, flags, tbase, tt);
+      round_bit_simple<R, 3>(a, rd, flags, tbase, tt);
+      round_bit_simple<R, 4>(a, rd, flags, tbase, tt);
+      rd += rd[RD_WORDS];
+      continue;
     }
     round_bit<R, 0>(a, rd, flags, tbase, cta_bits, tt);
     round_bit<R, 1>(a, rd, flags, tbase, cta_bits, tt);

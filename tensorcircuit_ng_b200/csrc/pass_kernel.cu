@@ -15,6 +15,8 @@
 //     copied into a shared-memory pool; per tile, threads resolve the fill records (fused 1q
 //     products, diagonal gates against this tile's constant bits) from the pool — no global
 //     latency on the per-tile critical path.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "pass_core.cuh"
 #include "../../include/tcb200.h"
@@ -105,6 +107,7 @@ struct PassArgs {
   unsigned long long total_tiles;  // tiles_per_state * batch
   int log_tiles_per_state;
   int nbits, prog_words;
+  int stagger_ns, n_sm;
 };
 
 // shared-memory carve-up (bytes, every region 16-byte aligned)
@@ -179,6 +182,10 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
   const int hstep = (2 * NT) >> L;  // hi_flat entries per u step
   __syncthreads();                  // hi_flat and grp ready
 
+  if (A.stagger_ns > 0) {  // experiment: de-phase the CTAs that share an SM
+    const int phase = blockIdx.x / A.n_sm;
+    for (int i = 0; i < phase; ++i) __nanosleep(A.stagger_ns);
+  }
   long long cur_batch = -1;
   for (unsigned long long tg = blockIdx.x; tg < A.total_tiles; tg += gridDim.x) {
     const long long b = (long long)(tg >> A.log_tiles_per_state);
@@ -295,6 +302,11 @@ int launch_pass(const void* src, void* dst, int nbits, int64_t batch, const int3
   a.log_tiles_per_state = nbits - tile_bits;
   a.nbits = nbits;
   a.prog_words = program_words;
+  {
+    const char* e = getenv("TCB_STAGGER_NS");
+    a.stagger_ns = e ? atoi(e) : 0;
+    a.n_sm = sm_count();
+  }
   int rc = 0;
   switch (lt) {
     case 8: rc = launch_pass_lt<8>(a, total, smem, stream); break;

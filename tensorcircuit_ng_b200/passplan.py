@@ -49,6 +49,7 @@ H_TILEPOS, H_NONTILEPOS, HDR_WORDS = 8, 24, 80
 S_NROUNDS, S_KIND, S_REGBITS, S_GRPBITS, S_WORDS, SUB_HDR_WORDS = 0, 1, 2, 10, 22, 24
 SUB_REG, SUB_SMEM_DENSE = 0, 1
 RD_FLAGS, RD_NRR, RD_WORDS, RD_NRJ, RD_CTRL, RD_M, RD_F, RD_FIXED = 0, 1, 2, 3, 8, 20, 60, 80
+RD_GENERAL = 1 << 30
 TT_A, TT_B, TT_W, TT_WORDS = 0, 1, 4, 12
 OP_WORDS = 16
 OP_DENSE = 5
@@ -302,7 +303,7 @@ def terminal_diagonals(gates: Sequence[GateOp], nq: int) -> Set[int]:
 
 
 def compile_plan(gates: Sequence[GateOp], nqubits: int, *, nbits_local: Optional[int] = None,
-                 tile_bits: int = 12, low_bits: int = 4, max_ops_per_pass: int = 200,
+                 tile_bits: int = 12, low_bits: int = 3, max_ops_per_pass: int = 200,
                  lookahead: int = 512) -> Plan:  # fmt: skip
     """Compile a gate stream.  `nbits_local` < nqubits describes a sharded state whose top
     (nqubits - nbits_local) qubits are global: only diagonal gates / controls may touch them."""
@@ -419,18 +420,60 @@ def _diag_stride(g: GateOp) -> int:
 
 def _build_rounds(sub_gates: Sequence[GateOp], run: List[Tuple[int, str]], pos_of: Sequence[int],
                   reg_idx: Dict[int, int], tbit_of_pos: Dict[int, int], pool: _Pool) -> List[_Round]:  # fmt: skip
-    """Cut the ordered gate list of one register sub-pass into rounds (pass_core.cuh: a round is, per
-    register slot, an optional diagonal factor followed by at most one fused 2x2)."""
-    rounds: List[_Round] = [_Round()]
+    """List-schedule the ordered gate list of one register sub-pass into rounds (pass_core.cuh: a
+    round is, per register slot, an optional diagonal factor followed by at most one fused 2x2).
 
-    def fresh() -> _Round:
-        r = _Round()
-        rounds.append(r)
+    Diagonal gates commute with everything except a non-diagonal gate on one of their own qubits,
+    so they stay *pending* on their register slot(s) until the next gate on such a slot is placed and
+    then ride in that gate's round as its factor (no extra rounds, no factor-only multiplies); what
+    is still pending at the end goes into one trailing round."""
+    rounds: List[_Round] = []
+    fused_block = [False] * PASS_R  # something that does not commute came after the slot's latest gate
+    last_gate = [-1] * PASS_R  # round of the latest gate on slot j
+    floor = [0] * PASS_R  # earliest round the next gate on slot j may take
+    pend: List[List[Tuple[str, Any]]] = [[] for _ in range(PASS_R)]
+    pend_rr: List[Tuple[int, int, GateOp]] = []
+
+    def ensure(r: int) -> _Round:
+        while len(rounds) <= r:
+            rounds.append(_Round())
+        return rounds[r]
+
+    def flush(j: int, r: int) -> None:
+        """Move everything pending on slot j into the diagonal part of round r."""
+        rnd = ensure(r)
+        for kind, data in pend[j]:
+            if kind == "pair":
+                rnd.pair_src[j].extend(data)
+            else:
+                rnd.rj[j].append(data)
+        pend[j].clear()
+        keep = []
+        for ja, jb, g in pend_rr:
+            if j in (ja, jb):
+                rnd.rr.append((ja, jb, g))
+                other = jb if j == ja else ja
+                floor[other] = max(floor[other], r)  # diagonal part of round r precedes its gates
+                fused_block[other] = True  # a later gate on `other` must not join its earlier product
+            else:
+                keep.append((ja, jb, g))
+        pend_rr[:] = keep
+
+    def rr_floor(j: int) -> int:
+        r = 0
+        for ja, jb, _ in pend_rr:
+            if j in (ja, jb):
+                r = max(r, last_gate[jb if j == ja else ja] + 1)
         return r
+
+    def can_fuse(j: int) -> bool:
+        r = last_gate[j]
+        return (r >= 0 and rounds[r].gate[j]["ctrl"] is None and not pend[j] and floor[j] <= r + 1
+                and not any(j in (ja, jb) for ja, jb, _ in pend_rr) and j not in rounds[r].ctrl_regs
+                and not fused_block[j])  # fmt: skip
 
     for gi, how in run:
         g = sub_gates[gi]
-        cur = rounds[-1]
         if how in ("diag", "diag2"):
             st = _diag_stride(g)
             ps = [pos_of[q] for q in g.qubits]
@@ -438,40 +481,37 @@ def _build_rounds(sub_gates: Sequence[GateOp], run: List[Tuple[int, str]], pos_o
             if g.k == 1:
                 j = slots[0]
                 assert j is not None
-                gt = cur.gate[j]
-                if gt is not None and gt["ctrl"] is None and j not in cur.ctrl_regs:
+                if can_fuse(j):
                     # 1q diagonal right after dense gate(s) on the same slot: same 2x2 product
-                    gt["fusion"].append((g, 0, FF_MD, st))
-                    continue
-                if gt is not None:
-                    cur = fresh()
-                cur.pair_src[j].extend([pool.ref(g), FF_D1 | (st << 8), 0, 0])
+                    rounds[last_gate[j]].gate[j]["fusion"].append((g, 0, FF_MD, st))
+                else:
+                    pend[j].append(("pair", [pool.ref(g), FF_D1 | (st << 8), 0, 0]))
                 continue
             if slots[0] is not None and slots[1] is not None:
-                if cur.gate[slots[0]] is not None or cur.gate[slots[1]] is not None:
-                    cur = fresh()
-                cur.rr.append((slots[0], slots[1], g))
+                pend_rr.append((slots[0], slots[1], g))
                 continue
             own = 0 if slots[0] is not None else 1  # which gate qubit is the register bit
             j = slots[own]
             assert j is not None
-            if cur.gate[j] is not None:
-                cur = fresh()
             pp = ps[1 - own]
             if pp in tbit_of_pos:  # thread-constant partner: one LDS.128 lookup per thread
                 # W = [x_B=0: (d[x_A=0], d[x_A=1])], [x_B=1: ...]; A is the register bit
                 form = FF_T_SWAP if own == 0 else FF_T
-                cur.rj[j].append((tbit_of_pos[pp], g, form))
+                pend[j].append(("rj", (tbit_of_pos[pp], g, form)))
             else:  # CTA-constant partner: resolved per tile by the prologue
                 form = FF_D2_FIRST if own == 0 else FF_D2_SECOND
-                cur.pair_src[j].extend([pool.ref(g), form | (st << 8), pp, 0])
+                pend[j].append(("pair", [pool.ref(g), form | (st << 8), pp, 0]))
         elif how == "1q":
             j = reg_idx[pos_of[g.qubits[0]]]
-            if (cur.gate[j] is not None and cur.gate[j]["ctrl"] is not None) or j in cur.ctrl_regs:
-                cur = fresh()
-            if cur.gate[j] is None:
-                cur.gate[j] = {"fusion": [], "ctrl": None}
-            cur.gate[j]["fusion"].append((g, 0, FF_M, 2))
+            if can_fuse(j):
+                rounds[last_gate[j]].gate[j]["fusion"].append((g, 0, FF_M, 2))
+                continue
+            r = max(floor[j], rr_floor(j))
+            rnd = ensure(r)
+            assert rnd.gate[j] is None
+            rnd.gate[j] = {"fusion": [(g, 0, FF_M, 2)], "ctrl": None}
+            flush(j, r)
+            last_gate[j], floor[j], fused_block[j] = r, r + 1, False
         elif how == "c1q":
             nctrl, pol = g.kind[1], g.kind[2]
             j = reg_idx[pos_of[g.qubits[-1]]]
@@ -490,17 +530,29 @@ def _build_rounds(sub_gates: Sequence[GateOp], run: List[Tuple[int, str]], pos_o
                     tcs.append(tbit_of_pos[p] | 0x80 | (want << 8))
                 else:
                     tcs.append(p | (want << 8))
-            if cur.gate[j] is not None or j in cur.ctrl_regs or any(cur.gate[k] is not None for k in regs):
-                cur = fresh()
+            r = max(floor[j], rr_floor(j))
+            for k in regs:  # a round applies its gates in slot order, not program order
+                r = max(r, last_gate[k] + 1)
+            rnd = ensure(r)
+            assert rnd.gate[j] is None
             D = 1 << g.k
             polval = 0
             for ci in range(nctrl):
                 polval = (polval << 1) | ((pol >> ci) & 1)
             delta = (polval * 2) * D + polval * 2  # top-left of the active 2x2 block
-            cur.gate[j] = {"fusion": [(g, delta, FF_M, D)], "ctrl": {"cmask": cmask, "cwant": cwant, "tcs": tcs}}
-            cur.ctrl_regs |= regs
+            rnd.gate[j] = {"fusion": [(g, delta, FF_M, D)], "ctrl": {"cmask": cmask, "cwant": cwant, "tcs": tcs}}
+            rnd.ctrl_regs |= regs
+            flush(j, r)
+            last_gate[j], floor[j], fused_block[j] = r, r + 1, False
+            for k in regs:
+                floor[k] = max(floor[k], r + 1)
+                fused_block[k] = True
         else:  # pragma: no cover
             raise AssertionError(how)
+    # whatever is still pending: one trailing diagonal part per slot, after the slot's last gate
+    for j in range(PASS_R):
+        if pend[j] or any(j in (ja, jb) for ja, jb, _ in pend_rr):
+            flush(j, max(last_gate[j] + 1, floor[j], rr_floor(j)))
     return [r for r in rounds if not r.empty()]
 
 
@@ -544,8 +596,11 @@ def _emit_round(words: List[int], fills: List[List[int]], rnd: _Round, pool: _Po
         for tb, g, form in rnd.rj[j]:
             tables.append((j, tb, g, form))
     rec[RD_NRR] = len(rnd.rr)
-    for ja, jb, g in rnd.rr:
-        tables.append((ja, jb, g, FF_T))
+    for ja, jb, g in rnd.rr:  # W[2 * x_A + x_B] with A < B (pass_core.cuh dispatches on the slot pair)
+        tables.append((ja, jb, g, FF_T) if ja < jb else (jb, ja, g, FF_T_SWAP))
+    if any(gt is not None and gt["ctrl"] is not None for gt in rnd.gate) or any(
+            rnd.has_factor(j) and rnd.gate[j] is None for j in range(PASS_R)):  # fmt: skip
+        flags |= RD_GENERAL  # pass_core.cuh: everything else takes the compact fast path
     rec[RD_FLAGS] = flags
     rec[RD_WORDS] = RD_FIXED + TT_WORDS * len(tables)
     words.extend(rec)

@@ -220,7 +220,12 @@ class CompiledCircuit:
 
 
 _plan_cache: Dict[Any, CompiledCircuit] = {}
-plan_options: Dict[str, Any] = {"tile_bits": 12, "low_bits": 4}
+import os as _os
+
+plan_options: Dict[str, Any] = {
+    "tile_bits": int(_os.environ.get("TCB_TILE_BITS", "12")),
+    "low_bits": int(_os.environ.get("TCB_LOW_BITS", "3")),
+}
 
 
 def compile_circuit(nq: int, structure: Sequence[Tuple[Tuple[int, ...], Tuple[Any, ...], int]],

@@ -16,12 +16,12 @@ hi = list(range(9)); lo = [n - 1, n - 2, n - 3, n - 4]
 cases = {
     "rx1": [([0], ("dense",), rx(0.3))],
     "rx4": [([q], ("dense",), rx(0.3 + q)) for q in hi[:4]],
-    "rx13": [([q], ("dense",), rx(0.3 + q)) for q in hi + lo],
+    "rx12": [([q], ("dense",), rx(0.3 + q)) for q in hi[:8] + lo],
     "zz45": [([int(a), int(b)], ("diag",), zz(0.2)) for a, b in (rng.permutation(n)[:2] for _ in range(45))],
 }
 L = _lib.load()
 fn = L.tcb_debug_pass_prof; fn.restype = ctypes.c_int; fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
-names = ["pool", "fill", "wait+sync", "issue", "subpasses", "store", "endsync"]
+names = ["issue-load", "fill", "wait+sync", "-", "subpasses", "store", "endsync"]
 for case, gates in cases.items():
     ops, bufs, off = [], [], 0
     for qubits, kind, mat in gates:
@@ -35,6 +35,6 @@ for case, gates in cases.items():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); cc.run(state, gatebuf); e1.record(); torch.cuda.synchronize()
     fn(out, 1)
-    ntiles = 2 ** (n - 13)
+    ntiles = 2 ** (n - 12)
     tot = sum(out[i] for i in range(7))
     print(f"{case}: {e0.elapsed_time(e1):.3f} ms; cycles per tile: " + ", ".join(f"{names[i]} {out[i]/ntiles:.0f}" for i in range(7)) + f"  total {tot/ntiles:.0f}")
