@@ -171,26 +171,44 @@ int launch_diag(void* state, int nbits, int64_t batch, const int* bitpos, int k,
 // vector.  Each thread holds 32 probabilities whose indices differ in 5 known bits (bit 0 and
 // bits 9..12 of x); one in-register WHT (80 adds) turns them into the 32 possible signed sums,
 // so every term costs ONE coefficient lookup + the sign of the remaining bits per 32 amplitudes
-// instead of 32 sign evaluations.  Warp-shuffle reduction per term, double accumulation.
+// instead of 32 sign evaluations.  Per-thread float partial sums per term live in shared memory
+// ([term][thread], conflict-free); every EZ_FLUSH iterations they are warp-reduced into double
+// accumulators, so the shuffle tree is off the streaming path (it was 80% of the old kernel).
 constexpr int EZ_THREADS = 256;
 constexpr int EZ_VEC = 16;  // float4 loads per thread per iteration (32 amplitudes)
 constexpr int EZ_MAX_TERMS = 1024;
+constexpr int EZ_TERMS_PER_LAUNCH = 64;
+constexpr int EZ_FLUSH = 32;
 
 __global__ void __launch_bounds__(EZ_THREADS)
 expect_z_kernel(const float4* __restrict__ state, uint64_t nvec_per_state,
-                const unsigned long long* __restrict__ zmasks, int nterms,
+                const unsigned long long* __restrict__ zmasks, int nterms, int out_stride,
                 unsigned long long index_base, double* out) {
   extern __shared__ __align__(16) unsigned char ez_smem[];
-  float* coef = reinterpret_cast<float*>(ez_smem);                               // [32][EZ_THREADS]
-  double* acc = reinterpret_cast<double*>(ez_smem + 32 * EZ_THREADS * sizeof(float));  // [warps][nterms]
+  float* coef = reinterpret_cast<float*>(ez_smem);               // [32][EZ_THREADS]
+  float* part = coef + 32 * EZ_THREADS;                          // [nterms][EZ_THREADS]
+  double* acc = reinterpret_cast<double*>(part + nterms * EZ_THREADS);  // [warps][nterms]
+  unsigned long long* smask = reinterpret_cast<unsigned long long*>(acc + (EZ_THREADS / 32) * nterms);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarps = EZ_THREADS / 32;
   for (int e = tid; e < nwarps * nterms; e += EZ_THREADS) acc[e] = 0.0;
+  for (int t = tid; t < nterms; t += EZ_THREADS) smask[t] = zmasks[t];
+  for (int t = 0; t < nterms; ++t) part[t * EZ_THREADS + tid] = 0.f;
   __syncthreads();
   const unsigned b = blockIdx.y;
   const float4* st = state + (size_t)b * nvec_per_state;
   double* my = acc + warp * nterms;
   const uint64_t chunk = (uint64_t)EZ_THREADS * EZ_VEC;
+  auto flush = [&]() {
+    for (int t = 0; t < nterms; ++t) {
+      float val = part[t * EZ_THREADS + tid];
+      part[t * EZ_THREADS + tid] = 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+      if (lane == 0) my[t] += (double)val;
+    }
+  };
+  int it = 0;
   // group bits of x: bit 0 (pair inside a float4) and bits 9..12 (u); everything else is "rest"
   for (uint64_t v0 = (uint64_t)blockIdx.x * chunk; v0 < nvec_per_state;
        v0 += (uint64_t)gridDim.x * chunk) {
@@ -219,22 +237,26 @@ expect_z_kernel(const float4* __restrict__ state, uint64_t nvec_per_state,
     for (int i = 0; i < 32; ++i) coef[i * EZ_THREADS + tid] = p[i];
     // (each thread only reads back its own column: no barrier needed)
     const unsigned long long xrest = ((v0 + (uint64_t)tid) << 1) | index_base;
+#pragma unroll 4
     for (int t = 0; t < nterms; ++t) {
-      const unsigned long long m = zmasks[t];
+      const unsigned long long m = smask[t];
       const int c = (int)(m & 1ull) | (int)(((m >> 9) & 15ull) << 1);
-      float val = coef[c * EZ_THREADS + tid];
+      const float val = coef[c * EZ_THREADS + tid];
       // xrest has zeros at the 5 group bits, so they are not counted twice
-      if (__popcll(xrest & m) & 1) val = -val;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-      if (lane == 0) my[t] += (double)val;
+      const float sgn = (__popcll(xrest & m) & 1) ? -val : val;
+      part[t * EZ_THREADS + tid] += sgn;
+    }
+    if (++it == EZ_FLUSH) {
+      flush();
+      it = 0;
     }
   }
+  flush();
   __syncthreads();
   for (int t = tid; t < nterms; t += EZ_THREADS) {
     double sum = 0.0;
     for (int w = 0; w < nwarps; ++w) sum += acc[w * nterms + t];
-    atomicAdd(out + (size_t)b * nterms + t, sum);
+    atomicAdd(out + (size_t)b * out_stride + t, sum);
   }
 }
 
@@ -247,20 +269,26 @@ int launch_expect_z(const void* state, int nbits, int64_t batch, const uint64_t*
   const uint64_t nvec = 1ull << (nbits - 1);
   const uint64_t chunk = (uint64_t)EZ_THREADS * EZ_VEC;
   uint64_t gx = (nvec + chunk - 1) / chunk;
-  const uint64_t cap = (uint64_t)sm_count() * 4;
+  const uint64_t cap = (uint64_t)sm_count() * 2;
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, (unsigned)batch);
-  const size_t smem = 32 * EZ_THREADS * sizeof(float) + sizeof(double) * (EZ_THREADS / 32) * nterms;
   static bool attr_set = false;
   if (!attr_set) {
     TCB_CHECK_CUDA(cudaFuncSetAttribute(expect_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        100 * 1024));
+                                        110 * 1024));
     attr_set = true;
   }
-  expect_z_kernel<<<grid, EZ_THREADS, smem, stream>>>(
-      reinterpret_cast<const float4*>(state), nvec,
-      reinterpret_cast<const unsigned long long*>(zmasks), nterms, (unsigned long long)index_base, out);
-  TCB_CHECK_CUDA(cudaGetLastError());
+  // the per-thread partial sums bound the terms of one launch; more terms = more reads of the state
+  for (int t0 = 0; t0 < nterms; t0 += EZ_TERMS_PER_LAUNCH) {
+    const int nt = nterms - t0 < EZ_TERMS_PER_LAUNCH ? nterms - t0 : EZ_TERMS_PER_LAUNCH;
+    const size_t smem = 32 * EZ_THREADS * sizeof(float) + (size_t)nt * EZ_THREADS * sizeof(float) +
+                        sizeof(double) * (EZ_THREADS / 32) * nt + sizeof(unsigned long long) * nt;
+    expect_z_kernel<<<grid, EZ_THREADS, smem, stream>>>(
+        reinterpret_cast<const float4*>(state), nvec,
+        reinterpret_cast<const unsigned long long*>(zmasks) + t0, nt, nterms, (unsigned long long)index_base,
+        out + t0);
+    TCB_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

@@ -79,13 +79,22 @@ def pauli_expectation(psi: torch.Tensor, n: int, xs: Sequence[int], ys: Sequence
     return _pauli_raw(psi, n, xs, ys, zs)
 
 
+_mask_cache: dict = {}
+
+
 def z_expectations(psi: torch.Tensor, n: int, terms: Sequence[Sequence[int]]) -> torch.Tensor:
     """All Z-string expectations in ONE read of the state: terms[t] = qubits carrying Z.
     Returns float64 [len(terms)].  (Pauli-sum expectation, diagonal part.)"""
     _lib.require_cuda(psi, "state")
     psi = psi.resolve_conj().contiguous()
-    masks = np.array([_mask(n, t) for t in terms], dtype=np.int64)
-    zm = torch.from_numpy(masks).to(psi.device)
+    key = (n, str(psi.device), tuple(tuple(int(q) for q in t) for t in terms))
+    zm = _mask_cache.get(key)
+    if zm is None:  # the masks of a Hamiltonian are uploaded once, not once per step
+        masks = np.array([_mask(n, t) for t in terms], dtype=np.int64)
+        zm = torch.from_numpy(masks).to(psi.device)
+        if len(_mask_cache) > 64:
+            _mask_cache.clear()
+        _mask_cache[key] = zm
     out = torch.zeros(len(terms), dtype=torch.float64, device=psi.device)
     _lib.call("tcb_sv_expect_z", psi.data_ptr(), n, 1, zm.data_ptr(), len(terms), 0, out.data_ptr(),
               _lib.stream_ptr())  # fmt: skip
