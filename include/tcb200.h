@@ -103,6 +103,14 @@ int tcb_sv_gate_grad(const void* lam, const void* psi_in, int nbits, int64_t bat
  * send buffer (and the inverse), so the exchange itself is one NCCL send/recv.           */
 int tcb_sv_pack_half(const void* state, void* buf, int nbits, int local_bit, int want, void* stream);
 int tcb_sv_unpack_half(void* state, const void* buf, int nbits, int local_bit, int want, void* stream);
+/* m-qubit swap: the sub-block of the local state whose `nsel` selected bits (ascending positions)
+ * equal `pattern` (bit k of pattern <-> sel_bits[k]) has 2^(nbits-nsel) amplitudes; elements
+ * [first, first+count) of it, in block order, are copied to / from a contiguous buffer, so a swap
+ * can be streamed through a small staging buffer chunk by chunk.                               */
+int tcb_sv_pack_bits(const void* state, void* buf, int nbits, int nsel, const int* sel_bits_host,
+                     uint64_t pattern, uint64_t first, uint64_t count, void* stream);
+int tcb_sv_unpack_bits(void* state, const void* buf, int nbits, int nsel, const int* sel_bits_host,
+                       uint64_t pattern, uint64_t first, uint64_t count, void* stream);
 
 /* ---- tensor network: pairwise contraction (K1/K6/K7) ----------------------
  * All tensor modes have extent 2.  Every mode of A, B and C is described by the flat-index

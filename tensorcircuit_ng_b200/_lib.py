@@ -92,6 +92,14 @@ SYMBOLS = {
     ),
     "tcb_sv_pack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tcb_sv_unpack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tcb_sv_pack_bits": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_uint64, c_uint64, c_uint64, c_void_p],
+    ),
+    "tcb_sv_unpack_bits": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_uint64, c_uint64, c_uint64, c_void_p],
+    ),
     "tcb_tn_contract": (
         c_int,
         [c_void_p, c_int64, c_void_p, c_int64, c_void_p, POINTER(ContractDesc), c_int, c_void_p],

@@ -42,6 +42,7 @@ int launch_inner(const void*, const void*, int, int64_t, double*, cudaStream_t);
 int launch_gate_grad(const void*, const void*, int, int64_t, const int*, int, void*, int64_t,
                      cudaStream_t);
 int launch_pack_half(const void*, void*, int, int, int, int, cudaStream_t);
+int launch_pack_bits(void*, void*, int, int, const int*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
 int launch_contract(const void*, int64_t, const void*, int64_t, void*, const tcb_contract_desc*, int,
                     cudaStream_t);
 
@@ -154,6 +155,24 @@ int tcb_sv_unpack_half(void* state, const void* buf, int nbits, int local_bit, i
   NOTNULL(state, "tcb_sv_unpack_half");
   NOTNULL(buf, "tcb_sv_unpack_half");
   return launch_pack_half(state, const_cast<void*>(buf), nbits, local_bit, want, 1, S(stream));
+}
+
+int tcb_sv_pack_bits(const void* state, void* buf, int nbits, int nsel, const int* sel_bits_host,
+                     uint64_t pattern, uint64_t first, uint64_t count, void* stream) {
+  NOTNULL(state, "tcb_sv_pack_bits");
+  NOTNULL(buf, "tcb_sv_pack_bits");
+  NOTNULL(sel_bits_host, "tcb_sv_pack_bits");
+  return launch_pack_bits(const_cast<void*>(state), buf, nbits, nsel, sel_bits_host, pattern, first, count, 0,
+                          S(stream));
+}
+
+int tcb_sv_unpack_bits(void* state, const void* buf, int nbits, int nsel, const int* sel_bits_host,
+                       uint64_t pattern, uint64_t first, uint64_t count, void* stream) {
+  NOTNULL(state, "tcb_sv_unpack_bits");
+  NOTNULL(buf, "tcb_sv_unpack_bits");
+  NOTNULL(sel_bits_host, "tcb_sv_unpack_bits");
+  return launch_pack_bits(state, const_cast<void*>(buf), nbits, nsel, sel_bits_host, pattern, first, count, 1,
+                          S(stream));
 }
 
 int tcb_tn_contract(const void* a, int64_t a_offset, const void* b, int64_t b_offset, void* c,

@@ -536,4 +536,58 @@ int launch_pack_half(const void* state, void* buf, int nbits, int bit, int want,
   return 0;
 }
 
+// pack / unpack the sub-block of the state whose `nsel` selected local bits equal `pattern`
+// (m-qubit global<->local swap: one such block goes to each of the 2^m - 1 partner ranks).
+// Elements [first, first + count) of the block, in block order; V = float4 moves amplitude pairs
+// (legal when bit 0 is not selected and first, count are even).
+struct SelBits {
+  int n;
+  int pos[8];  // ascending
+};
+template <typename V>
+__global__ void __launch_bounds__(256)
+pack_bits_kernel(V* __restrict__ state, V* __restrict__ buf, uint64_t first, uint64_t count, SelBits sb,
+                 uint64_t patmask, int unpack) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    uint64_t x = first + i;
+#pragma unroll 1
+    for (int k = 0; k < sb.n; ++k) x = insert_zero(x, sb.pos[k]);
+    x |= patmask;
+    if (unpack)
+      state[x] = buf[i];
+    else
+      buf[i] = state[x];
+  }
+}
+
+int launch_pack_bits(void* state, void* buf, int nbits, int nsel, const int* sel_bits, uint64_t pattern,
+                     uint64_t first, uint64_t count, int unpack, cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_pack_bits: nbits=%d", nbits);
+  TCB_REQUIRE(nsel >= 1 && nsel <= 8 && nsel <= nbits, "tcb_sv_pack_bits: nsel=%d out of range", nsel);
+  SelBits sb;
+  sb.n = nsel;
+  uint64_t patmask = 0;
+  for (int k = 0; k < nsel; ++k) {
+    TCB_REQUIRE(sel_bits[k] >= 0 && sel_bits[k] < nbits, "tcb_sv_pack_bits: bit %d out of range", sel_bits[k]);
+    TCB_REQUIRE(k == 0 || sel_bits[k] > sel_bits[k - 1], "tcb_sv_pack_bits: selected bits must be ascending");
+    sb.pos[k] = sel_bits[k];
+    patmask |= ((pattern >> k) & 1ull) << sel_bits[k];
+  }
+  const uint64_t block = 1ull << (nbits - nsel);
+  TCB_REQUIRE(first + count <= block, "tcb_sv_pack_bits: range exceeds the block");
+  if (count == 0) return 0;
+  if (sel_bits[0] >= 1 && (first & 1ull) == 0 && (count & 1ull) == 0) {
+    for (int k = 0; k < nsel; ++k) sb.pos[k] -= 1;
+    pack_bits_kernel<float4><<<grid_for(count / 2, 256), 256, 0, stream>>>(
+        reinterpret_cast<float4*>(state), reinterpret_cast<float4*>(buf), first / 2, count / 2, sb, patmask >> 1,
+        unpack);
+  } else {
+    pack_bits_kernel<float2><<<grid_for(count, 256), 256, 0, stream>>>(
+        reinterpret_cast<float2*>(state), reinterpret_cast<float2*>(buf), first, count, sb, patmask, unpack);
+  }
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace tcb

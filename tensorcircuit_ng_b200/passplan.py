@@ -174,8 +174,10 @@ class _Frontier:
         self.remaining -= len(done)
 
     def simulate(self, inside: Set[int], pos_of: Sequence[int], max_dense: int, limit: int,
-                 commit: bool = False, allow: Optional[Set[int]] = None) -> List[Tuple[int, str]]:  # fmt: skip
-        """Greedily run every gate that is ready and applicable; returns [(gate index, how)]."""
+                 commit: bool = False, allow: Optional[Set[int]] = None,
+                 pred: Optional[Any] = None) -> List[Tuple[int, str]]:  # fmt: skip
+        """Greedily run every gate that is ready and applicable; returns [(gate index, how)].
+        `pred(gate) -> how | None` replaces the tile applicability rule (sharded.py)."""
         ptr = self.ptr if commit else self.clone_ptr()
         out: List[Tuple[int, str]] = []
         nq = len(self.queues)
@@ -190,7 +192,7 @@ class _Frontier:
                     break
                 if not self.ready(gi, ptr):
                     break
-                how = _applicable(self.gates[gi], pos_of, inside, max_dense)
+                how = _applicable(self.gates[gi], pos_of, inside, max_dense) if pred is None else pred(self.gates[gi])
                 if how is None:
                     break
                 out.append((gi, how))
@@ -304,11 +306,13 @@ def terminal_diagonals(gates: Sequence[GateOp], nq: int) -> Set[int]:
 
 def compile_plan(gates: Sequence[GateOp], nqubits: int, *, nbits_local: Optional[int] = None,
                  tile_bits: int = 12, low_bits: int = 3, max_ops_per_pass: int = 200,
-                 lookahead: int = 512) -> Plan:  # fmt: skip
-    """Compile a gate stream.  `nbits_local` < nqubits describes a sharded state whose top
-    (nqubits - nbits_local) qubits are global: only diagonal gates / controls may touch them."""
+                 lookahead: int = 512, pos_of: Optional[Sequence[int]] = None) -> Plan:  # fmt: skip
+    """Compile a gate stream.  `nbits_local` < nqubits describes a sharded state: flat-index positions
+    >= nbits_local are global (rank bits): only diagonal gates / controls may touch them.
+    `pos_of[q]` = flat-index bit position of qubit q (default: qubit 0 is the most significant bit,
+    tensorcircuit/circuit.py:711-719; the sharded scheduler passes its current qubit layout)."""
     nbits = nqubits if nbits_local is None else nbits_local
-    pos_of = [nqubits - 1 - q for q in range(nqubits)]  # qubit -> flat bit position
+    pos_of = [nqubits - 1 - q for q in range(nqubits)] if pos_of is None else list(pos_of)
     for gi, g in enumerate(gates):
         if g.gid < 0:
             g.gid = gi

@@ -1,0 +1,381 @@
+"""
+Sharded statevector (BASELINE.json configs[3]): 2^n amplitudes over G = 2^g GPUs.
+
+The reference has no sharded statevector (its multi-device examples shard Hamiltonian terms or
+contraction slices, `examples/ng_whitepaper/VIA_sharding_vqe.py:34-37`,
+`tensorcircuit/experimental.py:881-894`); the scheme is the north-star's: the g highest flat-index
+bit positions are *global* (rank r holds the amplitudes whose global bits equal r).
+
+  * diagonal gates and controls on global qubits are local work: every kernel takes `index_base`
+    (= rank << n_local) and reads those bits from it;
+  * a dense gate on a global qubit needs the qubit to be local first: an m-qubit global<->local
+    swap is one exchange in which every rank keeps 2^-m of its shard and trades one sub-block with each
+    of the 2^m - 1 ranks that differ in the swapped rank bits (`tcb_sv_pack_bits` -> P2P -> unpack,
+    streamed through two staging buffers so packing overlaps the wire);
+  * expectations are per-rank partial sums + one all-reduce.
+
+The host scheduler cuts the gate stream into local segments (each compiled by passplan into fused
+HBM passes under the *current* qubit layout) separated by swaps; which local qubits are evicted is
+decided Belady-style (farthest next dense use).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import passplan
+from .passplan import GateOp, _Frontier
+
+
+@dataclass
+class RunSegment:
+    gate_ids: List[int]  # indices into the circuit's gate list, in a valid execution order
+    pos_of: List[int]  # qubit -> flat bit position while this segment runs
+
+
+@dataclass
+class SwapSegment:
+    pairs: List[Tuple[int, int]]  # (global position, local position) exchanged, one pair per swapped qubit
+    pos_of_after: List[int]
+
+
+@dataclass
+class ShardedPlan:
+    nqubits: int
+    nglobal: int
+    segments: List[Any]
+    final_pos_of: List[int]
+    cache: Dict[Any, Any] = field(default_factory=dict)  # compiled segments (device programs), per rank
+
+    @property
+    def n_swaps(self) -> int:
+        return sum(1 for s in self.segments if isinstance(s, SwapSegment))
+
+    @property
+    def swapped_qubits(self) -> int:
+        return sum(len(s.pairs) for s in self.segments if isinstance(s, SwapSegment))
+
+
+def _needs_local(g: GateOp) -> Tuple[int, ...]:
+    """Qubits of g that must be local for it to run (the rest may sit on rank bits)."""
+    if g.is_diag:
+        return ()
+    if g.kind[0] == "ctrl" and g.kind[1] <= 2 and g.k == g.kind[1] + 1:
+        return (g.qubits[-1],)
+    return tuple(g.qubits)
+
+
+def compile_sharded(gates: Sequence[GateOp], nqubits: int, nglobal: int, *, avoid_low: int = 1) -> ShardedPlan:
+    """Cut the gate stream into local segments and swaps.  `avoid_low`: the lowest local positions are
+    never chosen for eviction (keeps the exchange 16-byte vectorised and the coalescing bits put)."""
+    nl = nqubits - nglobal
+    pos_of = [nqubits - 1 - q for q in range(nqubits)]
+    for gi, g in enumerate(gates):
+        if g.gid < 0:
+            g.gid = gi
+    front = _Frontier(gates, nqubits)
+    segments: List[Any] = []
+
+    def runnable(g: GateOp) -> Optional[str]:
+        return "local" if all(pos_of[q] < nl for q in _needs_local(g)) else None
+
+    while front.remaining > 0:
+        run = front.simulate(set(), pos_of, 0, 1 << 60, commit=True, pred=runnable)
+        if run:
+            segments.append(RunSegment([gi for gi, _ in run], list(pos_of)))
+        if front.remaining == 0:
+            break
+        # next dense use of every qubit (distance in pending gates on its own queue)
+        def next_dense_use(q: int) -> int:
+            qq = front.queues[q]
+            for d, gi in enumerate(qq[front.ptr[q]:]):
+                if q in _needs_local(gates[gi]):
+                    return gates[gi].gid
+            return 1 << 60
+
+        incoming = [q for q in range(nqubits) if pos_of[q] >= nl and next_dense_use(q) < (1 << 60)]
+        incoming.sort(key=next_dense_use)
+        # qubits the blocked head gates need stay local
+        pinned = set()
+        for gi in front.heads():
+            pinned.update(gates[gi].qubits)
+        cand = [q for q in range(nqubits) if avoid_low <= pos_of[q] < nl and q not in pinned]
+        cand.sort(key=lambda q: -next_dense_use(q))
+        incoming = incoming[: len(cand)]
+        if not incoming:
+            raise RuntimeError("sharded planner stalled: a gate needs more local qubits than the shard has")
+        outgoing = cand[: len(incoming)]
+        # never evict a qubit that is needed sooner than the one it makes room for
+        keep = [(a, b) for a, b in zip(incoming, outgoing) if next_dense_use(b) > next_dense_use(a)]
+        if not keep:
+            keep = [(incoming[0], outgoing[0])]
+        pairs = []
+        for qin, qout in keep:
+            pairs.append((pos_of[qin], pos_of[qout]))
+            pos_of[qin], pos_of[qout] = pos_of[qout], pos_of[qin]
+        segments.append(SwapSegment(pairs, list(pos_of)))
+    return ShardedPlan(nqubits, nglobal, segments, list(pos_of))
+
+
+# ---------------------------------------------------------------------------------------------
+class CudaExecutor:
+    """Local work of one rank through the C ABI (the product path)."""
+
+    def __init__(self, device: Any) -> None:
+        import torch
+
+        self.torch = torch
+        self.device = device
+
+    def zeros(self, n: int) -> Any:
+        return self.torch.zeros(n, dtype=self.torch.complex64, device=self.device)
+
+    def empty(self, n: int) -> Any:
+        return self.torch.empty(n, dtype=self.torch.complex64, device=self.device)
+
+    def set_one(self, state: Any) -> None:
+        state[0] = 1.0
+
+    def run_gates(self, state: Any, ops: Sequence[GateOp], gatebuf: Any, nq: int, nl: int, pos_of: Sequence[int],
+                  index_base: int, cache: Dict[Any, Any], key: Any) -> None:  # fmt: skip
+        from . import svengine
+
+        cc = cache.get(key)
+        if cc is None:
+            plan = passplan.compile_plan(list(ops), nq, nbits_local=nl, pos_of=pos_of, **svengine.plan_options)
+            cc = svengine.CompiledCircuit(plan, list(ops), self.device)
+            cache[key] = cc
+        cc.run(state, gatebuf, index_base=index_base)
+
+    def pack(self, state: Any, buf: Any, nl: int, sel: Sequence[int], pattern: int, first: int, count: int,
+             unpack: bool) -> None:  # fmt: skip
+        from . import _lib
+
+        _lib.call("tcb_sv_unpack_bits" if unpack else "tcb_sv_pack_bits", state.data_ptr(), buf.data_ptr(), nl,
+                  len(sel), _lib.int_array(sel), pattern, first, count, _lib.stream_ptr())  # fmt: skip
+
+    def expect_z(self, state: Any, nl: int, masks: Sequence[int], index_base: int) -> Any:
+        from . import _lib
+
+        t = self.torch
+        zm = t.from_numpy(np.asarray(masks, dtype=np.int64)).to(self.device)
+        out = t.zeros(len(masks), dtype=t.float64, device=self.device)
+        _lib.call("tcb_sv_expect_z", state.data_ptr(), nl, 1, zm.data_ptr(), len(masks), index_base, out.data_ptr(),
+                  _lib.stream_ptr())  # fmt: skip
+        return out
+
+    def norm2(self, state: Any) -> Any:
+        return self.expect_z(state, int(state.numel()).bit_length() - 1, [0], 0)
+
+    def read(self, state: Any, idx: int) -> Any:
+        return state[idx : idx + 1].clone()
+
+
+class TorchDistComm:
+    """torch.distributed plumbing: NCCL on GPUs, gloo in the CPU test tier."""
+
+    def __init__(self, group: Any = None) -> None:
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def exchange(self, sends: List[Tuple[int, Any]], recvs: List[Tuple[int, Any]]) -> None:
+        import torch
+
+        def real(t: Any) -> Any:  # complex tensors travel as (re, im) views of the same memory
+            return torch.view_as_real(t) if t.is_complex() else t
+
+        ops = []
+        for peer, t in sends:
+            ops.append(self.dist.P2POp(self.dist.isend, real(t), peer, self.group))
+        for peer, t in recvs:
+            ops.append(self.dist.P2POp(self.dist.irecv, real(t), peer, self.group))
+        for w in self.dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def all_reduce_sum(self, t: Any) -> Any:
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+class ShardedStatevector:
+    """One rank's shard of an n-qubit state + the collective operations on it."""
+
+    def __init__(self, nqubits: int, comm: Any, executor: Any, chunk_elems: int = 1 << 26) -> None:
+        world = comm.world
+        if world & (world - 1):
+            raise ValueError("the number of ranks must be a power of two")
+        self.n = nqubits
+        self.g = world.bit_length() - 1
+        self.nl = nqubits - self.g
+        if self.nl < 1:
+            raise ValueError("more ranks than amplitudes")
+        self.comm = comm
+        self.ex = executor
+        self.rank = comm.rank
+        self.index_base = self.rank << self.nl
+        self.state = executor.zeros(1 << self.nl)
+        if self.rank == 0:
+            executor.set_one(self.state)
+        self.pos_of = [nqubits - 1 - q for q in range(nqubits)]
+        self.chunk = max(2, min(chunk_elems, 1 << self.nl))
+        self._bufs: Optional[Tuple[Any, Any]] = None
+        self._cache: Dict[Any, Any] = {}
+        self.bytes_sent = 0
+        self.swaps_done = 0
+
+    def reset(self) -> None:
+        """Back to |0...0> in the canonical layout (the shard buffer is reused)."""
+        self.state.zero_()
+        if self.rank == 0:
+            self.ex.set_one(self.state)
+        self.pos_of = [self.n - 1 - q for q in range(self.n)]
+
+    # -- evolution ---------------------------------------------------------------------------
+    def run(self, plan: ShardedPlan, gates: Sequence[GateOp], gatebuf: Any) -> None:
+        assert plan.nqubits == self.n and plan.nglobal == self.g
+        for si, seg in enumerate(plan.segments):
+            if isinstance(seg, RunSegment):
+                assert seg.pos_of == self.pos_of, "segment compiled for a different qubit layout"
+                ops = [gates[gi] for gi in seg.gate_ids]
+                self.ex.run_gates(self.state, ops, gatebuf, self.n, self.nl, seg.pos_of, self.index_base,
+                                  plan.cache, (self.rank, si))  # fmt: skip
+            else:
+                self.swap(seg.pairs)
+                assert self.pos_of == seg.pos_of_after
+
+    def swap(self, pairs: Sequence[Tuple[int, int]]) -> None:
+        """Exchange the qubits at global positions P_i with those at local positions p_i."""
+        m = len(pairs)
+        order = sorted(range(m), key=lambda i: pairs[i][1])  # pack kernel wants ascending local bits
+        sel = [pairs[i][1] for i in order]
+        jbits = [pairs[i][0] - self.nl for i in order]  # rank bit of each swapped global position
+        assert all(0 <= j < self.g for j in jbits) and all(0 <= p < self.nl for p in sel)
+        mine = 0
+        for k, j in enumerate(jbits):
+            mine |= ((self.rank >> j) & 1) << k
+        block = 1 << (self.nl - m)
+        chunk = min(self.chunk, block)
+        if self._bufs is None or self._bufs[0].numel() < chunk * ((1 << m) - 1):
+            nb = chunk * ((1 << m) - 1)
+            self._bufs = (self.ex.empty(nb), self.ex.empty(nb))
+        sendbuf, recvbuf = self._bufs
+        peers = []
+        for x in range(1 << m):
+            if x == mine:
+                continue
+            peer = self.rank
+            for k, j in enumerate(jbits):
+                peer = (peer & ~(1 << j)) | (((x >> k) & 1) << j)
+            peers.append((x, peer))
+        for first in range(0, block, chunk):
+            cnt = min(chunk, block - first)
+            sends, recvs = [], []
+            for i, (x, peer) in enumerate(peers):
+                sb = sendbuf[i * chunk : i * chunk + cnt]
+                rb = recvbuf[i * chunk : i * chunk + cnt]
+                # the amplitudes with local pattern x move to the rank whose bits are x ...
+                self.ex.pack(self.state, sb, self.nl, sel, x, first, cnt, False)
+                sends.append((peer, sb))
+                recvs.append((peer, rb))
+            self.comm.exchange(sends, recvs)
+            for i, (x, peer) in enumerate(peers):
+                # ... and that rank's block with local pattern `mine` takes their place
+                self.ex.pack(self.state, recvbuf[i * chunk : i * chunk + cnt], self.nl, sel, x, first, cnt, True)
+            self.bytes_sent += 8 * cnt * len(peers)
+        inv = {p: q for q, p in enumerate(self.pos_of)}
+        for P, p in pairs:
+            qa, qb = inv[P], inv[p]
+            self.pos_of[qa], self.pos_of[qb] = p, P
+        self.swaps_done += 1
+
+    # -- read-out ----------------------------------------------------------------------------
+    def _mask(self, qubits: Sequence[int]) -> int:
+        m = 0
+        for q in qubits:
+            m ^= 1 << self.pos_of[q]
+        return m
+
+    def z_expectations(self, terms: Sequence[Sequence[int]]) -> Any:
+        """<Z_S> for every term (qubit lists), all-reduced over the ranks (float64)."""
+        out = self.ex.expect_z(self.state, self.nl, [self._mask(t) for t in terms], self.index_base)
+        return self.comm.all_reduce_sum(out)
+
+    def norm2(self) -> Any:
+        out = self.ex.expect_z(self.state, self.nl, [0], self.index_base)
+        return self.comm.all_reduce_sum(out)
+
+    def amplitude(self, bits: Sequence[int]) -> Any:
+        """Amplitude of the computational basis state `bits` (qubit 0 first), on every rank."""
+        phys = 0
+        for q, b in enumerate(bits):
+            phys |= (int(b) & 1) << self.pos_of[q]
+        owner, local = phys >> self.nl, phys & ((1 << self.nl) - 1)
+        v = self.ex.read(self.state, local if owner == self.rank else 0)
+        if owner != self.rank:
+            v = v * 0
+        # complex all-reduce as two reals (gloo has no complex sum on every version)
+        vr = self._view_real(v)
+        self.comm.all_reduce_sum(vr)
+        return v
+
+    @staticmethod
+    def _view_real(v: Any) -> Any:
+        import torch
+
+        return torch.view_as_real(v)
+
+
+# ---------------------------------------------------------------------------------------------
+_plan_cache: Dict[Any, Tuple[ShardedPlan, List[GateOp]]] = {}
+
+
+def evolve(circuit: Any, comm: Any = None, executor: Any = None, chunk_elems: int = 1 << 26,
+           reuse: Optional[ShardedStatevector] = None) -> ShardedStatevector:
+    """Run a `Circuit` (built with the ordinary gate API; construction never touches amplitudes,
+    tensorcircuit/basecircuit.py:183-371) as a statevector sharded over the ranks of `comm`."""
+    import torch
+
+    from . import svengine
+
+    if comm is None:
+        comm = TorchDistComm()
+    nodes, d_edges = circuit._copy()
+    n, init, gates = svengine.extract_gate_stream(nodes, d_edges, max_qubits=48)
+    if init is not None:
+        raise NotImplementedError("sharded evolution starts from |0...0>")
+    if executor is None:
+        dev = svengine.pick_device([g[0].tensor for g in gates])
+        executor = CudaExecutor(dev)
+    structure = tuple((g[1], svengine.gate_kind(g[0], g[2]), int(g[0].tensor.numel())) for g in gates)
+    key = (n, comm.world, structure)
+    hit = _plan_cache.get(key)
+    if hit is None:
+        ops, off = [], 0
+        for gi, (qubits, kind, numel) in enumerate(structure):
+            ops.append(GateOp(tuple(qubits), tuple(kind), off, gi))
+            off += numel
+        plan = compile_sharded(ops, n, comm.world.bit_length() - 1)
+        if len(_plan_cache) > 32:
+            _plan_cache.clear()
+        _plan_cache[key] = hit = (plan, ops)
+    plan, ops = hit
+    tensors = [g[0].tensor for g in gates]
+    if isinstance(executor, CudaExecutor):
+        gatebuf = svengine.build_gatebuf(tensors, executor.device)
+    else:
+        gatebuf = torch.cat([t.reshape(-1).to(torch.complex64) for t in tensors])
+    if reuse is not None and reuse.n == n:
+        sv = reuse
+        sv.reset()
+    else:
+        sv = ShardedStatevector(n, comm, executor, chunk_elems=chunk_elems)
+    sv.run(plan, ops, gatebuf)
+    sv.plan, sv.ops, sv.gatebuf = plan, ops, gatebuf  # type: ignore[attr-defined]
+    return sv

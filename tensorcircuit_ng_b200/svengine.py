@@ -45,7 +45,8 @@ def _other_end(edge: Any, node: Any, axis: int) -> Tuple[Any, int]:
     return edge.node1, edge.axis1
 
 
-def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any]):
+def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any],
+                        max_qubits: int = _MAX_STATE_QUBITS):
     """Walk every output wire back to its input; returns (n, init_node or None, gate list).
 
     gate list entries: (node, qubits tuple, packed_diagonal flag) sorted by creation order
@@ -54,7 +55,7 @@ def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any]):
     amplitude networks, MPS inputs, ...).
     """
     n = len(output_edge_order)
-    if n == 0 or n > _MAX_STATE_QUBITS:
+    if n == 0 or n > max_qubits:
         raise NotCircuitShaped("no dangling outputs" if n == 0 else "too many qubits for a statevector")
     node_ids = {id(x) for x in nodes}
     legs: Dict[int, List[Optional[int]]] = {}
