@@ -51,7 +51,11 @@ P_LAYERS = 8
 def qaoa_problem(n: int, p: int) -> Tuple[List[Tuple[int, int]], np.ndarray, np.ndarray]:
     import networkx as nx
 
-    g = nx.random_regular_graph(3, n, seed=0)
+    if n % 2 == 0:
+        g = nx.random_regular_graph(3, n, seed=0)
+    else:  # no 3-regular graph on an odd number of nodes: the last node hangs on nodes 0, 1, 2
+        g = nx.random_regular_graph(3, n - 1, seed=0)
+        g.add_edges_from([(n - 1, 0), (n - 1, 1), (n - 1, 2)])
     rng = np.random.default_rng(0)
     gam = rng.uniform(0, np.pi, p).astype(np.float32)
     bet = rng.uniform(0, np.pi, p).astype(np.float32)

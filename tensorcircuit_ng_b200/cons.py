@@ -302,10 +302,88 @@ def b200_contractor(nodes: List[Any], output_edge_order: Optional[List[Any]] = N
     return _tn_route(nodes, order, ignore_edge_order, optimizer, **kws)
 
 
+def diagonal_to_hyperedges(input_sets: List[List[str]], output_set: List[str], size_dict: Dict[str, int],
+                           sorted_nodes: Sequence[Any], tensors: List[Any]):  # fmt: skip
+    """Exact network simplification: a DIAGONAL k-qubit gate tensor [out.., in..] (cz, rzz, rz, cphase,
+    exp1(ZZ) ... — dense rank-2k `Gate` nodes in the reference, SURVEY §7 "hard parts") does not cut
+    the wires it sits on: out_j and in_j are the same index.  The node becomes its diagonal, a rank-k
+    tensor on k hyper-indices, which lowers the contraction width of circuit networks a lot
+    (a CZ crossing a cut costs 1 bit of bond instead of 2) — what the reference only gets from its
+    explicit `diagonal/cmz` hyperedge API (tensorcircuit/basecircuit.py:318-369).
+    Only nodes whose structural hint says "diag" are touched; returns rewritten copies."""
+    parent: Dict[str, str] = {}
+
+    def find(x: str) -> str:
+        while parent.get(x, x) != x:
+            parent[x] = parent.get(parent[x], parent[x])
+            x = parent[x]
+        return x
+
+    picked = []
+    out_syms = set(output_set)
+    for i, node in enumerate(sorted_nodes):
+        kind = getattr(node, "_b200_kind", None)
+        syms = input_sets[i]
+        if kind is None or kind[0] != "diag" or len(syms) % 2 or len(syms) == 0 or len(set(syms)) != len(syms):
+            continue
+        k = len(syms) // 2
+        if any(syms[j] in out_syms and syms[j + k] in out_syms for j in range(k)):
+            continue  # (an isolated diagonal gate with both legs dangling keeps its matrix form)
+        picked.append((i, k))
+        for j in range(k):
+            ra, rb = find(syms[j]), find(syms[j + k])
+            if ra != rb:
+                # keep the symbol of a dangling leg as the representative so the output order survives
+                if rb in out_syms:
+                    ra, rb = rb, ra
+                parent[rb] = ra
+    if not picked:
+        return input_sets, output_set, size_dict, tensors
+    new_inputs = [[find(x) for x in t] for t in input_sets]
+    new_tensors = list(tensors)
+    for i, k in picked:
+        t = tensors[i]
+        new_tensors[i] = t.reshape(2**k, 2**k).diagonal().reshape([2] * k)
+        new_inputs[i] = new_inputs[i][:k]
+    for t in new_inputs:
+        if len(set(t)) != len(t):  # a wire closed on itself through a diagonal gate: leave the network alone
+            return input_sets, output_set, size_dict, tensors
+    new_output = [find(x) for x in output_set]
+    if len(set(new_output)) != len(new_output):
+        return input_sets, output_set, size_dict, tensors
+    new_size = {find(k_): v for k_, v in size_dict.items()}
+    return new_inputs, new_output, new_size, new_tensors
+
+
+def wire_groups(input_sets: Sequence[Sequence[str]], sorted_nodes: Sequence[Any]) -> Dict[str, str]:
+    """symbol -> representative symbol of its qubit wire: leg j and leg j + k of every 2k-leg gate node
+    [out.., in..] (tensorcircuit/basecircuit.py:288-290) lie on the same wire.  A planner hint."""
+    parent: Dict[str, str] = {}
+
+    def find(x: str) -> str:
+        while parent.get(x, x) != x:
+            parent[x] = parent.get(parent[x], parent[x])
+            x = parent[x]
+        return x
+
+    for syms, node in zip(input_sets, sorted_nodes):
+        flag = str(getattr(node, "flag", ""))
+        if len(syms) % 2 == 0 and len(syms) >= 2 and (flag.startswith("gate") or hasattr(node, "_b200_kind")):
+            k = len(syms) // 2
+            for j in range(k):
+                ra, rb = find(syms[j]), find(syms[j + k])
+                if ra != rb:
+                    parent[rb] = ra
+    return {x: find(x) for t in input_sets for x in t}
+
+
 def _tn_route(nodes: List[Any], order: Optional[List[Any]], ignore_edge_order: bool, optimizer: Any,
               **kws: Any) -> Any:  # fmt: skip
     (input_sets, output_set, size_dict), sorted_nodes = get_tn_info(nodes)
     tensors = [n.tensor for n in sorted_nodes]
+    if kws.get("hyper_diagonal", True):
+        input_sets, output_set, size_dict, tensors = diagonal_to_hyperedges(
+            input_sets, output_set, size_dict, sorted_nodes, tensors)  # fmt: skip
     device = svengine.pick_device(tensors)
     tensors = [t if t.device == device else t.to(device) for t in tensors]
     dangling = sorted_edges(_subgraph_dangling(nodes))
