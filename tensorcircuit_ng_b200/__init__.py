@@ -32,3 +32,5 @@ from . import svengine  # noqa: F401
 from . import tnengine  # noqa: F401
 from . import expect  # noqa: F401
 from . import autograd  # noqa: F401
+from . import sharded  # noqa: F401
+from . import experimental  # noqa: F401

@@ -1,0 +1,96 @@
+"""Host logic of the sliced / distributed contraction path (CPU): slice partition, plan schema,
+slice-id -> index map, planners.  SURVEY §8a R13-R16."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slice_partition_matches_reference_rule(built):
+    from tensorcircuit_ng_b200.experimental import slice_partition
+
+    # tensorcircuit/experimental.py:877-894: S = ceil(n/G), row-major ids, -1 padding
+    p = slice_partition(10, 4)
+    assert p.shape == (4, 3) and p.dtype == np.int32
+    assert p.tolist() == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, -1, -1]]
+    assert slice_partition(1, 8).tolist() == [[0]] + [[-1]] * 7
+    assert slice_partition(16, 2).tolist() == [list(range(8)), list(range(8, 16))]
+
+
+def test_slice_values_mixed_radix(built):
+    from tensorcircuit_ng_b200 import planner
+
+    sd = {"a": 2, "b": 2, "c": 2}
+    seen = set()
+    for s in range(8):
+        v = planner.slice_values(s, ["a", "b", "c"], sd)
+        assert v == {"a": (s >> 2) & 1, "b": (s >> 1) & 1, "c": s & 1}  # last index fastest
+        seen.add(tuple(sorted(v.items())))
+    assert len(seen) == 8
+
+
+def _nodes_fn(params):
+    import tensorcircuit_ng_b200 as tc
+
+    c = tc.Circuit(4)
+    c.rx(range(4), theta=params["x"])
+    c.cnot([0, 1, 2], [1, 2, 3])
+    c.ry(range(4), theta=params["y"])
+    return c.expectation_before([tc.gates.z(), [-1]], reuse=False)
+
+
+def test_tree_data_schema_and_slicing(built):
+    """The plan interchange format of tensorcircuit/experimental.py:947-953 (+ our labels)."""
+    from tensorcircuit_ng_b200 import planner
+    from tensorcircuit_ng_b200.experimental import DistributedContractor
+
+    params = {"x": np.ones([4], dtype=np.float32), "y": 0.3 * np.ones([4], dtype=np.float32)}
+    td = DistributedContractor._get_tree_data(_nodes_fn, params, {"slicing_reconf_opts": {"target_size": 2**2}})
+    assert {"inputs", "output", "size_dict", "path", "sliced_inds"} <= set(td)
+    assert td["output"] == ()
+    st = planner.path_stats(td["inputs"], td["output"], td["size_dict"], td["path"], list(td["sliced_inds"]))
+    assert st["size"] <= 2**2 and st["nslices"] == 2 ** len(td["sliced_inds"]) and st["nslices"] >= 2
+    # a linear path consumes every tensor exactly once
+    n = len(td["inputs"])
+    live = n
+    for i, j in td["path"]:
+        assert 0 <= i < live and 0 <= j < live and i != j
+        live -= 1
+    assert live == 1
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 6), (4, 4, 8)])
+def test_planners_on_lattice_circuit(built, shape):
+    """Elimination / wire-sweep trees must not be worse than the pairwise greedy on lattice circuits."""
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import cons, planner
+
+    rows, cols, depth = shape
+    n = rows * cols
+    rng = np.random.default_rng(0)
+    c = tc.Circuit(n)
+    for l in range(depth):
+        for q in range(n):
+            c.rx(q, theta=float(rng.uniform(0, 6)))
+        for r in range(rows):
+            for q in range(cols):
+                i = r * cols + q
+                if l % 2 == 0 and q + 1 < cols and (q + r + l // 2) % 2 == 0:
+                    c.cz(i, i + 1)
+                if l % 2 == 1 and r + 1 < rows and (q + r + l // 2) % 2 == 0:
+                    c.cz(i, i + cols)
+    nodes = c.amplitude_before("0" * n)
+    (inp, out, sd), sn = cons.get_tn_info(nodes)
+    groups = cons.wire_groups(inp, sn)
+    assert len(set(groups.values())) == n
+    inp2, out2, sd2, _ = cons.diagonal_to_hyperedges(inp, out, sd, sn, [x.tensor for x in sn])
+    assert sum(len(t) for t in inp2) < sum(len(t) for t in inp)
+    te = planner.search_elimination(inp2, out2, sd2, groups=groups)
+    tg = planner.search(inp2, out2, sd2)
+    fe = planner.path_stats(inp2, out2, sd2, te["path"])["flops"]
+    fg = planner.path_stats(inp2, out2, sd2, tg["path"])["flops"]
+    assert fe <= 4 * fg
