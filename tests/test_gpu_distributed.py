@@ -59,7 +59,7 @@ def test_value_and_grad_matches_expectation_ps(cuda):
             assert abs(float(grad[key][i]) - fd) <= 2e-3
 
 
-@pytest.mark.parametrize("n,seed,target", [(8, 0, 2**6), (10, 1, 2**8), (12, 2, 2**30)])
+@pytest.mark.parametrize("n,seed,target", [(8, 0, 2**4), (10, 1, 2**5), (12, 2, 2**30)])
 def test_sliced_amplitudes_match_oracle(cuda, n, seed, target):
     import tensorcircuit_ng_b200 as tc
     from tensorcircuit_ng_b200.experimental import DistributedContractor
