@@ -8,20 +8,17 @@
 //
 // v1 (this file): SIMT FP32 kernel, shared-memory tiled:  C[b, m, n] = sum_k A[b,m,k] B[b,k,n]
 //   CTA tile 64 (m) x 64 (n) outputs, K chunks of 16, 256 threads, 4x4 micro-tile per thread.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "pass_core.cuh"
+#include "tn_common.cuh"
 #include "../../include/tcb200.h"
 
 namespace tcb {
 
-struct ContractParams {
-  int nb, nm, nn, nk;
-  int8_t batch_a[32], batch_b[32], batch_c[32];
-  int8_t m_a[32], m_c[32];
-  int8_t n_b[32], n_c[32];
-  int8_t k_a[32], k_b[32];
-  int conj_a, conj_b, accumulate;
-};
+int launch_contract_tc(const float2*, const float2*, float2*, const ContractParams&, cudaStream_t);
 
 __device__ __forceinline__ uint64_t deposit(uint64_t v, const int8_t* pos, int n) {
   uint64_t r = 0;
@@ -149,6 +146,22 @@ int launch_contract(const void* a, int64_t a_offset, const void* b, int64_t b_of
   p.conj_a = d->conj_a;
   p.conj_b = d->conj_b;
   p.accumulate = accumulate;
+  // kernel choice: the tensor-core kernel (tn_gemm_tc.cu) wants full 128-row tiles and enough work
+  // to amortise its pipeline; small / thin steps of a tree stay on the SIMT kernel.
+  // TCB_TN_KERNEL=simt|tc overrides (tests run both against the oracle).
+  {
+    static int forced = -1;  // 0 = auto, 1 = simt, 2 = tc
+    if (forced < 0) {
+      const char* e = getenv("TCB_TN_KERNEL");
+      forced = (e && !strcmp(e, "simt")) ? 1 : ((e && !strcmp(e, "tc")) ? 2 : 0);
+    }
+    const double macs = ldexp(1.0, p.nb + p.nm + p.nn + p.nk);
+    const bool want_tc = forced == 2 || (forced == 0 && p.nm >= 7 && p.nk >= 3 && p.nn >= 3 && macs >= 1 << 22);
+    if (want_tc)
+      return launch_contract_tc(reinterpret_cast<const float2*>(a) + a_offset,
+                                reinterpret_cast<const float2*>(b) + b_offset, reinterpret_cast<float2*>(c), p,
+                                stream);
+  }
   const uint64_t Mtot = 1ull << p.nm, Ntot = 1ull << p.nn;
   const uint64_t tiles = (((Mtot + TM - 1) / TM) * ((Ntot + TN - 1) / TN)) << p.nb;
   uint64_t grid = tiles;
