@@ -15,14 +15,18 @@
 // => 12 MMAs of 128 x BN x 8 per 8 complex k.
 //
 // Structure (one CTA per SM, persistent over output tiles of 128 (m) x BN (n)):
-//   warps 0-3  producers + epilogue: gather A / B from global memory with the bit-deposit
-//              addressing, split every component into TF32 hi / lo, store the eight operand tiles
-//              of a stage in the UMMA canonical K-major (no swizzle) core-matrix layout, publish
-//              them to the async proxy (fence.proxy.async) and arrive on the stage's `full`
-//              mbarrier; after the last k block: tcgen05.ld the two accumulators of their own TMEM
-//              lane quarter and scatter C (thread i owns row i of the tile).
-//   warp 4     TMEM allocation; one elected lane issues the MMAs and tcgen05.commit's each stage
-//              back to the producers (`empty`) and the finished tile to the epilogue (`tmem_full`).
+//   warps 0-7   producers: gather A / B from global memory with the bit-deposit addressing (32-byte
+//               vector loads when the two lowest k modes are the two lowest address bits), split
+//               every component into TF32 hi / lo, store the eight operand tiles of a stage in the
+//               UMMA canonical K-major (no swizzle) core-matrix layout, publish them to the async
+//               proxy (fence.proxy.async) and arrive on the stage's `full` mbarrier.
+//   warp 8      TMEM allocation; one elected lane issues the MMAs and tcgen05.commit's each stage
+//               back to the producers (`empty`) and the finished tile to the epilogue (`tmem_full`).
+//   warps 9-12  epilogue: tcgen05.ld the two accumulators of their TMEM lane quarter (warp % 4),
+//               scatter C, hand the accumulator stage back (`tmem_empty`).
+//   The accumulators are double buffered in TMEM (4 BN columns), so the producers already stream
+//   tile t+1 while the tensor core works on t and the epilogue drains t-1: the skinny steps of a
+//   contraction tree (one k block per tile) are latency-bound without that overlap.
 // Bound: HBM for the skinny steps of a contraction tree (K, N <~ 64), the TF32 pipe / 3 beyond.
 #include "common.cuh"
 #include "tn_common.cuh"
@@ -35,8 +39,9 @@ namespace tc {
 constexpr int BM = 128;       // rows of an output tile = TMEM lanes
 constexpr int KB = 16;        // complex k per stage (two MMA k-steps of 8)
 constexpr int STAGES = 3;
-constexpr int N_PROD = 128;   // producer / epilogue threads (warps 0-3)
-constexpr int N_THREADS = N_PROD + 32;
+constexpr int N_PROD = 256;   // producer threads (warps 0-7)
+constexpr int N_EPI = 128;    // epilogue threads (warps 9-12)
+constexpr int N_THREADS = N_PROD + 32 + N_EPI;
 constexpr uint32_t LBO = 128;       // bytes between core matrices adjacent in K
 constexpr uint32_t SBO = 4 * 128;   // bytes between 8-row groups (KB / 4 core matrices each)
 
@@ -119,6 +124,46 @@ __device__ __forceinline__ uint32_t tile_off(int row, int kgroup) {  // 16-byte 
   return (uint32_t)(row >> 3) * SBO + (uint32_t)kgroup * LBO + (uint32_t)(row & 7) * 16;
 }
 
+// split four complex values into the hi / lo TF32 planes and store one 16-byte slot per plane
+__device__ __forceinline__ void split_store(unsigned char* st, uint32_t plane_bytes, uint32_t o, const float2 (&v)[4]) {
+  float hr[4], lr[4], hi_[4], li[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hr[j] = tf32_round(v[j].x);
+    lr[j] = tf32_round(v[j].x - hr[j]);
+    hi_[j] = tf32_round(v[j].y);
+    li[j] = tf32_round(v[j].y - hi_[j]);
+  }
+  *reinterpret_cast<float4*>(st + 0 * plane_bytes + o) = make_float4(hr[0], hr[1], hr[2], hr[3]);
+  *reinterpret_cast<float4*>(st + 1 * plane_bytes + o) = make_float4(lr[0], lr[1], lr[2], lr[3]);
+  *reinterpret_cast<float4*>(st + 2 * plane_bytes + o) = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
+  *reinterpret_cast<float4*>(st + 3 * plane_bytes + o) = make_float4(li[0], li[1], li[2], li[3]);
+}
+// four consecutive k of one row: two 16-byte loads when they are contiguous in memory
+__device__ __forceinline__ void load4(const float2* __restrict__ X, uint64_t base, const uint64_t* dlo, int g, bool vec,
+                                      bool ok, uint64_t k0, uint64_t Ktot, bool conj, float2 (&v)[4]) {
+  if (!ok) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = make_float2(0.f, 0.f);
+    return;
+  }
+  if (vec) {
+    const float4* q = reinterpret_cast<const float4*>(X + (base | dlo[4 * g]));
+    const float4 x = q[0], y = q[1];
+    v[0] = make_float2(x.x, x.y);
+    v[1] = make_float2(x.z, x.w);
+    v[2] = make_float2(y.x, y.y);
+    v[3] = make_float2(y.z, y.w);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (k0 + 4 * g + j < Ktot) ? X[base | dlo[4 * g + j]] : make_float2(0.f, 0.f);
+  }
+  if (conj) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j].y = -v[j].y;
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(N_THREADS, 1)
 gemm_tc_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float2* C, ContractParams p) {
@@ -127,28 +172,39 @@ gemm_tc_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float
   unsigned char* stages = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * St::BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  uint64_t* offBn = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // [BN]
-  uint64_t* offCn = offBn + BN;                                  // [BN]
+  uint64_t* tmem_full = empty + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* offBn = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // [BN]   (producers)
+  uint64_t* offCn = offBn + BN;                                  // [BN]   (epilogue)
+  uint64_t* dAlo = offCn + BN;                                   // [KB] deposit of the low 4 k bits into A
+  uint64_t* dBlo = dAlo + KB;                                    // [KB] ... into B
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;  // Cr: [0, BN), Ci: [BN, 2 BN)
+  constexpr uint32_t ACC_COLS = 2 * BN;        // one accumulator stage: Cr [0, BN), Ci [BN, 2 BN)
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+  constexpr int MMA_WARP = N_PROD / 32;
 
   if (tid == N_PROD) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, N_PROD);
       mbar_init(empty + s, 1);
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, N_PROD);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full + a, 1);
+      mbar_init(tmem_empty + a, N_EPI);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  const int nklo = p.nk < 4 ? p.nk : 4;
+  if (tid < KB) {
+    dAlo[tid] = deposit((uint64_t)tid, p.k_a, nklo);
+    dBlo[tid] = deposit((uint64_t)tid, p.k_b, nklo);
   }
   tc_fence_before();
   __syncthreads();
@@ -160,115 +216,104 @@ gemm_tc_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float
   const uint64_t tiles_per_batch = tiles_m * tiles_n;
   const uint64_t total_tiles = tiles_per_batch << p.nb;
   const uint32_t nkb = (uint32_t)((Ktot + KB - 1) / KB);
+  const bool vecA = p.nk >= 2 && p.k_a[0] == 0 && p.k_a[1] == 1;
+  const bool vecB = p.nk >= 2 && p.k_b[0] == 0 && p.k_b[1] == 1;
+  const bool vecC = p.nn >= 1 && p.n_c[0] == 0;  // (N is then even, so a pair never straddles the edge)
 
   uint32_t it = 0;      // k blocks processed by this CTA so far (stage ring position)
   uint32_t tcount = 0;  // tiles processed by this CTA so far
-  if (warp < 4) {
-    // ===================== producers + epilogue: thread `tid` owns tile row `tid` =====================
-    for (uint64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const uint64_t bt = tile / tiles_per_batch, tr = tile % tiles_per_batch;
-      const uint64_t m0 = (tr / tiles_n) * BM, n0 = (tr % tiles_n) * BN;
-      const uint64_t a_b = deposit(bt, p.batch_a, p.nb), b_b = deposit(bt, p.batch_b, p.nb),
-                     c_b = deposit(bt, p.batch_c, p.nb);
-      const bool row_ok = m0 + tid < Mtot;
-      const uint64_t offAm = a_b | deposit(m0 + tid, p.m_a, p.nm);
-      const uint64_t offCm = c_b | deposit(m0 + tid, p.m_c, p.nm);
-      // the previous tile's epilogue is done with the column tables (barrier among the 128 producers)
-      asm volatile("bar.sync 1, %0;" ::"n"(N_PROD));
-      if (tid < BN) {
-        offBn[tid] = b_b | deposit(n0 + tid, p.n_b, p.nn);
-        offCn[tid] = deposit(n0 + tid, p.n_c, p.nn);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(N_PROD));
-
-      for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
-        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-        mbar_wait(empty + s, ph ^ 1);
-        unsigned char* st = stages + (size_t)s * St::BYTES;
-        const uint64_t k0 = (uint64_t)kb * KB;
-        // k offsets of this block (every thread needs all 16: computed redundantly per group of 4)
+  if (warp < MMA_WARP) {
+    // ===================== producers =====================
+    // Work items = (tile, k block), flattened; the global loads of item w+1 are issued before item w
+    // is split and stored, so every thread keeps two batches in flight (a skinny step has ONE k block
+    // per tile: without the prefetch each tile pays a full DRAM latency).
+    const int row = tid & (BM - 1), half = tid >> 7;  // A: row `row`, k groups {2 half, 2 half + 1}
+    constexpr int UB = (BN * (KB / 4) + N_PROD - 1) / N_PROD;  // B units (row n, k group g) per thread
+    struct Batch {
+      float2 va[2][4];
+      float2 vb[UB][4];
+    };
+    uint64_t cur_tile = ~0ull, offAm = 0, offBn_r[UB];
+    bool row_ok = false, col_ok[UB];
+    auto issue = [&](uint64_t tile, uint32_t kb, Batch& r) {
+      if (tile != cur_tile) {  // new tile: row / column bases
+        cur_tile = tile;
+        const uint64_t bt = tile / tiles_per_batch, tr = tile % tiles_per_batch;
+        const uint64_t m0 = (tr / tiles_n) * BM, n0 = (tr % tiles_n) * BN;
+        row_ok = m0 + row < Mtot;
+        offAm = deposit(bt, p.batch_a, p.nb) | deposit(m0 + row, p.m_a, p.nm);
+        const uint64_t b_b = deposit(bt, p.batch_b, p.nb);
 #pragma unroll
-        for (int g = 0; g < KB / 4; ++g) {
-          // ---- A: row tid, k = 4g .. 4g+3 ----
-          float hr[4], lr[4], hi_[4], li[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t k = k0 + 4 * g + j;
-            float2 v = make_float2(0.f, 0.f);
-            if (row_ok && k < Ktot) v = A[offAm | deposit(k, p.k_a, p.nk)];
-            if (p.conj_a) v.y = -v.y;
-            hr[j] = tf32_round(v.x);
-            lr[j] = tf32_round(v.x - hr[j]);
-            hi_[j] = tf32_round(v.y);
-            li[j] = tf32_round(v.y - hi_[j]);
-          }
-          const uint32_t o = tile_off(tid, g);
-          *reinterpret_cast<float4*>(st + 0 * St::A_TILE + o) = make_float4(hr[0], hr[1], hr[2], hr[3]);
-          *reinterpret_cast<float4*>(st + 1 * St::A_TILE + o) = make_float4(lr[0], lr[1], lr[2], lr[3]);
-          *reinterpret_cast<float4*>(st + 2 * St::A_TILE + o) = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
-          *reinterpret_cast<float4*>(st + 3 * St::A_TILE + o) = make_float4(li[0], li[1], li[2], li[3]);
-        }
-        // ---- B: units (row n, k group g), BN * 4 of them over 128 threads ----
-        for (int u = tid; u < BN * (KB / 4); u += N_PROD) {
-          const int n = u % BN, g = u / BN;
-          const bool col_ok = n0 + n < Ntot;
-          const uint64_t ob = offBn[n];
-          float hr[4], lr[4], hi_[4], li[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t k = k0 + 4 * g + j;
-            float2 v = make_float2(0.f, 0.f);
-            if (col_ok && k < Ktot) v = B[ob | deposit(k, p.k_b, p.nk)];
-            if (p.conj_b) v.y = -v.y;
-            hr[j] = tf32_round(v.x);
-            lr[j] = tf32_round(v.x - hr[j]);
-            hi_[j] = tf32_round(v.y);
-            li[j] = tf32_round(v.y - hi_[j]);
-          }
-          const uint32_t o = 4 * St::A_TILE + tile_off(n, g);
-          *reinterpret_cast<float4*>(st + 0 * St::B_TILE + o) = make_float4(hr[0], hr[1], hr[2], hr[3]);
-          *reinterpret_cast<float4*>(st + 1 * St::B_TILE + o) = make_float4(lr[0], lr[1], lr[2], lr[3]);
-          *reinterpret_cast<float4*>(st + 2 * St::B_TILE + o) = make_float4(hi_[0], hi_[1], hi_[2], hi_[3]);
-          *reinterpret_cast<float4*>(st + 3 * St::B_TILE + o) = make_float4(li[0], li[1], li[2], li[3]);
-        }
-        fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
-        mbar_arrive(full + s);
-      }
-
-      // ---- epilogue: the accumulators of this tile ----
-      mbar_wait(tmem_full, tcount & 1);
-      tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 8) {
-        float cr[8], ci[8];
-        tmem_ld8(trow + c0, cr);
-        tmem_ld8(trow + BN + c0, ci);
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (n0 + c0 + j < Ntot) {
-              const uint64_t addr = offCm | offCn[c0 + j];
-              float2 v = make_float2(cr[j], ci[j]);
-              if (p.accumulate) {
-                const float2 old = C[addr];
-                v.x += old.x;
-                v.y += old.y;
-              }
-              C[addr] = v;
-            }
-          }
+        for (int i = 0; i < UB; ++i) {
+          const int u = tid + i * N_PROD, n = u % BN;
+          col_ok[i] = u < BN * (KB / 4) && n0 + n < Ntot;
+          offBn_r[i] = b_b | deposit(n0 + n, p.n_b, p.nn);
         }
       }
-      tc_fence_before();
-      mbar_arrive(tmem_empty);
+      const uint64_t k0 = (uint64_t)kb * KB;
+      // k = k0 + j with k0 a multiple of 16: deposit(k) = deposit(high bits) | deposit(j)
+      const uint64_t hiA = p.nk > 4 ? deposit((uint64_t)kb, p.k_a + 4, p.nk - 4) : 0;
+      const uint64_t hiB = p.nk > 4 ? deposit((uint64_t)kb, p.k_b + 4, p.nk - 4) : 0;
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg)
+        load4(A, offAm | hiA, dAlo, 2 * half + gg, vecA, row_ok && k0 + 4 * (2 * half + gg) < Ktot, k0, Ktot,
+              p.conj_a != 0, r.va[gg]);
+#pragma unroll
+      for (int i = 0; i < UB; ++i) {
+        const int g = (tid + i * N_PROD) / BN;
+        load4(B, offBn_r[i] | hiB, dBlo, g, vecB, col_ok[i] && k0 + 4 * g < Ktot, k0, Ktot, p.conj_b != 0, r.vb[i]);
+      }
+    };
+    auto commit = [&](const Batch& r) {
+      const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+      mbar_wait(empty + s, ph ^ 1);
+      unsigned char* st = stages + (size_t)s * St::BYTES;
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg) split_store(st, St::A_TILE, tile_off(row, 2 * half + gg), r.va[gg]);
+#pragma unroll
+      for (int i = 0; i < UB; ++i) {
+        const int u = tid + i * N_PROD;
+        if (u < BN * (KB / 4)) split_store(st + 4 * St::A_TILE, St::B_TILE, tile_off(u % BN, u / BN), r.vb[i]);
+      }
+      fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+      mbar_arrive(full + s);
+      ++it;
+    };
+    Batch b0, b1;
+    uint64_t tile = blockIdx.x;
+    uint32_t kb = 0;
+    bool have = tile < total_tiles;
+    if (have) issue(tile, kb, b0);
+    while (have) {
+      // next item
+      uint64_t ntile = tile;
+      uint32_t nkb_i = kb + 1;
+      if (nkb_i == nkb) {
+        nkb_i = 0;
+        ntile = tile + gridDim.x;
+      }
+      const bool more = ntile < total_tiles;
+      if (more) issue(ntile, nkb_i, b1);
+      commit(b0);
+      if (!more) break;
+      tile = ntile;
+      kb = nkb_i + 1;
+      if (kb == nkb) {
+        kb = 0;
+        tile = ntile + gridDim.x;
+      }
+      const bool more2 = tile < total_tiles;
+      if (more2) issue(tile, kb, b0);
+      commit(b1);
+      have = more2;
     }
-  } else {
-    // ===================== MMA issuer (warp 4) =====================
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
     constexpr uint32_t ID_POS = make_idesc(BN, 0), ID_NEG = make_idesc(BN, 1);
-    const uint32_t d_cr = tmem_base, d_ci = tmem_base + BN;
     for (uint64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      mbar_wait(tmem_empty, (tcount & 1) ^ 1);  // the epilogue has drained the accumulators
+      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      const uint32_t d_cr = tmem_base + a * ACC_COLS, d_ci = d_cr + BN;
+      mbar_wait(tmem_empty + a, aph ^ 1);  // the epilogue has drained this accumulator stage
       tc_fence_after();
       for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
@@ -300,24 +345,75 @@ gemm_tc_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float
             tc_mma(d_ci, ar_h, bi_h, ID_POS, 1u);
             tc_mma(d_ci, ai_h, br_h, ID_POS, 1u);
           }
-          tc_commit(empty + s);                      // the stage is free once these MMAs have read it
-          if (kb + 1 == nkb) tc_commit(tmem_full);   // ... and the tile is complete
+          tc_commit(empty + s);                          // the stage is free once these MMAs have read it
+          if (kb + 1 == nkb) tc_commit(tmem_full + a);   // ... and the tile is complete
         }
         __syncwarp();
       }
+    }
+  } else {
+    // ===================== epilogue: row = TMEM lane = 32 (warp % 4) + lane =====================
+    const int row = (warp & 3) * 32 + lane;
+    const int etid = tid - (N_PROD + 32);
+    for (uint64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      const uint64_t bt = tile / tiles_per_batch, tr = tile % tiles_per_batch;
+      const uint64_t m0 = (tr / tiles_n) * BM, n0 = (tr % tiles_n) * BN;
+      const uint64_t c_b = deposit(bt, p.batch_c, p.nb);
+      const bool row_ok = m0 + row < Mtot;
+      const uint64_t offCm = c_b | deposit(m0 + row, p.m_c, p.nm);
+      asm volatile("bar.sync 2, %0;" ::"n"(N_EPI));
+      if (etid < BN) offCn[etid] = deposit(n0 + etid, p.n_c, p.nn);
+      asm volatile("bar.sync 2, %0;" ::"n"(N_EPI));
+      mbar_wait(tmem_full + a, aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + a * ACC_COLS + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 8) {
+        float cr[8], ci[8];
+        tmem_ld8(trow + c0, cr);
+        tmem_ld8(trow + BN + c0, ci);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (n0 + c0 + j < Ntot) {
+              const uint64_t addr = offCm | offCn[c0 + j];
+              float2 v = make_float2(cr[j], ci[j]);
+              if (p.accumulate) {
+                const float2 old = C[addr];
+                v.x += old.x;
+                v.y += old.y;
+              }
+              if (vecC && !(j & 1)) {  // n, n+1 adjacent in C: one 16-byte store for the pair
+                float2 w = make_float2(cr[j + 1], ci[j + 1]);
+                if (p.accumulate) {
+                  const float2 old = C[addr + 1];
+                  w.x += old.x;
+                  w.y += old.y;
+                }
+                *reinterpret_cast<float4*>(C + addr) = make_float4(v.x, v.y, w.x, w.y);
+              } else if (!vecC) {
+                C[addr] = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty + a);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
 template <int BN>
 static size_t smem_bytes() {
-  return (size_t)STAGES * Stage<BN>::BYTES + (2 * STAGES + 2) * 8 + 16 + (size_t)2 * BN * 8 + 128;
+  return (size_t)STAGES * Stage<BN>::BYTES + (2 * STAGES + 4) * 8 + 16 + (size_t)2 * BN * 8 + (size_t)2 * KB * 8 + 128;
 }
 
 template <int BN>
@@ -340,12 +436,14 @@ static int launch(const float2* a, const float2* b, float2* c, const ContractPar
 
 }  // namespace tc
 
-// N tile: the smallest of 16 / 32 / 64 that covers N (M = 128 needs N % 16 == 0; more N tiles beyond 64)
+// N tile: the smallest of 16 / 32 / 64 / 128 that covers N (M = 128 needs N % 16 == 0; more N tiles
+// beyond 128: every extra column of a tile amortises the hi / lo split of the A rows)
 int launch_contract_tc(const float2* a, const float2* b, float2* c, const ContractParams& p, cudaStream_t stream) {
   const uint64_t Ntot = 1ull << p.nn;
   if (Ntot <= 16) return tc::launch<16>(a, b, c, p, stream);
   if (Ntot <= 32) return tc::launch<32>(a, b, c, p, stream);
-  return tc::launch<64>(a, b, c, p, stream);
+  if (Ntot <= 64) return tc::launch<64>(a, b, c, p, stream);
+  return tc::launch<128>(a, b, c, p, stream);
 }
 
 }  // namespace tcb

@@ -103,6 +103,18 @@ def contract_raw(a: torch.Tensor, modes_a: Sequence[Mode], b: torch.Tensor, mode
     for m in modes_b:
         if m not in pc and m not in fixed and m not in pa:
             raise _lib.EngineError(f"mode {m!r} appears only in the right operand and is not an output")
+    # Inside a class the logical bit order is free (it only has to agree between the operands):
+    # K bit i <-> i-th lowest position in A, N bit i <-> i-th lowest position in C, M likewise, so
+    # that the kernels can use vector loads / stores when a class occupies an operand's lowest bits.
+    def _sort(keys: Sequence[str], by: str) -> None:
+        order = sorted(range(len(lists[by])), key=lambda i: lists[by][i])
+        for kname in keys:
+            lists[kname] = [lists[kname][i] for i in order]
+
+    _sort(("k_a", "k_b"), "k_a")
+    _sort(("n_b", "n_c"), "n_c")
+    _sort(("m_a", "m_c"), "m_c")
+    _sort(("batch_a", "batch_b", "batch_c"), "batch_c")
     for k, v in lists.items():
         if len(v) > 32:
             raise _lib.EngineError("too many modes in one class (max 32)")
