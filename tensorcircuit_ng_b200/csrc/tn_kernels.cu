@@ -120,6 +120,136 @@ contract_kernel(const float2* __restrict__ A, const float2* __restrict__ B, floa
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming kernel for the skinny steps of a contraction tree: a big tensor absorbs a small one,
+//   C[b, m, n] = sum_k A[b, m, k] B[b, k, n],   K, N <= 8, the whole of B at most 64 elements
+// (batch modes are the hyper-indices a diagonal gate leaves on the wire it sits on).
+// These steps dominate sliced lattice plans (variable elimination contracts one or two indices at a
+// time) and are pure HBM streaming: one thread per (b, m) row reads its K amplitudes, applies the
+// K x N block held in shared memory and writes its N outputs — the statevector gate kernel in
+// tensor-network clothes.  Rows are numbered so that consecutive threads take consecutive low bits
+// of the OUTPUT address (M modes are sorted by their position in C on the host), so both the reads
+// and the writes of a warp are coalesced; the bit-deposit of the low 10 row bits comes from a
+// shared-memory table, the high bits are deposited once per 1024-row chunk.
+constexpr int SR_THREADS = 256, SR_ROWS = 4, SR_CHUNK_BITS = 10;
+
+template <int NK, int NN>
+__global__ void __launch_bounds__(SR_THREADS)
+stream_contract_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float2* C, ContractParams p) {
+  constexpr int K = 1 << NK, N = 1 << NN;
+  __shared__ uint64_t tabA[1 << SR_CHUNK_BITS], tabC[1 << SR_CHUNK_BITS];
+  __shared__ float2 sB[64];  // [batch][k][n]
+  // row bits: first the M modes (ascending position in C), then the batch modes
+  const int nrow = p.nm + p.nb;
+  auto row_a = [&](int i) { return i < p.nm ? p.m_a[i] : p.batch_a[i - p.nm]; };
+  auto row_c = [&](int i) { return i < p.nm ? p.m_c[i] : p.batch_c[i - p.nm]; };
+  const int nlo = nrow < SR_CHUNK_BITS ? nrow : SR_CHUNK_BITS;
+  for (int t = threadIdx.x; t < (1 << nlo); t += SR_THREADS) {
+    uint64_t xa = 0, xc = 0;
+    for (int i = 0; i < nlo; ++i) {
+      const uint64_t bit = (t >> i) & 1;
+      xa |= bit << row_a(i);
+      xc |= bit << row_c(i);
+    }
+    tabA[t] = xa;
+    tabC[t] = xc;
+  }
+  for (int e = threadIdx.x; e < (K * N) << p.nb; e += SR_THREADS) {
+    const int bb = e / (K * N), k = (e / N) % K, n = e % N;
+    uint64_t off = 0;
+    for (int i = 0; i < p.nb; ++i) off |= (uint64_t)((bb >> i) & 1) << p.batch_b[i];
+    for (int i = 0; i < NK; ++i) off |= (uint64_t)((k >> i) & 1) << p.k_b[i];
+    for (int i = 0; i < NN; ++i) off |= (uint64_t)((n >> i) & 1) << p.n_b[i];
+    float2 v = B[off];
+    if (p.conj_b) v.y = -v.y;
+    sB[e] = v;
+  }
+  uint64_t offAk[K], offCn[N];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    uint64_t off = 0;
+#pragma unroll
+    for (int i = 0; i < NK; ++i) off |= (uint64_t)((k >> i) & 1) << p.k_a[i];
+    offAk[k] = off;
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    uint64_t off = 0;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) off |= (uint64_t)((n >> i) & 1) << p.n_c[i];
+    offCn[n] = off;
+  }
+  __syncthreads();
+  const uint64_t rows = 1ull << nrow;
+  const uint64_t nchunks = (rows + (1ull << SR_CHUNK_BITS) - 1) >> SR_CHUNK_BITS;
+  for (uint64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    uint64_t hiA = 0, hiC = 0;
+    for (int i = SR_CHUNK_BITS; i < nrow; ++i) {
+      const uint64_t bit = (ch >> (i - SR_CHUNK_BITS)) & 1ull;
+      hiA |= bit << row_a(i);
+      hiC |= bit << row_c(i);
+    }
+    float2 a[SR_ROWS][K];
+    uint64_t ca[SR_ROWS];
+    bool ok[SR_ROWS];
+    int bsel[SR_ROWS];
+#pragma unroll
+    for (int r = 0; r < SR_ROWS; ++r) {
+      const int t = threadIdx.x + r * SR_THREADS;
+      const uint64_t rowid = ((uint64_t)ch << SR_CHUNK_BITS) | (uint64_t)t;
+      ok[r] = rowid < rows;
+      bsel[r] = (int)(rowid >> p.nm) * (K * N);
+      const uint64_t ra = hiA | tabA[t & ((1 << nlo) - 1)];
+      ca[r] = hiC | tabC[t & ((1 << nlo) - 1)];
+#pragma unroll
+      for (int k = 0; k < K; ++k) a[r][k] = ok[r] ? A[ra | offAk[k]] : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < SR_ROWS; ++r) {
+      if (!ok[r]) continue;
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float2 x = a[r][k];
+          if (p.conj_a) x.y = -x.y;
+          acc = cfma(x, sB[bsel[r] + k * N + n], acc);
+        }
+        const uint64_t addr = ca[r] | offCn[n];
+        if (p.accumulate) {
+          const float2 old = C[addr];
+          acc.x += old.x;
+          acc.y += old.y;
+        }
+        C[addr] = acc;
+      }
+    }
+  }
+}
+
+template <int NK, int NN>
+static int launch_stream(const float2* a, const float2* b, float2* c, const ContractParams& p, cudaStream_t stream) {
+  const uint64_t rows = 1ull << (p.nm + p.nb);
+  uint64_t grid = (rows + (1ull << SR_CHUNK_BITS) - 1) >> SR_CHUNK_BITS;
+  const uint64_t cap = (uint64_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  stream_contract_kernel<NK, NN><<<(unsigned)grid, SR_THREADS, 0, stream>>>(a, b, c, p);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_stream_dispatch(const float2* a, const float2* b, float2* c, const ContractParams& p,
+                                  cudaStream_t stream) {
+#define SRC(NK_, NN_) \
+  if (p.nk == NK_ && p.nn == NN_) return launch_stream<NK_, NN_>(a, b, c, p, stream);
+  SRC(0, 0) SRC(0, 1) SRC(0, 2) SRC(0, 3) SRC(1, 0) SRC(1, 1) SRC(1, 2) SRC(1, 3)
+  SRC(2, 0) SRC(2, 1) SRC(2, 2) SRC(2, 3) SRC(3, 0) SRC(3, 1) SRC(3, 2) SRC(3, 3)
+#undef SRC
+  set_error("tcb_tn_contract: streaming kernel called with nk=%d nn=%d", p.nk, p.nn);
+  return 2;
+}
+
 int launch_contract(const void* a, int64_t a_offset, const void* b, int64_t b_offset, void* c,
                     const tcb_contract_desc* d, int accumulate, cudaStream_t stream) {
   TCB_REQUIRE(d != nullptr, "tcb_tn_contract: null descriptor");
@@ -155,6 +285,12 @@ int launch_contract(const void* a, int64_t a_offset, const void* b, int64_t b_of
       const char* e = getenv("TCB_TN_KERNEL");
       forced = (e && !strcmp(e, "simt")) ? 1 : ((e && !strcmp(e, "tc")) ? 2 : 0);
     }
+    // B has no batch modes, K and N are tiny, many rows: the streaming kernel (HBM bound)
+    if (forced != 2 && !(forced == 1 && getenv("TCB_TN_NOSTREAM")) && p.nk <= 3 && p.nn <= 3 &&
+        p.nb + p.nk + p.nn <= 6 && p.nm + p.nb >= 10)
+      return launch_stream_dispatch(reinterpret_cast<const float2*>(a) + a_offset,
+                                    reinterpret_cast<const float2*>(b) + b_offset, reinterpret_cast<float2*>(c), p,
+                                    stream);
     const double macs = ldexp(1.0, p.nb + p.nm + p.nn + p.nk);
     const bool want_tc = forced == 2 || (forced == 0 && p.nm >= 7 && p.nk >= 3 && p.nn >= 3 && macs >= 1 << 22);
     if (want_tc)

@@ -38,7 +38,9 @@ def check(nb, nm, nn, nk, seed, conj_a=False, conj_b=False, tol=None):
 
 if __name__ == "__main__":
     cases = [(0, 7, 4, 3), (0, 8, 6, 5), (1, 7, 3, 4), (0, 5, 2, 1), (2, 9, 5, 6), (0, 10, 7, 7), (0, 7, 0, 9), (3, 7, 4, 0),
-             (0, 12, 6, 6), (0, 3, 8, 2)]
+             (0, 12, 6, 6), (0, 3, 8, 2),
+             # skinny steps: the streaming kernel (auto / simt modes)
+             (0, 14, 1, 1), (0, 12, 3, 2), (2, 11, 2, 1), (3, 10, 0, 3), (1, 13, 3, 0), (0, 10, 2, 3), (2, 9, 1, 2)]
     for i, c in enumerate(cases):
         check(*c, seed=i, conj_a=bool(i % 2), conj_b=bool((i // 2) % 2))
     print("ok", os.environ.get("TCB_TN_KERNEL", "auto"))

@@ -29,5 +29,5 @@ def bench(nm, nn, nk, nb=0, reps=5):
     print(f"M=2^{nm} N=2^{nn} K=2^{nk} b=2^{nb}: ours {best:8.3f} ms {flops/best/1e9:8.1f} TFLOP/s {byt/best/1e6:7.0f} GB/s | torch.bmm {tb:8.3f} ms {flops/tb/1e9:8.1f} TFLOP/s", flush=True)
 
 print("kernel:", os.environ.get("TCB_TN_KERNEL", "auto"))
-for s in [(22, 3, 3), (24, 4, 4), (20, 6, 6), (18, 7, 7), (16, 8, 8), (14, 10, 10), (12, 12, 12)]:
+for s in [(26, 1, 1), (25, 2, 1), (24, 2, 2), (22, 3, 3), (24, 4, 4), (20, 6, 6), (18, 7, 7), (16, 8, 8), (14, 10, 10), (12, 12, 12)]:
     bench(*s)
