@@ -30,6 +30,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -416,6 +417,210 @@ def build_random_circuit(mod: Any, n: int, depth: int, thetas: Any, kinds: np.nd
     return c
 
 
+def build_rcs(mod: Any, rows: int, cols: int, depth: int, seed: int = 0) -> Any:
+    """BASELINE.json configs[4]: rows x cols grid, per cycle one random gate of
+    {sqrt X = rx(pi/2), sqrt Y = ry(pi/2), sqrt W = u(pi/2, -pi/4, pi/4)} per qubit (the mapping of
+    `from_qsim_file`, tensorcircuit/abstractcircuit.py:1319-1326; never the same gate twice in a row on
+    a qubit), then cz on one coupler class of the ABCDCDAB pattern."""
+    n = rows * cols
+    rng = np.random.default_rng(seed)
+    c = mod.Circuit(n)
+    last = [-1] * n
+
+    def pairs(kind: str) -> List[Tuple[int, int]]:
+        out = []
+        for r in range(rows):
+            for q in range(cols):
+                i = r * cols + q
+                if kind == "A" and q + 1 < cols and (q + r) % 2 == 0:
+                    out.append((i, i + 1))
+                if kind == "B" and q + 1 < cols and (q + r) % 2 == 1:
+                    out.append((i, i + 1))
+                if kind == "C" and r + 1 < rows and (q + r) % 2 == 0:
+                    out.append((i, i + cols))
+                if kind == "D" and r + 1 < rows and (q + r) % 2 == 1:
+                    out.append((i, i + cols))
+        return out
+
+    seq = "ABCDCDAB"
+    for l in range(depth):
+        for q in range(n):
+            k = int(rng.choice([x for x in range(3) if x != last[q]]))
+            last[q] = k
+            if k == 0:
+                c.rx(q, theta=np.pi / 2)
+            elif k == 1:
+                c.ry(q, theta=np.pi / 2)
+            else:
+                c.u(q, theta=np.pi / 2, phi=-np.pi / 4, lbd=np.pi / 4)
+        for a, b in pairs(seq[l % 8]):
+            c.cz(a, b)
+    return c
+
+
+def rcs_plan_path(rows: int, cols: int, depth: int, log2_target: int) -> str:
+    return os.path.join(ROOT, "plans", f"rcs_{rows}x{cols}_d{depth}_t{log2_target}.pkl")
+
+
+def run_contraction(args: argparse.Namespace) -> None:
+    """BASELINE.json configs[4]: one amplitude of the 7x7 depth-20 random circuit as a sliced tensor
+    network.  A step contracts `--slices` slices per GPU of the full plan (the full job has
+    2^(#sliced indices) slices; TFLOP/s is a per-slice rate, so the sample is representative)."""
+    import pickle
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import _lib, planner
+    from tensorcircuit_ng_b200.experimental import DistributedContractor
+
+    torch.set_default_device(dev)
+    rows, cols, depth = args.grid, args.grid, args.depth
+    bits = "0" * (rows * cols)
+
+    def nodes_fn(_: Any) -> Any:
+        return build_rcs(tc, rows, cols, depth).amplitude_before(bits)
+
+    path = rcs_plan_path(rows, cols, depth, args.log2_target)
+    t0 = time.perf_counter()
+    if os.path.exists(path):
+        td = pickle.load(open(path, "rb"))
+        plan_src = os.path.relpath(path, ROOT)
+    else:
+        td = None
+        if rank == 0:
+            td = DistributedContractor._get_tree_data(
+                nodes_fn, None, {"slicing_reconf_opts": {"target_size": 2**args.log2_target}})  # fmt: skip
+        if world > 1:
+            box = [td]
+            dist.broadcast_object_list(box, src=0)
+            td = box[0]
+        plan_src = f"searched at start ({time.perf_counter() - t0:.0f} s)"
+    dc = DistributedContractor(nodes_fn, torch.zeros(1), tree_data=td)
+    st = dc.stats
+    nsl = max(1, min(args.slices, dc.nslices))
+    my_ids = [(rank + world * i) % dc.nslices for i in range(nsl)]
+    # algorithmic work per slice: 8 real flops per complex MAC; bytes: every step reads its
+    # two operands and writes its result once
+    flops_slice = 8.0 * st["flops"]
+    bytes_slice = 8.0 * sum(2.0**a + 2.0**b + 2.0**c for a, b, c, _ in st["steps"])
+    tensors = dc._arrays(torch.zeros(1))
+    stream = torch.cuda.current_stream()
+
+    def step() -> Any:
+        acc = None
+        for s in my_ids:
+            r = dc._single_slice(tensors, s)
+            acc = r if acc is None else acc + r
+        return acc
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            amp = step()
+        e1.record(stream)
+        barrier()
+        launches = _lib.launch_count - l0
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        # e2e: the public call (DistributedContractor over its own slice list is the full job; here the same
+        # sample through nodes_fn -> arrays -> slices -> host)
+        t0 = time.perf_counter()
+        arrays2 = dc._arrays(torch.zeros(1))
+        acc = None
+        for s in my_ids:
+            r = dc._single_slice(arrays2, s)
+            acc = r if acc is None else acc + r
+        amp_host = complex(acc.cpu())
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    tflops = flops_slice * nsl * world / (ms_per_step * 1e-3) / 1e12
+    gbs = bytes_slice * nsl / (ms_per_step * 1e-3) / 1e9  # per GPU
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    if rank == 0:
+        line = {
+            "metric": "sliced-contraction TFLOP/s",
+            "value": tflops,
+            "unit": "TFLOP/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "complex64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"rcs_{rows}x{cols}_depth{depth}_amplitude_sliced",
+                "plan": plan_src,
+                "planner": td.get("planner", "external tree_data"),
+                "hyper_diagonal": bool(td.get("hyper_diagonal", False)),
+                "tensors": len(dc.inputs),
+                "sliced_indices": len(dc.sliced_inds),
+                "log2_nslices": math.log2(dc.nslices),
+                "slices_per_gpu_per_step": nsl,
+                "log10_cmacs_per_slice": math.log10(st["flops"]),
+                "log2_size": math.log2(st["size"]),
+                "log2_write": math.log2(st["write"]),
+                "l2": "intermediates larger than L2",
+                "multi_gpu": "slices scattered over the ranks (tensorcircuit/experimental.py:877-894), one all-reduce per full job",
+                "amplitude_sample": [amp_host.real, amp_host.imag],
+                "full_job_estimate_s": ms_per_step * 1e-3 / nsl * dc.nslices / world,
+            },
+            "roofline": {
+                "kernel": "tcb::stream_contract_kernel / tcb::tc::gemm_tc_kernel (plan is streaming-dominated)",
+                "bound": "hbm",
+                "achieved": gbs,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": gbs / peak,
+                "traffic": None,
+                "alg_bytes_per_slice": bytes_slice,
+            },
+            "cpu_baseline": None,
+            "e2e": {
+                "value": flops_slice * nsl * world / e2e_s / 1e12,
+                "unit": "TFLOP/s",
+                "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 8,
+                "ms_per_step": e2e_s * 1e3,
+            },
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_sharded(args: argparse.Namespace) -> None:
     import torch
     import torch.distributed as dist
@@ -625,9 +830,13 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--qubits", type=int, default=None)
     ap.add_argument("--depth", type=int, default=20, help="layers of the sharded random circuit (N > 1)")
-    ap.add_argument("--workload", default="qaoa", choices=["qaoa", "random"],
-                    help="N > 1: `qaoa` = the N=1 family at n = 30 + log2 N (weak scaling, default); "
-                         "`random` = BASELINE configs[3] (use --qubits 34..36)")
+    ap.add_argument("--workload", default="qaoa", choices=["qaoa", "random", "contraction"],
+                    help="`qaoa` (default): statevector, N=1 n=30, N>1 the same family at n = 30 + log2 N (weak "
+                         "scaling); `random` = BASELINE configs[3] (N > 1, use --qubits 34..36); `contraction` = "
+                         "BASELINE configs[4], sliced 7x7 depth-20 amplitude")
+    ap.add_argument("--grid", type=int, default=7)
+    ap.add_argument("--slices", type=int, default=1, help="contraction: slices per GPU per step")
+    ap.add_argument("--log2-target", type=int, default=30, help="contraction: slicing target size")
     ap.add_argument("--ref-qubits", type=int, default=24, help="size of the bounded CPU sample (even: 3-regular graph)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -637,6 +846,8 @@ def main() -> None:
         args.qubits = N_QUBITS_1GPU
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "contraction":
+        run_contraction(args)
     elif int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_sharded(args)
     else:

@@ -276,6 +276,21 @@ int launch_contract(const void* a, int64_t a_offset, const void* b, int64_t b_of
   p.conj_a = d->conj_a;
   p.conj_b = d->conj_b;
   p.accumulate = accumulate;
+  // C = A.B is symmetric under (A, m) <-> (B, n): make the larger free side the row side, which is
+  // what the streaming kernel (rows = M + batch) and the tensor-core kernel (128-row tiles) want
+  if (p.nm < p.nn) {
+    for (int i = 0; i < 32; ++i) {
+      int8_t t;
+      t = p.m_a[i]; p.m_a[i] = p.n_b[i]; p.n_b[i] = t;
+      t = p.m_c[i]; p.m_c[i] = p.n_c[i]; p.n_c[i] = t;
+      t = p.k_a[i]; p.k_a[i] = p.k_b[i]; p.k_b[i] = t;
+      t = p.batch_a[i]; p.batch_a[i] = p.batch_b[i]; p.batch_b[i] = t;
+    }
+    int t = p.nm; p.nm = p.nn; p.nn = t;
+    t = p.conj_a; p.conj_a = p.conj_b; p.conj_b = t;
+    const void* tp = a; a = b; b = tp;
+    const int64_t to = a_offset; a_offset = b_offset; b_offset = to;
+  }
   // kernel choice: the tensor-core kernel (tn_gemm_tc.cu) wants full 128-row tiles and enough work
   // to amortise its pipeline; small / thin steps of a tree stay on the SIMT kernel.
   // TCB_TN_KERNEL=simt|tc overrides (tests run both against the oracle).

@@ -94,7 +94,10 @@ class DistributedContractor:
         self.nslices = 1
         for s in self.sliced_inds:
             self.nslices *= int(self.size_dict[s])
-        self.batched_slice_indices = slice_partition(self.nslices, self.num_devices)
+        # (materialised only when it is small: a sampled run of a 2^57-slice plan never needs the table)
+        self.batched_slice_indices = (
+            slice_partition(self.nslices, self.num_devices) if self.nslices <= (1 << 24) else None
+        )
         self.stats = planner.path_stats(self.inputs, self.output, self.size_dict, self.path, self.sliced_inds)
         self._report_tree_info()
 
@@ -161,11 +164,12 @@ class DistributedContractor:
         fixed = planner.slice_values(int(slice_idx), self.sliced_inds, self.size_dict) if self.sliced_inds else None
         return tnengine.contract_tree(tensors, self.inputs, self.output, self.path, fixed=fixed)
 
-    def _my_slices(self) -> List[int]:
-        row = self.batched_slice_indices[self.rank if self.num_devices > 1 and self._dist is not None else 0]
-        if self._dist is None and self.num_devices > 1:  # single process driving "devices": all slices
-            row = self.batched_slice_indices.reshape(-1)
-        return [int(s) for s in row if int(s) != PADDING_VALUE]
+    def _my_slices(self) -> Any:
+        """This rank's row of the (G, S) partition: slice ids [rank * S, min((rank + 1) * S, nslices))."""
+        if self._dist is None or self.num_devices == 1:  # single process: all slices
+            return range(self.nslices)
+        per = -(-self.nslices // self.num_devices)
+        return range(min(self.rank * per, self.nslices), min((self.rank + 1) * per, self.nslices))
 
     def _arrays(self, params: Any) -> List[torch.Tensor]:
         _, _, _, tensors, _ = self._network(self.nodes_fn, params, self.hyper)

@@ -67,6 +67,12 @@ def contract_raw(a: torch.Tensor, modes_a: Sequence[Mode], b: torch.Tensor, mode
     No autograd; see `contract` for the differentiable entry point.
     """
     fixed = fixed or {}
+    # the larger free side becomes the row side (A): streaming / 128-row tiles run along it
+    out_set = set(modes_out)
+    free_a = sum(1 for m in modes_a if m in out_set and m not in modes_b)
+    free_b = sum(1 for m in modes_b if m in out_set and m not in modes_a)
+    if free_b > free_a:
+        a, b, modes_a, modes_b, conj_a, conj_b = b, a, modes_b, modes_a, conj_b, conj_a
     a, pos_a, cja, _ = _physical(a)
     b, pos_b, cjb, _ = _physical(b)
     _lib.require_cuda(a, "left operand")

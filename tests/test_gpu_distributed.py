@@ -100,7 +100,7 @@ def _nccl_worker(rank, world, port, out):
     params = {"x": np.ones([4], dtype=np.float32), "y": 0.3 * np.ones([4], dtype=np.float32)}
     dc = DistributedContractor(_nodes_fn, params, {"slicing_reconf_opts": {"target_size": 2**2}})
     v, g = dc.value_and_grad(params)
-    torch.save({"v": v.cpu(), "gy": g["y"].cpu(), "mine": dc._my_slices(), "nslices": dc.nslices}, f"{out}.{rank}")
+    torch.save({"v": v.cpu(), "gy": g["y"].cpu(), "mine": list(dc._my_slices()), "nslices": dc.nslices}, f"{out}.{rank}")
     dist.destroy_process_group()
 
 
@@ -121,3 +121,28 @@ def test_distributed_contractor_two_gpus(cuda, tmp_path):
     for p in parts:
         np.testing.assert_allclose(float(p["v"]), float(v1), atol=1e-6)
         np.testing.assert_allclose(p["gy"].numpy(), g1["y"].cpu().numpy(), atol=1e-5)
+
+
+def test_rcs_amplitude_tn_vs_statevector(cuda):
+    """configs[4] family at a size the statevector path can check: 5x5 depth-12 random circuit, amplitude of
+    |0...0> by sliced tensor-network contraction (committed plan file) == wavefunction()[0]."""
+    import pickle
+
+    sys.path.insert(0, ROOT)
+    import bench
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200.experimental import DistributedContractor
+
+    rows = cols = 5
+    depth = 12
+    c = bench.build_rcs(tc, rows, cols, depth)
+    psi0 = complex(c.wavefunction()[0])
+    nodes_fn = lambda _: bench.build_rcs(tc, rows, cols, depth).amplitude_before("0" * 25)  # noqa: E731
+    td = pickle.load(open(bench.rcs_plan_path(rows, cols, depth, 30), "rb"))
+    dc = DistributedContractor(nodes_fn, torch.zeros(1), tree_data=td)
+    amp = complex(dc.value(torch.zeros(1)))
+    assert abs(amp - psi0) <= 1e-6, (amp, psi0)
+    # forced slicing of the same network
+    dc2 = DistributedContractor(nodes_fn, torch.zeros(1), {"slicing_reconf_opts": {"target_size": 2**16}})
+    assert dc2.nslices >= 2
+    assert abs(complex(dc2.value(torch.zeros(1))) - psi0) <= 1e-6
