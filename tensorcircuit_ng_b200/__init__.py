@@ -34,3 +34,4 @@ from . import expect  # noqa: F401
 from . import autograd  # noqa: F401
 from . import sharded  # noqa: F401
 from . import experimental  # noqa: F401
+from . import backend  # noqa: F401

@@ -374,3 +374,44 @@ def test_tn_route_gradient(cuda):
         loss = c.expectation([tc.gates.x(), [1]], reuse=False).real ** 2
     loss.backward()
     np.testing.assert_allclose(float(param.grad[0, 1]), -2.146e-3, atol=1e-5)
+
+
+def test_vvag_tfim_vqe_batch(cuda):
+    """configs[1] at test size: TFIM hardware-efficient ansatz (examples/benchmark_jax_vs_torch_vqe.py:160-200),
+    `vvag` over a batch of parameter sets; values vs the oracle, gradients vs central differences of the
+    oracle (atol 1e-4 relative: tests/test_backends.py:916-941 style)."""
+    import tensorcircuit_ng_b200 as tc
+
+    n, depth, batch = 8, 2, 3
+    rng = np.random.default_rng(5)
+    params = rng.normal(0, 0.4, size=(batch, depth, 2, n)).astype(np.float32)
+
+    def energy(mod, p, to_float):
+        c = mod.Circuit(n)
+        for q in range(n):
+            c.h(q)
+        for l in range(depth):
+            for q in range(n - 1):
+                c.rzz(q, q + 1, theta=p[l, 0, q])
+            for q in range(n):
+                c.rx(q, theta=p[l, 1, q])
+        e = 0.0
+        for q in range(n - 1):
+            e = e - to_float(c.expectation_ps(z=[q, q + 1]))
+        for q in range(n):
+            e = e - to_float(c.expectation_ps(x=[q]))
+        return e
+
+    f = lambda p: energy(tc, p, lambda v: v.real)  # noqa: E731
+    vals, grads = tc.backend.vvag(f, argnums=0, vectorized_argnums=0)(torch.from_numpy(params).cuda())
+    assert vals.shape == (batch,) and grads.shape == params.shape
+    ref = lambda p: float(energy(tc_oracle, p, lambda v: np.real(v)))  # noqa: E731
+    for b in range(batch):
+        assert abs(float(vals[b]) - ref(params[b])) <= 1e-4
+    eps = 2e-2
+    for b, l, k, q in [(0, 0, 0, 0), (1, 1, 1, 3), (2, 0, 1, 7), (2, 1, 0, 5)]:
+        pp, pm = params[b].copy(), params[b].copy()
+        pp[l, k, q] += eps
+        pm[l, k, q] -= eps
+        fd = (ref(pp) - ref(pm)) / (2 * eps)
+        assert abs(float(grads[b, l, k, q]) - fd) <= 3e-3, (b, l, k, q, float(grads[b, l, k, q]), fd)
