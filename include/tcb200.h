@@ -50,6 +50,11 @@ int tcb_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total
  * index_base : OR-ed into the flat index when a control/diagonal qubit lives above the
  *              local shard (sharded statevector); 0 on one GPU.              */
 int tcb_sv_init_zero(void* state, int nbits, int64_t batch, void* stream);
+/* product state: state[x] = prod_p vecs[p][bit p of (x | index_base)], p < total_bits; vecs is a device
+ * array of total_bits x 2 complex64 indexed by flat bit POSITION (positions >= nbits are rank bits of a
+ * sharded state and are read from index_base).  One write pass.                                       */
+int tcb_sv_init_product(void* state, int nbits, const void* vecs, int total_bits, uint64_t index_base,
+                        void* stream);
 int tcb_sv_apply_dense(void* state, int nbits, int64_t batch, const int* bitpos_host, int k,
                        const void* mat, int64_t mat_batch_stride, void* stream);
 /* diagonal gate given as 2^k complex64 entries spaced `diag_stride` apart (2^k+1 for the

@@ -59,6 +59,7 @@ SYMBOLS = {
     "tcb_last_error": (c_char_p, []),
     "tcb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_uint64)]),
     "tcb_sv_init_zero": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
+    "tcb_sv_init_product": (c_int, [c_void_p, c_int, c_void_p, c_int, c_uint64, c_void_p]),
     "tcb_sv_apply_dense": (
         c_int,
         [c_void_p, c_int, c_int64, POINTER(c_int), c_int, c_void_p, c_int64, c_void_p],

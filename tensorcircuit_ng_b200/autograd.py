@@ -29,8 +29,12 @@ assume_unitary = True
 def _forward(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor, init: Optional[torch.Tensor]) -> torch.Tensor:
     nbits = cc.plan.nbits
     if init is None:
-        state = svengine.new_zero_state(nbits, 1, gatebuf.device)
+        state = torch.empty(1 << nbits, dtype=torch.complex64, device=gatebuf.device)
+        _lib.require_cuda(state, "state")
+        cc.start(state, gatebuf)
     else:
+        if cc.prefix_levels:
+            raise _lib.EngineError("a circuit compiled with absorbed leading gates cannot start from `inputs`")
         state = init.detach().to(torch.complex64).resolve_conj().reshape(-1).clone()
         _lib.require_cuda(state, "inputs")
     cc.run(state, gatebuf)

@@ -30,6 +30,7 @@ int sm_count() {
 }
 
 int launch_init_zero(void*, int, int64_t, cudaStream_t);
+int launch_init_product(void*, int, const void*, int, uint64_t, cudaStream_t);
 int launch_dense(void*, int, int64_t, const int*, int, const void*, int64_t, cudaStream_t);
 int launch_diag(void*, int, int64_t, const int*, int, const void*, int64_t, int64_t, uint64_t,
                 cudaStream_t);
@@ -90,6 +91,13 @@ int tcb_sv_apply_diag(void* state, int nbits, int64_t batch, const int* bitpos, 
   NOTNULL(diag, "tcb_sv_apply_diag");
   return launch_diag(state, nbits, batch, bitpos, k, diag, diag_stride, mat_batch_stride, index_base,
                      S(stream));
+}
+
+int tcb_sv_init_product(void* state, int nbits, const void* vecs, int total_bits, uint64_t index_base,
+                        void* stream) {
+  NOTNULL(state, "tcb_sv_init_product");
+  NOTNULL(vecs, "tcb_sv_init_product");
+  return launch_init_product(state, nbits, vecs, total_bits, index_base, S(stream));
 }
 
 int tcb_sv_run_pass(void* state, int nbits, int64_t batch, const int32_t* program,

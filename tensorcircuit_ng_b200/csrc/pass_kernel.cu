@@ -25,6 +25,22 @@ namespace tcb {
 
 #ifdef PASS_PROFILE
 __device__ unsigned long long g_pass_prof[16];
+// timeline of the CTAs resident on SM 0: [cta slot][tile][phase stamp] (globaltimer ns)
+__device__ unsigned long long g_trace[8][64][6];
+__device__ int g_trace_slots;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+#define TRACE_DECL int _slot = -1, _tk = 0; if (threadIdx.x == 0 && smid() == 0) _slot = atomicAdd(&g_trace_slots, 1);
+#define TRACE(ph) do { if (_slot >= 0 && _slot < 8 && _tk < 64) g_trace[_slot][_tk][ph] = gtime(); } while (0)
+#define TRACE_NEXT ++_tk
 #define PROF_DECL unsigned long long _pt = clock64();
 #define PROF_MARK(slot)                                            \
   do {                                                             \
@@ -37,6 +53,9 @@ __device__ unsigned long long g_pass_prof[16];
 #else
 #define PROF_DECL
 #define PROF_MARK(slot)
+#define TRACE_DECL
+#define TRACE(ph)
+#define TRACE_NEXT
 #endif
 
 __device__ __forceinline__ void cp_async16(float2* smem_dst, const float2* gmem_src) {
@@ -186,6 +205,7 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
     const int phase = blockIdx.x / A.n_sm;
     for (int i = 0; i < phase; ++i) __nanosleep(A.stagger_ns);
   }
+  TRACE_DECL
   long long cur_batch = -1;
   for (unsigned long long tg = blockIdx.x; tg < A.total_tiles; tg += gridDim.x) {
     const long long b = (long long)(tg >> A.log_tiles_per_state);
@@ -193,6 +213,7 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
     const uint64_t cta_bits = base | A.index_base;
     const float2* gates = A.gatebuf + (size_t)b * A.gate_bstride;
     PROF_DECL
+    TRACE(0);
     // ---- load: 16-byte cp.async straight into the swizzled tile (no registers held) ----
     {
       const float2* src_b = A.src + ((size_t)b << A.nbits) + (base | (uint64_t)((2 * tid) & lowmask));
@@ -218,9 +239,11 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
     prologue_fill_threads(sprog, A.prog_words, pool, cta_bits, tid, NT, nstatic, nshort_end);
     prologue_fill_warps(sprog, A.prog_words, pool, cta_bits, warp, lane, NWARPS, nshort_end, nfill);
     PROF_MARK(1);
+    TRACE(1);
     cp_async_wait_all();
     __syncthreads();
     PROF_MARK(2);
+    TRACE(2);
 
     // ---- sub-passes ----
     const int32_t* sp = hdr + HDR_WORDS;
@@ -235,6 +258,7 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
       sp += sp[S_WORDS];
     }
     PROF_MARK(4);
+    TRACE(3);
 
     // ---- store ----
     {
@@ -250,8 +274,11 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
       for (int u = 0; u < N_IO; ++u) stg_stream(reinterpret_cast<float4*>(dst_b + off[u]), v[u]);
     }
     PROF_MARK(5);
+    TRACE(4);
     __syncthreads();  // the tile and sprog may be overwritten from here on
     PROF_MARK(6);
+    TRACE(5);
+    TRACE_NEXT;
   }
 }
 
@@ -320,6 +347,13 @@ int launch_pass(const void* src, void* dst, int nbits, int64_t batch, const int3
 }
 
 #ifdef PASS_PROFILE
+extern "C" int tcb_debug_pass_trace(unsigned long long* out_host /* [8][64][6] */, int* nslots) {
+  cudaMemcpyFromSymbol(out_host, g_trace, sizeof(unsigned long long) * 8 * 64 * 6);
+  cudaMemcpyFromSymbol(nslots, g_trace_slots, sizeof(int));
+  int z = 0;
+  cudaMemcpyToSymbol(g_trace_slots, &z, sizeof(int));
+  return 0;
+}
 extern "C" int tcb_debug_pass_prof(unsigned long long* out16_host, int reset) {
   cudaMemcpyFromSymbol(out16_host, g_pass_prof, sizeof(unsigned long long) * 16);
   if (reset) {

@@ -165,6 +165,56 @@ int launch_diag(void* state, int nbits, int64_t batch, const int* bitpos, int k,
 }
 
 // ---------------------------------------------------------------------------------
+// product state: state[x] = prod_p v[p][bit p of (x | index_base)]   (one write pass, no read).
+// The gates every qubit sees before its first multi-qubit gate act on |0> alone, so the host
+// folds them into per-qubit 2-vectors (the reference's _merge_single_gates does the same to its
+// input nodes, tensorcircuit/cons.py:298-374) and the first passes over the state disappear.
+__global__ void __launch_bounds__(256)
+init_product_kernel(float4* __restrict__ state, const float2* __restrict__ vecs, int nbits, int total_bits,
+                    unsigned long long index_base, uint64_t ngroups) {
+  __shared__ float2 sv[64 * 2];
+  for (int i = threadIdx.x; i < 2 * total_bits; i += blockDim.x) sv[i] = vecs[i];
+  __syncthreads();
+  const int nlow = nbits < 5 ? nbits : 5;  // amplitudes per thread: 2^nlow (nbits >= 1)
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const unsigned long long hi = (g << nlow) | index_base;
+    float2 c = make_float2(1.f, 0.f);
+    for (int p = nlow; p < total_bits; ++p) c = cmul(c, sv[2 * p + (int)((hi >> p) & 1ull)]);
+    float2 a[32];
+    a[0] = c;
+    for (int p = 0; p < nlow; ++p) {
+      const float2 v0 = sv[2 * p], v1 = sv[2 * p + 1];
+      for (int i = (1 << p) - 1; i >= 0; --i) {
+        a[i | (1 << p)] = cmul(a[i], v1);
+        a[i] = cmul(a[i], v0);
+      }
+    }
+    if (nlow == 5) {
+      float4* dst = state + (g << 4);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dst[i] = make_float4(a[2 * i].x, a[2 * i].y, a[2 * i + 1].x, a[2 * i + 1].y);
+    } else {
+      float2* dst = reinterpret_cast<float2*>(state) + (g << nlow);
+      for (int i = 0; i < (1 << nlow); ++i) dst[i] = a[i];
+    }
+  }
+}
+
+int launch_init_product(void* state, int nbits, const void* vecs, int total_bits, uint64_t index_base,
+                        cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_init_product: nbits=%d", nbits);
+  TCB_REQUIRE(total_bits >= nbits && total_bits <= 64, "tcb_sv_init_product: total_bits=%d", total_bits);
+  const int nlow = nbits < 5 ? nbits : 5;
+  const uint64_t ngroups = 1ull << (nbits - nlow);
+  init_product_kernel<<<grid_for(ngroups, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(state),
+                                                                  reinterpret_cast<const float2*>(vecs), nbits,
+                                                                  total_bits, (unsigned long long)index_base, ngroups);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 // Z-string expectations: one read of the state for all terms.
 //
 // <Z_S> = sum_x (-1)^{popc(x & m)} |psi_x|^2 is a Walsh-Hadamard coefficient of the probability

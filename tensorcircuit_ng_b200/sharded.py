@@ -185,7 +185,9 @@ class TorchDistComm:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def exchange(self, sends: List[Tuple[int, Any]], recvs: List[Tuple[int, Any]]) -> None:
+    def exchange_async(self, sends: List[Tuple[int, Any]], recvs: List[Tuple[int, Any]]) -> Any:
+        """Post the P2P batch (NCCL runs it on its own stream, after the work already queued on the
+        current stream); `wait` makes the current stream wait for it."""
         import torch
 
         def real(t: Any) -> Any:  # complex tensors travel as (re, im) views of the same memory
@@ -196,7 +198,14 @@ class TorchDistComm:
             ops.append(self.dist.P2POp(self.dist.isend, real(t), peer, self.group))
         for peer, t in recvs:
             ops.append(self.dist.P2POp(self.dist.irecv, real(t), peer, self.group))
-        for w in self.dist.batch_isend_irecv(ops):
+        return self.dist.batch_isend_irecv(ops)
+
+    def exchange(self, sends: List[Tuple[int, Any]], recvs: List[Tuple[int, Any]]) -> None:
+        self.wait(self.exchange_async(sends, recvs))
+
+    @staticmethod
+    def wait(works: Any) -> None:
+        for w in works or []:
             w.wait()
 
     def all_reduce_sum(self, t: Any) -> Any:
@@ -262,10 +271,10 @@ class ShardedStatevector:
             mine |= ((self.rank >> j) & 1) << k
         block = 1 << (self.nl - m)
         chunk = min(self.chunk, block)
-        if self._bufs is None or self._bufs[0].numel() < chunk * ((1 << m) - 1):
-            nb = chunk * ((1 << m) - 1)
-            self._bufs = (self.ex.empty(nb), self.ex.empty(nb))
-        sendbuf, recvbuf = self._bufs
+        nb = chunk * ((1 << m) - 1)
+        if self._bufs is None or self._bufs[0].numel() < nb:
+            # two send + two receive staging buffers: chunk c+1 is packed while chunk c is on the wire
+            self._bufs = tuple(self.ex.empty(nb) for _ in range(4))
         peers = []
         for x in range(1 << m):
             if x == mine:
@@ -274,21 +283,40 @@ class ShardedStatevector:
             for k, j in enumerate(jbits):
                 peer = (peer & ~(1 << j)) | (((x >> k) & 1) << j)
             peers.append((x, peer))
-        for first in range(0, block, chunk):
-            cnt = min(chunk, block - first)
+        async_ok = hasattr(self.comm, "exchange_async")
+
+        def post(ci: int, first: int, cnt: int) -> Any:
+            sendbuf, recvbuf = self._bufs[ci & 1], self._bufs[2 + (ci & 1)]
             sends, recvs = [], []
             for i, (x, peer) in enumerate(peers):
                 sb = sendbuf[i * chunk : i * chunk + cnt]
-                rb = recvbuf[i * chunk : i * chunk + cnt]
                 # the amplitudes with local pattern x move to the rank whose bits are x ...
                 self.ex.pack(self.state, sb, self.nl, sel, x, first, cnt, False)
                 sends.append((peer, sb))
-                recvs.append((peer, rb))
+                recvs.append((peer, recvbuf[i * chunk : i * chunk + cnt]))
+            if async_ok:
+                return self.comm.exchange_async(sends, recvs)
             self.comm.exchange(sends, recvs)
+            return None
+
+        def finish(ci: int, first: int, cnt: int, works: Any) -> None:
+            if async_ok:
+                self.comm.wait(works)
+            recvbuf = self._bufs[2 + (ci & 1)]
             for i, (x, peer) in enumerate(peers):
                 # ... and that rank's block with local pattern `mine` takes their place
                 self.ex.pack(self.state, recvbuf[i * chunk : i * chunk + cnt], self.nl, sel, x, first, cnt, True)
             self.bytes_sent += 8 * cnt * len(peers)
+
+        pending = None
+        for ci, first in enumerate(range(0, block, chunk)):
+            cnt = min(chunk, block - first)
+            works = post(ci, first, cnt)  # (reads positions this rank has not unpacked into yet)
+            if pending is not None:
+                finish(*pending)
+            pending = (ci, first, cnt, works)
+        if pending is not None:
+            finish(*pending)
         inv = {p: q for q, p in enumerate(self.pos_of)}
         for P, p in pairs:
             qa, qb = inv[P], inv[p]

@@ -173,13 +173,48 @@ def gate_kind(node: Any, packed_diag: bool) -> Tuple[Any, ...]:
 
 
 # ---------------------------------------------------------------------------------------
+def split_prefix(ops: Sequence[GateOp], nq: int) -> Tuple[List[List[GateOp]], List[GateOp]]:
+    """(per-qubit leading 1q gates, remaining gates).  The 1q gates a qubit sees before its first
+    multi-qubit gate act on |0> alone: they fold into a per-qubit 2-vector (what the reference's
+    `_merge_single_gates` does to its input nodes, tensorcircuit/cons.py:298-374)."""
+    open_ = [True] * nq
+    prefix: List[List[GateOp]] = [[] for _ in range(nq)]
+    rest: List[GateOp] = []
+    for g in ops:
+        if g.k == 1 and open_[g.qubits[0]] and g.kind[0] in ("dense", "diag", "diagvec"):
+            prefix[g.qubits[0]].append(g)
+        else:
+            for q in g.qubits:
+                open_[q] = False
+            rest.append(g)
+    return prefix, rest
+
+
 class CompiledCircuit:
     """A plan plus its device-resident programs (uploaded once, reused every step)."""
 
-    def __init__(self, plan: Plan, ops: List[GateOp], device: torch.device) -> None:
+    def __init__(self, plan: Plan, ops: List[GateOp], device: torch.device,
+                 prefix: Optional[List[List[GateOp]]] = None, nq: Optional[int] = None) -> None:  # fmt: skip
         self.plan = plan
-        self.ops = ops
+        self.ops = ops  # the WHOLE circuit in program order (the adjoint backward pass walks it)
         self.device = device
+        # product-state start: per level, (flat bit positions, [m, 4] indices into cat(gatebuf, 0))
+        self.prefix_levels: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        self.nq = nq if nq is not None else plan.nbits
+        if prefix is not None and any(prefix):
+            depth = max(len(p) for p in prefix)
+            for lvl in range(depth):
+                pos, idx = [], []
+                for q, gl in enumerate(prefix):
+                    if lvl < len(gl):
+                        g = gl[lvl]
+                        pos.append(self.nq - 1 - q)
+                        if g.kind[0] == "diagvec":
+                            idx.append([g.mat_off, -1, -1, g.mat_off + 1])
+                        else:
+                            idx.append([g.mat_off, g.mat_off + 1, g.mat_off + 2, g.mat_off + 3])
+                self.prefix_levels.append((torch.tensor(pos, dtype=torch.long, device=device),
+                                           torch.tensor(idx, dtype=torch.long, device=device)))  # fmt: skip
         chunks = [s.program for s in plan.steps if isinstance(s, PassStep)]
         self.offsets: List[int] = []
         off = 0
@@ -192,9 +227,25 @@ class CompiledCircuit:
         else:
             self.programs = torch.zeros(1, dtype=torch.int32, device=device)
 
+    def start(self, state: torch.Tensor, gatebuf: torch.Tensor) -> None:
+        """Write the initial state of the compiled part: |0...0>, or the product state that the
+        absorbed leading 1q gates make of it (one write pass, no read)."""
+        nbits = self.plan.nbits
+        if not self.prefix_levels:
+            _lib.call("tcb_sv_init_zero", state.data_ptr(), nbits, 1, _lib.stream_ptr())
+            return
+        gb = torch.cat([gatebuf.detach(), torch.zeros(1, dtype=gatebuf.dtype, device=gatebuf.device)])
+        v = torch.zeros(self.nq, 2, dtype=torch.complex64, device=self.device)
+        v[:, 0] = 1.0
+        for pos, idx in self.prefix_levels:
+            m = gb[idx].reshape(-1, 2, 2)
+            v[pos] = torch.bmm(m, v[pos].unsqueeze(-1)).squeeze(-1)
+        _lib.call("tcb_sv_init_product", state.data_ptr(), nbits, v.data_ptr(), self.nq, 0, _lib.stream_ptr())
+
     def run(self, state: torch.Tensor, gatebuf: torch.Tensor, batch: int = 1, gate_batch_stride: int = 0,
             index_base: int = 0) -> None:  # fmt: skip
-        """Apply the circuit IN PLACE to `state` ([batch * 2^nbits] complex64 on the GPU)."""
+        """Apply the compiled part of the circuit IN PLACE to `state` ([batch * 2^nbits] complex64 on
+        the GPU).  With absorbed leading gates the state must come from `start`."""
         _lib.require_cuda(state, "state")
         _lib.require_cuda(gatebuf, "gate buffer")
         nbits = self.plan.nbits
@@ -230,9 +281,12 @@ plan_options: Dict[str, Any] = {
 
 
 def compile_circuit(nq: int, structure: Sequence[Tuple[Tuple[int, ...], Tuple[Any, ...], int]],
-                    device: torch.device, nbits_local: Optional[int] = None) -> CompiledCircuit:  # fmt: skip
-    """structure: per gate (qubits, kind, numel of its tensor). Cached by structure."""
-    key = (nq, nbits_local, tuple(structure), str(device), tuple(sorted(plan_options.items())))
+                    device: torch.device, nbits_local: Optional[int] = None,
+                    absorb_prefix: bool = False) -> CompiledCircuit:  # fmt: skip
+    """structure: per gate (qubits, kind, numel of its tensor). Cached by structure.
+    `absorb_prefix`: the circuit starts from |0...0>, fold each qubit's leading 1q gates into the
+    initial product state (CompiledCircuit.start)."""
+    key = (nq, nbits_local, tuple(structure), str(device), tuple(sorted(plan_options.items())), absorb_prefix)
     cc = _plan_cache.get(key)
     if cc is None:
         ops: List[GateOp] = []
@@ -240,8 +294,12 @@ def compile_circuit(nq: int, structure: Sequence[Tuple[Tuple[int, ...], Tuple[An
         for gi, (qubits, kind, numel) in enumerate(structure):
             ops.append(GateOp(tuple(qubits), tuple(kind), off, gi))
             off += numel
-        plan = passplan.compile_plan(ops, nq, nbits_local=nbits_local, **plan_options)
-        cc = CompiledCircuit(plan, ops, device)
+        prefix = None
+        plan_ops: List[GateOp] = ops
+        if absorb_prefix and nbits_local is None:
+            prefix, plan_ops = split_prefix(ops, nq)
+        plan = passplan.compile_plan(plan_ops, nq, nbits_local=nbits_local, **plan_options)
+        cc = CompiledCircuit(plan, ops, device, prefix=prefix, nq=nq)
         if len(_plan_cache) > 256:
             _plan_cache.clear()
         _plan_cache[key] = cc
@@ -286,7 +344,7 @@ def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) 
     tensors = [g[0].tensor for g in gates]
     device = pick_device(tensors + ([init_node.tensor] if init_node is not None else []))
     structure = [(g[1], gate_kind(g[0], g[2]), int(g[0].tensor.numel())) for g in gates]
-    cc = compile_circuit(n, structure, device)
+    cc = compile_circuit(n, structure, device, absorb_prefix=init_node is None)
     gatebuf = build_gatebuf(tensors, device)
     init = None
     if init_node is not None:

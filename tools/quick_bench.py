@@ -30,7 +30,7 @@ del psi
 nodes, d_edges = c._copy()
 nq, init, gates = svengine.extract_gate_stream(nodes, d_edges)
 structure = [(gg[1], svengine.gate_kind(gg[0], gg[2]), int(gg[0].tensor.numel())) for gg in gates]
-cc = svengine.compile_circuit(n, structure, torch.device("cuda:0"))
+cc = svengine.compile_circuit(n, structure, torch.device("cuda:0"), absorb_prefix=True)
 gatebuf = svengine.build_gatebuf([gg[0].tensor for gg in gates], torch.device("cuda:0"))
 plan = cc.plan
 print("gates", plan.n_gates, "passes", plan.n_passes, "launches", plan.n_launches)
@@ -38,10 +38,10 @@ state = svengine.new_zero_state(n, 1, torch.device("cuda:0"))
 for it in range(3):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); cc.run(state, gatebuf); e1.record(); torch.cuda.synchronize()
+    e0.record(); cc.start(state, gatebuf); cc.run(state, gatebuf); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     byt = plan.n_passes * 16 * 2**n
-    print(f"iter {it}: {ms:.2f} ms  {plan.n_gates/ms*1e3:.0f} gates/s  pass-GB/s {byt/ms/1e6:.0f}  per-pass {ms/plan.n_passes:.3f} ms")
+    print(f"iter {it}: {ms:.2f} ms  {len(gates)/ms*1e3:.0f} gates/s  pass-GB/s {byt/ms/1e6:.0f}  per-pass {ms/plan.n_passes:.3f} ms")
 # per-pass timing
 pi = 0
 for step in plan.steps:
