@@ -670,8 +670,10 @@ def run_sharded(args: argparse.Namespace) -> None:
     plan, ops, gatebuf = sv.plan, sv.ops, sv.gatebuf
     stream = torch.cuda.current_stream()
 
+    vecs = sharded.product_vectors(sv.prefix, gatebuf, n) if any(sv.prefix) else None
+
     def step_resident() -> Any:
-        sv.reset()
+        sv.reset(vecs)
         sv.run(plan, ops, gatebuf)
         return sv.z_expectations(terms)
 
@@ -699,7 +701,7 @@ def run_sharded(args: argparse.Namespace) -> None:
     norm = float(sv.norm2()[0])
 
     # ---- roofline of the dominant kernel + wire time: one instrumented step ---------------------
-    sv.reset()
+    sv.reset(vecs)
     pass_ms: List[float] = []
     swap_ms: List[float] = []
     evs = []

@@ -139,6 +139,11 @@ class CudaExecutor:
     def set_one(self, state: Any) -> None:
         state[0] = 1.0
 
+    def init_product(self, state: Any, nl: int, vecs: Any, nq: int, index_base: int) -> None:
+        from . import _lib
+
+        _lib.call("tcb_sv_init_product", state.data_ptr(), nl, vecs.data_ptr(), nq, index_base, _lib.stream_ptr())
+
     def run_gates(self, state: Any, ops: Sequence[GateOp], gatebuf: Any, nq: int, nl: int, pos_of: Sequence[int],
                   index_base: int, cache: Dict[Any, Any], key: Any) -> None:  # fmt: skip
         from . import svengine
@@ -239,12 +244,16 @@ class ShardedStatevector:
         self.bytes_sent = 0
         self.swaps_done = 0
 
-    def reset(self) -> None:
-        """Back to |0...0> in the canonical layout (the shard buffer is reused)."""
+    def reset(self, vecs: Any = None) -> None:
+        """Back to |0...0> in the canonical layout (the shard buffer is reused), or to the product state
+        prod_p vecs[p][x_p] (vecs: [n, 2] complex64 indexed by flat bit position; one write pass)."""
+        self.pos_of = [self.n - 1 - q for q in range(self.n)]
+        if vecs is not None:
+            self.ex.init_product(self.state, self.nl, vecs, self.n, self.index_base)
+            return
         self.state.zero_()
         if self.rank == 0:
             self.ex.set_one(self.state)
-        self.pos_of = [self.n - 1 - q for q in range(self.n)]
 
     # -- evolution ---------------------------------------------------------------------------
     def run(self, plan: ShardedPlan, gates: Sequence[GateOp], gatebuf: Any) -> None:
@@ -361,7 +370,23 @@ class ShardedStatevector:
 
 
 # ---------------------------------------------------------------------------------------------
-_plan_cache: Dict[Any, Tuple[ShardedPlan, List[GateOp]]] = {}
+_plan_cache: Dict[Any, Any] = {}
+
+
+def product_vectors(prefix: Sequence[Sequence[GateOp]], gatebuf: Any, n: int) -> Any:
+    """[n, 2] complex64, row = flat bit position: U_k ... U_1 |0> for every qubit's leading 1q gates."""
+    import torch
+
+    v = torch.zeros(n, 2, dtype=torch.complex64, device=gatebuf.device)
+    v[:, 0] = 1.0
+    for q, gl in enumerate(prefix):
+        for g in gl:
+            if g.kind[0] == "diagvec":
+                m = torch.diag(gatebuf[g.mat_off : g.mat_off + 2])
+            else:
+                m = gatebuf[g.mat_off : g.mat_off + 4].reshape(2, 2)
+            v[n - 1 - q] = m.to(torch.complex64) @ v[n - 1 - q]
+    return v
 
 
 def evolve(circuit: Any, comm: Any = None, executor: Any = None, chunk_elems: int = 1 << 26,
@@ -385,25 +410,31 @@ def evolve(circuit: Any, comm: Any = None, executor: Any = None, chunk_elems: in
     key = (n, comm.world, structure)
     hit = _plan_cache.get(key)
     if hit is None:
-        ops, off = [], 0
+        allops, off = [], 0
         for gi, (qubits, kind, numel) in enumerate(structure):
-            ops.append(GateOp(tuple(qubits), tuple(kind), off, gi))
+            allops.append(GateOp(tuple(qubits), tuple(kind), off, gi))
             off += numel
+        # every qubit's leading 1q gates act on |0> alone: they become the initial product state
+        prefix, ops = svengine.split_prefix(allops, n)
         plan = compile_sharded(ops, n, comm.world.bit_length() - 1)
         if len(_plan_cache) > 32:
             _plan_cache.clear()
-        _plan_cache[key] = hit = (plan, ops)
-    plan, ops = hit
+        _plan_cache[key] = hit = (plan, ops, prefix)
+    plan, ops, prefix = hit
     tensors = [g[0].tensor for g in gates]
     if isinstance(executor, CudaExecutor):
         gatebuf = svengine.build_gatebuf(tensors, executor.device)
     else:
         gatebuf = torch.cat([t.reshape(-1).to(torch.complex64) for t in tensors])
+    vecs = product_vectors(prefix, gatebuf, n) if any(prefix) else None
     if reuse is not None and reuse.n == n:
         sv = reuse
-        sv.reset()
+        sv.reset(vecs)
     else:
         sv = ShardedStatevector(n, comm, executor, chunk_elems=chunk_elems)
+        if vecs is not None:
+            sv.reset(vecs)
+    sv.prefix = prefix  # type: ignore[attr-defined]
     sv.run(plan, ops, gatebuf)
     sv.plan, sv.ops, sv.gatebuf = plan, ops, gatebuf  # type: ignore[attr-defined]
     return sv

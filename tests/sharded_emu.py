@@ -34,6 +34,14 @@ class EmuExecutor:
     def set_one(self, state):
         state[0] = 1.0
 
+    def init_product(self, state, nl, vecs, nq, index_base):
+        v = vecs.numpy()
+        x = np.arange(1 << nl, dtype=np.int64) | index_base
+        out = np.ones(1 << nl, dtype=np.complex64)
+        for p in range(nq):
+            out *= v[p][(x >> p) & 1]
+        state.numpy()[:] = out
+
     def run_gates(self, state, ops, gatebuf, nq, nl, pos_of, index_base, cache, key):
         from tensorcircuit_ng_b200 import passplan
 

@@ -146,3 +146,36 @@ def test_sharded_gloo_world2(built, tmp_path):
     full = gather_logical([p["state"].numpy() for p in parts], parts[0]["pos_of"], n, n - 1)
     assert np.abs(full - ref).max() <= 1e-5
     assert torch.allclose(parts[0]["zz"], parts[1]["zz"])
+
+
+def test_sharded_evolve_api_with_product_start(built):
+    """`sharded.evolve(circuit, ...)`: the Circuit front end + leading 1q gates folded into the initial
+    product state of every shard (rank bits read from index_base)."""
+    import tensorcircuit_ng_b200 as tc
+    from sharded_emu import EmuExecutor, ThreadWorld, gather_logical
+    from tensorcircuit_ng_b200 import sharded
+
+    n, world = 12, 4
+    ops = [("h", [q], {}) for q in range(n)] + [("rz", [0], {"theta": 0.3})] + random_layers(n, 2, 9)
+    tw = ThreadWorld(world)
+    shards = [None] * world
+    errors = []
+
+    def worker(r):
+        try:
+            c = build(tc, n, ops)
+            shards[r] = sharded.evolve(c, tw.comm(r), EmuExecutor(), chunk_elems=1 << 6)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+            raise
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert sum(len(p) for p in shards[0].prefix) >= n  # the h layer (+ rz) was absorbed
+    ref = _oracle_state(n, ops)
+    full = gather_logical([s.state.numpy() for s in shards], shards[0].pos_of, n, n - 2)
+    assert np.abs(full - ref).max() <= 1e-5
