@@ -410,7 +410,7 @@ def build_random_circuit(mod: Any, n: int, depth: int, thetas: Any, kinds: np.nd
     c = mod.Circuit(n)
     for l in range(depth):
         for q in range(n):
-            (c.rx, c.ry, c.rz)[int(kinds[l, q])](q, theta=thetas[l, q])
+            (c.rx, c.ry, c.rz)[int(kinds[l][q])](q, theta=thetas[l][q])
         perm = np.random.default_rng(l).permutation(n)
         for i in range(l % 2, n - 1, 2):
             c.cz(int(perm[i]), int(perm[i + 1]))
