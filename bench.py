@@ -511,8 +511,13 @@ def run_contraction(args: argparse.Namespace) -> None:
     my_ids = [(rank + world * i) % dc.nslices for i in range(nsl)]
     # algorithmic work per slice: 8 real flops per complex MAC; bytes: every step reads its
     # two operands and writes its result once
+    from tensorcircuit_ng_b200 import tnengine
+
     flops_slice = 8.0 * st["flops"]
-    bytes_slice = 8.0 * sum(2.0**a + 2.0**b + 2.0**c for a, b, c, _ in st["steps"])
+    plan_bytes_slice = 8.0 * sum(2.0**a + 2.0**b + 2.0**c for a, b, c, _ in st["steps"])
+    # what is launched: the schedule with skinny absorption chains fused (tnengine.build_schedule)
+    sched = tnengine.build_schedule(dc.inputs, dc.output, dc.path, sorted(dc.sliced_inds))
+    bytes_slice = sum(8.0 * (2.0 ** len(ta) + 2.0 ** len(tb) + 2.0 ** len(k)) for _, _, ta, tb, k, _ in sched)
     tensors = dc._arrays(torch.zeros(1))
     stream = torch.cuda.current_stream()
 
@@ -604,6 +609,7 @@ def run_contraction(args: argparse.Namespace) -> None:
                 "frac": gbs / peak,
                 "traffic": None,
                 "alg_bytes_per_slice": bytes_slice,
+                "plan_bytes_per_slice_unfused": plan_bytes_slice,
             },
             "cpu_baseline": None,
             "e2e": {

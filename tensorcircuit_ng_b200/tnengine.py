@@ -206,6 +206,151 @@ def slice_leaf(t: torch.Tensor, modes: Sequence[str], fixed: Dict[str, int]) -> 
     return t, out_modes
 
 
+# ---- tree schedules -----------------------------------------------------------------------------
+_FUSE_SMALL = 64  # elements: what the streaming kernel keeps in shared memory (csrc/tn_kernels.cu)
+_FUSE_BIG = 1 << 16
+_schedule_cache: Dict[Any, Any] = {}
+fuse_skinny_chains = True
+
+
+def _keep_modes(ta: Sequence[str], tb: Sequence[str], occ: Dict[str, int], out_set: set) -> List[str]:
+    """Modes of a pairwise result: kept(left) ++ kept(right); a mode survives when the output or a third
+    tensor still carries it (hyper-indices included)."""
+    sa, sb = set(ta), set(tb)
+    keep = []
+    for m in dict.fromkeys(list(ta) + list(tb)):
+        if m in out_set or occ[m] - (m in sa) - (m in sb) > 0:
+            keep.append(m)
+    return keep
+
+
+def _stream_ok(big: Sequence[str], small: Sequence[str], keep: Sequence[str]) -> bool:
+    """Would (big, small) -> keep run on the streaming kernel?  (mirror of launch_contract's rule)"""
+    sb, ss, sk = set(big), set(small), set(keep)
+    nb = sum(1 for m in keep if m in sb and m in ss)
+    nn = sum(1 for m in keep if m in ss and m not in sb)
+    nk = sum(1 for m in big if m in ss and m not in sk)
+    nm = sum(1 for m in keep if m in sb and m not in ss)
+    return nk <= 3 and nn <= 3 and nb + nk + nn <= 6 and nm + nb >= 10 and nn <= nm
+
+
+def build_schedule(inputs: Sequence[Sequence[str]], output: Sequence[str], path: Sequence[Tuple[int, ...]],
+                   sliced: Sequence[str] = (), fuse: Optional[bool] = None) -> List[Tuple[int, int, List[str], List[str], List[str], int]]:  # fmt: skip
+    """Linear path -> SSA steps (a, b, modes_a, modes_b, keep, out), cached.
+
+    With `fuse`, chains of skinny absorptions are re-associated: when a large tensor absorbs a small one
+    and the result immediately absorbs another small one, the two small tensors are contracted with each
+    other first (a few dozen elements) and the large tensor is streamed through HBM ONCE instead of twice
+    — the tensor-network form of fusing consecutive gates into one statevector pass.  Any association
+    order of a tensor network is valid; kept modes are recomputed from occurrence counts."""
+    fuse = fuse_skinny_chains if fuse is None else fuse
+    key = (tuple(tuple(t) for t in inputs), tuple(output), tuple(tuple(p) for p in path), tuple(sliced), fuse)
+    hit = _schedule_cache.get(key)
+    if hit is not None:
+        return hit
+    sl = set(sliced)
+    terms: Dict[int, List[str]] = {i: [m for m in t if m not in sl] for i, t in enumerate(inputs)}
+    n = len(inputs)
+    # linear -> SSA
+    live = list(range(n))
+    ssa: List[Tuple[int, int]] = []
+    nxt = n
+    for step in path:
+        if len(step) != 2:
+            continue
+        i, j = step
+        ssa.append((live[i], live[j]))
+        for k in sorted((i, j), reverse=True):
+            live.pop(k)
+        live.append(nxt)
+        nxt += 1
+    if len(live) != 1:
+        raise _lib.EngineError("contraction path does not reduce the network to one tensor")
+    out_set = set(output)
+
+    def forward(pairs: Sequence[Tuple[int, int, int]]):
+        """Recompute every step's kept modes for an SSA step list [(a, b, out)]."""
+        occ: Dict[str, int] = {}
+        for t in list(terms.values())[:n]:
+            for m in t:
+                occ[m] = occ.get(m, 0) + 1
+        tm = {i: terms[i] for i in range(n)}
+        steps = []
+        for si, (a, b, o) in enumerate(pairs):
+            ta, tb = tm[a], tm[b]
+            keep = list(output) if si == len(pairs) - 1 else _keep_modes(ta, tb, occ, out_set)
+            for m in ta:
+                occ[m] -= 1
+            for m in tb:
+                occ[m] -= 1
+            for m in keep:
+                occ[m] = occ.get(m, 0) + 1
+            tm[o] = keep
+            steps.append((a, b, list(ta), list(tb), keep, o))
+        return steps, tm
+
+    pairs = [(a, b, n + k) for k, (a, b) in enumerate(ssa)]
+    steps, tm = forward(pairs)
+    if fuse and len(pairs) > 2:
+        changed = True
+        rounds = 0
+        while changed and rounds < 8:
+            changed = False
+            rounds += 1
+            producer = {o: k for k, (_, _, o) in enumerate(pairs)}
+            consumer: Dict[int, int] = {}
+            for k, (a, b, _) in enumerate(pairs):
+                consumer[a] = k
+                consumer[b] = k
+            size = {i: 2 ** len(t) for i, t in tm.items()}
+            new_pairs: List[Optional[Tuple[int, int, int]]] = list(pairs)
+            extra: Dict[int, List[Tuple[int, int, int]]] = {}
+            used = set()
+            for k, (a, b, o) in enumerate(pairs):
+                if k in used or k == len(pairs) - 1:
+                    continue
+                big, small = (a, b) if size[a] >= size[b] else (b, a)
+                if size[big] < _FUSE_BIG or size[small] > _FUSE_SMALL:
+                    continue
+                k2 = consumer.get(o)
+                if k2 is None or k2 in used or k2 == len(pairs) - 1:
+                    continue
+                a2, b2, o2 = pairs[k2]
+                w = b2 if a2 == o else a2
+                if size[w] > _FUSE_SMALL or size[o] < _FUSE_BIG:
+                    continue
+                if w >= n and producer[w] > k:
+                    continue  # the second small tensor does not exist yet when the chain starts
+                # would the merged small tensor stay small, and the fused step stay on the streaming kernel?
+                occ: Dict[str, int] = {}
+                for i2, t in tm.items():
+                    pass
+                merged = [m for m in dict.fromkeys(tm[small] + tm[w])]
+                if 2 ** len(merged) > _FUSE_SMALL:
+                    continue
+                if not _stream_ok(tm[big], merged, tm[o2]):
+                    continue
+                s12 = nxt
+                nxt += 1
+                new_pairs[k] = None
+                extra.setdefault(k, []).append((small, w, s12))
+                new_pairs[k2] = (big, s12, o2)
+                used.update((k, k2))
+                changed = True
+            if changed:
+                rebuilt: List[Tuple[int, int, int]] = []
+                for k, pr in enumerate(new_pairs):
+                    rebuilt.extend(extra.get(k, []))
+                    if pr is not None:
+                        rebuilt.append(pr)
+                pairs = rebuilt
+                steps, tm = forward(pairs)
+    if len(_schedule_cache) > 64:
+        _schedule_cache.clear()
+    _schedule_cache[key] = steps
+    return steps
+
+
 def contract_tree(arrays: Sequence[torch.Tensor], inputs: Sequence[Sequence[str]], output: Sequence[str],
                   path: Sequence[Tuple[int, ...]], fixed: Optional[Dict[str, int]] = None) -> torch.Tensor:  # fmt: skip
     """Execute an opt_einsum-style linear path (pop both operands, append the result —
@@ -214,39 +359,25 @@ def contract_tree(arrays: Sequence[torch.Tensor], inputs: Sequence[Sequence[str]
     `fixed` pins sliced indices (leaves carrying them are read through offset views).
     Intermediate layouts are  kept(left) ++ kept(right)  (the convention of
     examples/omeco_ready_wave_benchmark.py:198-263); the last step writes `output` order
-    directly, so there is no final transpose pass (K2).
+    directly, so there is no final transpose pass (K2).  The step list comes from
+    `build_schedule` (cached; skinny absorption chains fused).
     """
     fixed = dict(fixed or {})
-    terms: List[List[str]] = []
-    tens: List[torch.Tensor] = []
-    for t, modes in zip(arrays, inputs):
+    tens: Dict[int, torch.Tensor] = {}
+    for i, (t, modes) in enumerate(zip(arrays, inputs)):
         if fixed:
-            t, modes = slice_leaf(t, list(modes), fixed)
-        terms.append(list(modes))
-        tens.append(t)
-    out_set = set(output)
-    steps = [p for p in path if len(p) == 2]
-    for si, (i, j) in enumerate(steps):
-        a, b = tens[i], tens[j]
-        ta, tb = terms[i], terms[j]
-        rest = set(out_set)
-        for k, t in enumerate(terms):
-            if k not in (i, j):
-                rest.update(t)
-        last = si == len(steps) - 1
-        if last:
-            keep = [m for m in output]
-        else:
-            keep = [m for m in dict.fromkeys(ta + tb) if m in rest]
-        r = contract(a, ta, b, tb, keep)
-        for k in sorted((i, j), reverse=True):
-            terms.pop(k)
-            tens.pop(k)
-        terms.append(list(keep))
-        tens.append(r)
-    if len(tens) != 1:
-        raise _lib.EngineError("contraction path does not reduce the network to one tensor")
-    final, t = terms[0], tens[0]
-    if list(final) != list(output):
-        t = t.permute([final.index(m) for m in output])
-    return t
+            t, _ = slice_leaf(t, list(modes), fixed)
+        tens[i] = t
+    if len(arrays) == 1:
+        t = tens[0]
+        final = [m for m in inputs[0] if m not in fixed]
+        if list(final) != list(output):
+            t = t.permute([final.index(m) for m in output])
+        return t
+    steps = build_schedule(inputs, output, path, sorted(fixed))
+    r = None
+    for a, b, ta, tb, keep, o in steps:
+        r = contract(tens.pop(a), ta, tens.pop(b), tb, keep)
+        tens[o] = r
+    assert r is not None
+    return r

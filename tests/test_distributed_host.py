@@ -94,3 +94,59 @@ def test_planners_on_lattice_circuit(built, shape):
     fe = planner.path_stats(inp2, out2, sd2, te["path"])["flops"]
     fg = planner.path_stats(inp2, out2, sd2, tg["path"])["flops"]
     assert fe <= 4 * fg
+
+
+def _einsum_run(steps, arrays, inputs, fixed):
+    tens = {}
+    for i, (t, modes) in enumerate(zip(arrays, inputs)):
+        idx = tuple(fixed[m] if m in fixed else slice(None) for m in modes)
+        tens[i] = t.numpy()[idx]
+    o = None
+    for a, b, ta, tb, keep, o in steps:
+        syms = {m: k for k, m in enumerate(dict.fromkeys(list(ta) + list(tb)))}
+        tens[o] = np.einsum(tens.pop(a), [syms[m] for m in ta], tens.pop(b), [syms[m] for m in tb], [syms[m] for m in keep])
+    assert len(tens) == 1
+    return tens[o]
+
+
+@pytest.mark.parametrize("shape,target", [((4, 8), 30), ((4, 8), 8), ((5, 10), 12)])
+def test_schedule_chain_fusion_is_exact(built, monkeypatch, shape, target):
+    """tnengine.build_schedule re-associates chains of skinny absorptions (A.S1).S2 -> A.(S1.S2): the value of
+    every slice must not change (numpy einsum executes both schedules), and big-tensor traffic must not grow."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import planner, tnengine
+    from tensorcircuit_ng_b200.experimental import DistributedContractor
+
+    rows, depth = shape
+    monkeypatch.setattr(tnengine, "_FUSE_BIG", 1 << 5)  # let the rule fire at test sizes
+    monkeypatch.setattr(tnengine, "_stream_ok", lambda big, small, keep: True)
+    nodes_fn = lambda _: bench.build_rcs(tc, rows, rows, depth).amplitude_before("0" * (rows * rows))  # noqa: E731
+    inp, out, sd, tensors, groups = DistributedContractor._network(nodes_fn, None, True)
+    td = planner.search_elimination(inp, out, sd, target_size=2**target, groups=groups)
+    sl = list(td["sliced_inds"])
+    s0 = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sorted(sl), fuse=False)
+    s1 = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sorted(sl), fuse=True)
+    w0 = sum(2 ** len(k) for *_, k, _ in s0 if len(k) >= 5)
+    w1 = sum(2 ** len(k) for *_, k, _ in s1 if len(k) >= 5)
+    assert w1 <= w0
+    for sid in range(min(4, 2 ** len(sl))):
+        fixed = planner.slice_values(sid, sl, sd)
+        v0, v1 = _einsum_run(s0, tensors, td["inputs"], fixed), _einsum_run(s1, tensors, td["inputs"], fixed)
+        assert abs(v0 - v1) <= 1e-7 * max(1.0, abs(v0))
+
+
+def test_schedule_fusion_halves_the_traffic_of_the_committed_plan(built):
+    import pickle
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from tensorcircuit_ng_b200 import tnengine
+
+    td = pickle.load(open(bench.rcs_plan_path(7, 7, 20, 30), "rb"))
+    sl = sorted(td["sliced_inds"])
+    s0 = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sl, fuse=False)
+    s1 = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sl, fuse=True)
+    traffic = lambda st: sum(8.0 * (2 ** len(ta) + 2 ** len(tb) + 2 ** len(k)) for _, _, ta, tb, k, _ in st)  # noqa: E731
+    assert traffic(s1) < 0.6 * traffic(s0)
