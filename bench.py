@@ -627,6 +627,85 @@ def run_contraction(args: argparse.Namespace) -> None:
         dist.destroy_process_group()
 
 
+def run_vqe(args: argparse.Namespace) -> None:
+    """BASELINE.json configs[1]: 24-qubit 1D TFIM hardware-efficient ansatz
+    (examples/benchmark_jax_vs_torch_vqe.py:160-200: H on all, depth 6 x [rzz(i,i+1), rx(i)]), energy
+    = -sum <Z_i Z_i+1> - sum <X_i> via expectation_ps, `vvag` over a batch of 64 parameter sets."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import _lib
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.set_default_device(dev)
+    n, depth, batch = args.qubits if args.qubits_set else 24, 6, args.batch
+    torch.manual_seed(0)
+    params_host = (0.1 * torch.randn(batch, depth, 2, n, device="cpu")).pin_memory()
+
+    def energy(p: Any) -> Any:
+        c = tc.Circuit(n)
+        for q in range(n):
+            c.h(q)
+        for l in range(depth):
+            for q in range(n - 1):
+                c.rzz(q, q + 1, theta=p[l, 0, q])
+            for q in range(n):
+                c.rx(q, theta=p[l, 1, q])
+        e = 0.0
+        for q in range(n - 1):
+            e = e - c.expectation_ps(z=[q, q + 1]).real
+        for q in range(n):
+            e = e - c.expectation_ps(x=[q]).real
+        return e
+
+    vvag = tc.backend.vvag(energy, argnums=0, vectorized_argnums=0)
+    n_gates = n + depth * (2 * n - 1)
+
+    def step() -> Any:
+        p = params_host.to(dev, non_blocking=True)
+        vals, grads = vvag(p)
+        return vals.cpu(), grads
+
+    for _ in range(min(1, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = _lib.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vals, grads = step()
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    line = {
+        "metric": "gates/s",
+        "value": batch * n_gates / sec,
+        "unit": "gates/s",
+        "n_gpus": 1,
+        "steps": args.steps,
+        "warmup": min(1, args.warmup),
+        "ms_per_step": sec * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "complex64",
+        "data": "synthetic",
+        "config": {"workload": f"tfim_vqe_n{n}_depth{depth}_vvag_batch{batch}", "gates_per_sample": n_gates,
+                   "value_definition": "forward gates x batch / s for one value_and_grad step (backward = adjoint "
+                                       "method, one unfused launch per gate; vmap = loop over the batch)",
+                   "energy_mean": float(vals.mean()), "grad_norm": float(grads.norm())},
+        "roofline": None,
+        "cpu_baseline": None,
+        "e2e": {"value": batch * n_gates / sec, "unit": "gates/s", "h2d_bytes_per_step": int(params_host.numel() * 4),
+                "d2h_bytes_per_step": int(batch * 4), "ms_per_step": sec * 1e3},
+        "gpu_launches": _lib.launch_count - l0,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_sharded(args: argparse.Namespace) -> None:
     import torch
     import torch.distributed as dist
@@ -838,7 +917,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--qubits", type=int, default=None)
     ap.add_argument("--depth", type=int, default=20, help="layers of the sharded random circuit (N > 1)")
-    ap.add_argument("--workload", default="qaoa", choices=["qaoa", "random", "contraction"],
+    ap.add_argument("--batch", type=int, default=64, help="vqe: parameter sets per vvag step")
+    ap.add_argument("--workload", default="qaoa", choices=["qaoa", "random", "contraction", "vqe"],
                     help="`qaoa` (default): statevector, N=1 n=30, N>1 the same family at n = 30 + log2 N (weak "
                          "scaling); `random` = BASELINE configs[3] (N > 1, use --qubits 34..36); `contraction` = "
                          "BASELINE configs[4], sliced 7x7 depth-20 amplitude")
@@ -856,6 +936,8 @@ def main() -> None:
         run_reference(args)
     elif args.workload == "contraction":
         run_contraction(args)
+    elif args.workload == "vqe":
+        run_vqe(args)
     elif int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_sharded(args)
     else:

@@ -209,7 +209,7 @@ class Circuit:
                                     ir_dict={"gatef": gates.diagonal_gate, "parameters": vars})  # fmt: skip
             return
         gatef = getattr(gates, gname + "_gate")
-        gate = gatef(**vars)
+        gate = gates.memoised_gate(gatef, vars)
         self.apply_general_gate(gate, *index, name=localname, split=split,
                                 ir_dict={"gatef": gatef, "parameters": vars})  # fmt: skip
 

@@ -264,11 +264,47 @@ def _pauli_of(op: Any) -> Optional[str]:
     return name if name in ("x", "y", "z", "i") else None
 
 
+speculate_z_moments = True
+
+
+def _z_moment(ket: torch.Tensor, n: int, zq: Sequence[int]) -> Optional[torch.Tensor]:
+    """<Z_i> / <Z_i Z_j> on a cached state.  An energy is a sum of many such terms, each a separate
+    `expectation_ps` call in the reference's API and each a full read of the state (1.4 ms at n = 30).
+    The second query on the same state computes ALL one- and two-body Z moments in ceil((n + n(n-1)/2) / 64)
+    reads (`tcb_sv_expect_z`, 64 strings per read) and parks them on the state tensor object; later
+    queries are lookups.  Worst case (exactly two queries): ~10 reads instead of 2."""
+    from . import expect
+
+    if not speculate_z_moments or n < 2 or n > 40 or not ket.is_cuda:
+        return None
+    cache = getattr(ket, "_b200_zcache", None)
+    if cache is None or cache["version"] != ket._version:
+        cache = {"version": ket._version, "count": 0, "table": None, "index": None}
+        try:
+            ket._b200_zcache = cache  # type: ignore[attr-defined]
+        except Exception:  # pylint: disable=broad-except  (wrapper tensors)
+            return None
+    cache["count"] += 1
+    if cache["table"] is None:
+        if cache["count"] < 2:
+            return None
+        terms = [[i] for i in range(n)] + [[i, j] for i in range(n) for j in range(i + 1, n)]
+        cache["index"] = {tuple(t): k for k, t in enumerate(terms)}
+        cache["table"] = expect.z_expectations(ket.reshape(-1), n, terms).to(torch.complex64)
+    return cache["table"][cache["index"][tuple(zq)]]
+
+
 def _expectation_value(ket: torch.Tensor, n: int, ops: Sequence[Tuple[Any, Tuple[int, ...]]]) -> torch.Tensor:
     from . import expect
 
     psi = ket.reshape(-1)
     paulis = [_pauli_of(op) for op, _ in ops]
+    if all(p in ("z", "i") for p in paulis) and not (ket.requires_grad and torch.is_grad_enabled()):
+        zq = sorted(ax[0] for (op, ax), p in zip(ops, paulis) if p == "z")
+        if 1 <= len(zq) <= 2:
+            val = _z_moment(ket, n, zq)
+            if val is not None:
+                return val
     if all(p is not None for p in paulis):
         xs = [ax[0] for (op, ax), p in zip(ops, paulis) if p == "x"]
         ys = [ax[0] for (op, ax), p in zip(ops, paulis) if p == "y"]

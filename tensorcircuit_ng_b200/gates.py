@@ -361,6 +361,51 @@ def diagonal_gate(diag: Any, dim: int = 2, name: str = "diagonal") -> Gate:  # g
     return _mk(d.reshape([dim] * noe), ("diagvec",), name=name)
 
 
+# ---- memoised construction -----------------------------------------------------------------
+# A layer of a variational circuit applies the SAME parametrised gate (same parameter element) to many
+# qubits: `for q in range(n): c.rx(q, theta=beta[l])`.  Building the 2x2 tensor costs ~6 tiny torch
+# kernels, which at 630 gates is a third of the end-to-end step; the tensor only depends on the
+# parameter VALUE, so it is built once per distinct parameter element and shared by the nodes.
+_gate_memo: "Dict[Any, Tuple[Any, torch.Tensor, Tuple[Any, ...]]]" = {}
+_GATE_MEMO_MAX = 1024
+
+
+def _memo_key(v: Any) -> Any:
+    if isinstance(v, (bool, int, float, complex, str)) or v is None:
+        return ("v", type(v).__name__, v)
+    if isinstance(v, np.generic):
+        return ("v", "np", v.item())
+    if type(v) is torch.Tensor and v.numel() == 1:
+        return ("t", v.data_ptr(), str(v.dtype), str(v.device), v._version, bool(v.requires_grad))
+    if isinstance(v, np.ndarray) and v.size <= 64:
+        return ("a", v.shape, v.dtype.str, v.tobytes())
+    return None
+
+
+def memoised_gate(gatef: Callable[..., Gate], kws: Dict[str, Any]) -> Gate:
+    """gatef(**kws), reusing the tensor of an earlier call with the same parameter elements."""
+    parts = []
+    for k in sorted(kws):
+        v = kws[k]
+        if isinstance(v, torch.Tensor) and v.requires_grad and torch.is_grad_enabled():
+            return gatef(**kws)  # differentiated parameters: every call owns its autograd graph
+        pk = _memo_key(v)
+        if pk is None:
+            return gatef(**kws)
+        parts.append((k, pk))
+    key = (getattr(gatef, "__name__", id(gatef)), tuple(parts), torch.is_grad_enabled())
+    hit = _gate_memo.get(key)
+    if hit is None:
+        g = gatef(**kws)
+        if len(_gate_memo) >= _GATE_MEMO_MAX:
+            _gate_memo.clear()
+        # the parameters are kept alive with the entry so that a recycled data_ptr can never alias it
+        _gate_memo[key] = (dict(kws), g.tensor, getattr(g, "_b200_kind", ("dense",)))
+        return g
+    _, tensor, kind = hit
+    return _mk(tensor, kind)
+
+
 def matrix_for_gate(g: Gate) -> np.ndarray:
     t_ = g.tensor
     d = int(round(math.sqrt(t_.numel())))

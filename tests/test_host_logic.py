@@ -95,7 +95,8 @@ def _run_emulated(n, structure, buf, **opts):
     return state, plan
 
 
-@pytest.mark.parametrize("n,depth,seed", [(4, 3, 0), (9, 3, 1), (10, 3, 2), (12, 4, 3), (14, 3, 4), (16, 2, 5)])
+@pytest.mark.parametrize("n,depth,seed", [(4, 3, 0), (9, 3, 1), (10, 3, 2), (12, 4, 3), (14, 3, 4), (16, 2, 5),
+                                          (11, 5, 6), (12, 5, 7), (13, 4, 8), (10, 6, 9), (15, 3, 10), (12, 6, 11)])
 def test_planner_and_kernel_logic_match_oracle(built, n, depth, seed):
     ops = random_layers(n, depth, seed)
     ref = oracle_state(n, ops)
