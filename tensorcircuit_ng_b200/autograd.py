@@ -54,6 +54,50 @@ def _dense_matrix(gatebuf: torch.Tensor, op: GateOp) -> torch.Tensor:
     return gatebuf[op.mat_off : op.mat_off + d * d].reshape(d, d)
 
 
+class _AdjointTables:
+    """Per-circuit index tables for the backward walk, built once and cached on the compiled circuit:
+    a dense row-major U^dagger for every gate comes from ONE gather of conj(gate buffer), and the
+    float64 per-gate reductions land in one buffer that is scattered back with ONE index_add."""
+
+    def __init__(self, cc: "svengine.CompiledCircuit", nelem: int, device: torch.device) -> None:
+        nq = cc.plan.nbits
+        dag_idx: List[int] = []
+        scat_src: List[int] = []
+        scat_dst: List[int] = []
+        self.items: List[Any] = []  # (k, bit positions, dense offset) in program order
+        for op in cc.ops:
+            d = 1 << op.k
+            if op.k > 2:
+                raise _lib.EngineError(
+                    f"gradient through a {op.k}-qubit gate is not supported yet (tcb_sv_gate_grad: k <= 2)"
+                )
+            off = len(dag_idx)
+            for r in range(d):
+                for c in range(d):
+                    if op.kind[0] == "diagvec":  # U^dagger[r, c] = conj(v[r]) on the diagonal, else the zero sentinel
+                        dag_idx.append(op.mat_off + r if r == c else nelem)
+                        if r == c:
+                            scat_src.append(off + r * d + c)
+                            scat_dst.append(op.mat_off + r)
+                    else:  # U^dagger[r, c] = conj(U[c, r])
+                        dag_idx.append(op.mat_off + c * d + r)
+                        scat_src.append(off + r * d + c)
+                        scat_dst.append(op.mat_off + r * d + c)
+            self.items.append((op.k, _lib.int_array([nq - 1 - q for q in op.qubits]), off))
+        self.total = len(dag_idx)
+        self.dag_idx = torch.tensor(dag_idx, dtype=torch.long, device=device)
+        self.scat_src = torch.tensor(scat_src, dtype=torch.long, device=device)
+        self.scat_dst = torch.tensor(scat_dst, dtype=torch.long, device=device)
+
+
+def _adjoint_tables(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor) -> _AdjointTables:
+    t = getattr(cc, "_adjoint_tables", None)
+    if t is None or t.dag_idx.device != gatebuf.device:
+        t = _AdjointTables(cc, gatebuf.numel(), gatebuf.device)
+        cc._adjoint_tables = t
+    return t
+
+
 class _Evolve(torch.autograd.Function):
     @staticmethod
     def forward(ctx: Any, gatebuf: torch.Tensor, init: Optional[torch.Tensor], cc: Any) -> torch.Tensor:
@@ -68,36 +112,23 @@ class _Evolve(torch.autograd.Function):
         gatebuf, psi_out = ctx.saved_tensors
         cc = ctx.cc
         nbits = cc.plan.nbits
-        nq = nbits
+        if not assume_unitary:
+            raise _lib.EngineError("autograd.assume_unitary=False (recompute mode) is not implemented in this round")
+        tabs = _adjoint_tables(cc, gatebuf)
         lam = grad_out.to(torch.complex64).resolve_conj().reshape(-1).clone()
         psi = psi_out.clone()
+        src = torch.cat([gatebuf.conj().resolve_conj(), torch.zeros(1, dtype=gatebuf.dtype, device=gatebuf.device)])
+        dag = src[tabs.dag_idx].contiguous()  # every U^dagger, dense row-major, in program order
+        g_all = torch.zeros(max(tabs.total, 1), 2, dtype=torch.float64, device=gatebuf.device)
+        lp, pp, dp, gp = lam.data_ptr(), psi.data_ptr(), dag.data_ptr(), g_all.data_ptr()
+        stream = _lib.stream_ptr()
+        for k, bp, off in reversed(tabs.items):
+            u = dp + off * 8
+            _lib.call("tcb_sv_apply_dense", pp, nbits, 1, bp, k, u, 0, stream)  # psi_in = U^dagger psi_out
+            _lib.call("tcb_sv_gate_grad", lp, pp, nbits, 1, bp, k, gp + off * 16, 0, stream)
+            _lib.call("tcb_sv_apply_dense", lp, nbits, 1, bp, k, u, 0, stream)  # lam_in = U^dagger lam_out
         grad_buf = torch.zeros_like(gatebuf)
-        stream_ops: List[GateOp] = cc.ops
-        for op in reversed(stream_ops):
-            d = 1 << op.k
-            u = _dense_matrix(gatebuf, op)
-            udag = u.conj().transpose(0, 1).contiguous()
-            if not assume_unitary:
-                raise _lib.EngineError(
-                    "autograd.assume_unitary=False (recompute mode) is not implemented in this round"
-                )
-            # psi_in = U^dagger psi_out
-            _apply_single(psi, nbits, nq, op, udag)
-            if op.k > 2:
-                raise _lib.EngineError(
-                    f"gradient through a {op.k}-qubit gate is not supported yet (tcb_sv_gate_grad: k <= 2)"
-                )
-            g = torch.zeros(d * d * 2, dtype=torch.float64, device=gatebuf.device)
-            bp = _lib.int_array([nq - 1 - q for q in op.qubits])
-            _lib.call("tcb_sv_gate_grad", lam.data_ptr(), psi.data_ptr(), nbits, 1, bp, op.k, g.data_ptr(), 0,
-                      _lib.stream_ptr())  # fmt: skip
-            gc = torch.view_as_complex(g.reshape(d * d, 2)).to(torch.complex64)
-            if op.kind[0] == "diagvec":
-                grad_buf[op.mat_off : op.mat_off + d] = gc.reshape(d, d).diagonal()
-            else:
-                grad_buf[op.mat_off : op.mat_off + d * d] = gc
-            # lam_in = U^dagger lam_out
-            _apply_single(lam, nbits, nq, op, udag)
+        torch.view_as_real(grad_buf).index_add_(0, tabs.scat_dst, g_all[tabs.scat_src].to(torch.float32))
         grad_init = lam if ctx.has_init and ctx.needs_input_grad[1] else None
         return grad_buf, grad_init, None
 
