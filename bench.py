@@ -630,7 +630,8 @@ def run_contraction(args: argparse.Namespace) -> None:
 def run_vqe(args: argparse.Namespace) -> None:
     """BASELINE.json configs[1]: 24-qubit 1D TFIM hardware-efficient ansatz
     (examples/benchmark_jax_vs_torch_vqe.py:160-200: H on all, depth 6 x [rzz(i,i+1), rx(i)]), energy
-    = -sum <Z_i Z_i+1> - sum <X_i> via expectation_ps, `vvag` over a batch of 64 parameter sets."""
+    = -sum <Z_i Z_i+1> - sum <X_i> via `operator_expectation` on the `PauliStringSum2COO` Hamiltonian
+    (:168-197), `vvag` over a batch of 64 parameter sets."""
     import torch
 
     import tensorcircuit_ng_b200 as tc
@@ -643,6 +644,19 @@ def run_vqe(args: argparse.Namespace) -> None:
     torch.manual_seed(0)
     params_host = (0.1 * torch.randn(batch, depth, 2, n, device="cpu")).pin_memory()
 
+    structures, weights = [], []
+    for q in range(n - 1):  # examples/benchmark_jax_vs_torch_vqe.py:168-186 (tfim_sparse_hamiltonian)
+        term = [0] * n
+        term[q] = term[q + 1] = 3
+        structures.append(term)
+        weights.append(-1.0)
+    for q in range(n):
+        term = [0] * n
+        term[q] = 1
+        structures.append(term)
+        weights.append(-1.0)
+    hamiltonian = tc.quantum.PauliStringSum2COO(structures, weights)
+
     def energy(p: Any) -> Any:
         c = tc.Circuit(n)
         for q in range(n):
@@ -652,12 +666,7 @@ def run_vqe(args: argparse.Namespace) -> None:
                 c.rzz(q, q + 1, theta=p[l, 0, q])
             for q in range(n):
                 c.rx(q, theta=p[l, 1, q])
-        e = 0.0
-        for q in range(n - 1):
-            e = e - c.expectation_ps(z=[q, q + 1]).real
-        for q in range(n):
-            e = e - c.expectation_ps(x=[q]).real
-        return e
+        return tc.templates.measurements.operator_expectation(c, hamiltonian)
 
     vvag = tc.backend.vvag(energy, argnums=0, vectorized_argnums=0)
     n_gates = n + depth * (2 * n - 1)

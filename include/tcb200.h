@@ -91,6 +91,18 @@ int tcb_sv_expect_z(const void* state, int nbits, int64_t batch, const uint64_t*
  * sum_x conj(psi[x ^ xmask]) * phase(x) * psi[x]   (xmask must be local: < 2^nbits)      */
 int tcb_sv_expect_pauli(const void* state, int nbits, int64_t batch, uint64_t xmask,
                         uint64_t zmask, int ny, uint64_t index_base, double* out, void* stream);
+/* Matrix-free Pauli-sum operator H = sum_t c_t P_t, P_t = X^{xmask_t} Z^{zmask_t} (a Y is a bit in both,
+ * its i folded into c_t = w_t i^{ny_t}); replaces the COO matvec behind
+ * tensorcircuit/templates/measurements.py:156-191 (operator_expectation / sparse_expectation) and the
+ * term loop of tensorcircuit/quantum.py:2222-2358 (PauliStringSum2MVP):
+ *   out_state[b][i] (=, or += when accumulate) sum_t c_t (-1)^popc(((i|index_base) ^ x_t) & z_t) psi_b[i ^ x_t]
+ *   out_value[b]    (2 x float64: re, im) += <psi_b| H |psi_b>
+ * Either output may be null.  xmask / zmask (uint64) and coef (complex64) are DEVICE arrays of nterms
+ * entries, best sorted by xmask (each run of equal xmask costs one read of the state); xmask must be
+ * local (< 2^nbits).  out_state must not alias state.                                          */
+int tcb_sv_pauli_sum(const void* state, int nbits, int64_t batch, const uint64_t* xmask,
+                     const uint64_t* zmask, const void* coef, int nterms, uint64_t index_base,
+                     void* out_state, int accumulate, double* out_value, void* stream);
 /* out[b] (2 x float64) += <a_b | b_b>  */
 int tcb_sv_inner(const void* a, const void* b, int nbits, int64_t batch, double* out, void* stream);
 

@@ -86,6 +86,11 @@ SYMBOLS = {
         c_int,
         [c_void_p, c_int, c_int64, c_uint64, c_uint64, c_int, c_uint64, c_void_p, c_void_p],
     ),
+    "tcb_sv_pauli_sum": (
+        c_int,
+        [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_uint64, c_void_p, c_int, c_void_p,
+         c_void_p],
+    ),  # fmt: skip
     "tcb_sv_inner": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "tcb_sv_gate_grad": (
         c_int,

@@ -40,6 +40,8 @@ int launch_expect_z(const void*, int, int64_t, const uint64_t*, int, uint64_t, d
 int launch_expect_pauli(const void*, int, int64_t, uint64_t, uint64_t, int, uint64_t, double*,
                         cudaStream_t);
 int launch_inner(const void*, const void*, int, int64_t, double*, cudaStream_t);
+int launch_pauli_sum(const void*, int, int64_t, const uint64_t*, const uint64_t*, const void*, int, uint64_t,
+                     void*, int, double*, cudaStream_t);
 int launch_gate_grad(const void*, const void*, int, int64_t, const int*, int, void*, int64_t,
                      cudaStream_t);
 int launch_pack_half(const void*, void*, int, int, int, int, cudaStream_t);
@@ -135,6 +137,19 @@ int tcb_sv_expect_pauli(const void* state, int nbits, int64_t batch, uint64_t xm
   NOTNULL(state, "tcb_sv_expect_pauli");
   NOTNULL(out, "tcb_sv_expect_pauli");
   return launch_expect_pauli(state, nbits, batch, xmask, zmask, ny, index_base, out, S(stream));
+}
+
+int tcb_sv_pauli_sum(const void* state, int nbits, int64_t batch, const uint64_t* xmask,
+                     const uint64_t* zmask, const void* coef, int nterms, uint64_t index_base,
+                     void* out_state, int accumulate, double* out_value, void* stream) {
+  NOTNULL(state, "tcb_sv_pauli_sum");
+  if (nterms > 0) {
+    NOTNULL(xmask, "tcb_sv_pauli_sum");
+    NOTNULL(zmask, "tcb_sv_pauli_sum");
+    NOTNULL(coef, "tcb_sv_pauli_sum");
+  }
+  return launch_pauli_sum(state, nbits, batch, xmask, zmask, coef, nterms, index_base, out_state,
+                          accumulate, out_value, S(stream));
 }
 
 int tcb_sv_inner(const void* a, const void* b, int nbits, int64_t batch, double* out, void* stream) {

@@ -492,6 +492,112 @@ int launch_inner(const void* a, const void* b, int nbits, int64_t batch, double*
 }
 
 // ---------------------------------------------------------------------------------
+// Matrix-free Pauli-sum operator  H = sum_t c_t P_t  (what the reference does with a
+// COO matrix in templates/measurements.py:156-191 or term by term in quantum.py:2222-2358):
+//   (H psi)[i] = sum_t c_t (-1)^popc((i ^ x_t) & z_t) psi[i ^ x_t],   c_t = w_t i^{ny_t}
+// Terms arrive sorted by flip mask; every run of equal x_t is one load of psi[i ^ x] and its
+// coefficients fold into one complex factor per amplitude before the multiply.  One launch writes
+// H psi and / or accumulates <psi|H|psi>; each thread owns two neighbouring amplitudes (16-byte
+// accesses; flips of bit 0 swap the halves in registers).
+constexpr int PS_MAX_TERMS = 1024;
+
+template <bool kWrite, bool kAccum, bool kValue>
+__global__ void __launch_bounds__(256)
+pauli_sum_kernel(const float4* __restrict__ state, uint64_t nvec_per_state,
+                 const unsigned long long* __restrict__ xs, const unsigned long long* __restrict__ zs,
+                 const float2* __restrict__ cs, int nterms, unsigned long long index_base,
+                 float4* __restrict__ out_state, double* out_value) {
+  __shared__ unsigned long long sx[PS_MAX_TERMS], sz[PS_MAX_TERMS];
+  __shared__ float2 sc[PS_MAX_TERMS];
+  for (int t = threadIdx.x; t < nterms; t += blockDim.x) {
+    sx[t] = xs[t];
+    sz[t] = zs[t];
+    sc[t] = cs[t];
+  }
+  __syncthreads();
+  const unsigned b = blockIdx.y;
+  const float4* st = state + (size_t)b * nvec_per_state;
+  float4* os = kWrite ? out_state + (size_t)b * nvec_per_state : nullptr;
+  double dre = 0.0, dim_ = 0.0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nvec_per_state; p += stride) {
+    const unsigned long long i0 = (p << 1) | index_base;
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+    int t = 0;
+    while (t < nterms) {
+      const unsigned long long x = sx[t];
+      float4 v = st[p ^ (x >> 1)];
+      if (x & 1ull) v = make_float4(v.z, v.w, v.x, v.y);
+      float2 d0 = make_float2(0.f, 0.f), d1 = d0;
+      do {
+        const unsigned long long z = sz[t];
+        const float2 c = sc[t];
+        const bool odd0 = __popcll((i0 ^ x) & z) & 1;
+        const bool odd1 = odd0 != bool(z & 1ull);
+        d0.x += odd0 ? -c.x : c.x;
+        d0.y += odd0 ? -c.y : c.y;
+        d1.x += odd1 ? -c.x : c.x;
+        d1.y += odd1 ? -c.y : c.y;
+        ++t;
+      } while (t < nterms && sx[t] == x);
+      a0.x += d0.x * v.x - d0.y * v.y;
+      a0.y += d0.x * v.y + d0.y * v.x;
+      a1.x += d1.x * v.z - d1.y * v.w;
+      a1.y += d1.x * v.w + d1.y * v.z;
+    }
+    if (kValue) {
+      const float4 u = st[p];  // conj(psi) . (H psi)
+      dre += (double)(u.x * a0.x + u.y * a0.y + u.z * a1.x + u.w * a1.y);
+      dim_ += (double)(u.x * a0.y - u.y * a0.x + u.z * a1.y - u.w * a1.x);
+    }
+    if (kWrite) {
+      float4 r = make_float4(a0.x, a0.y, a1.x, a1.y);
+      if (kAccum) {
+        const float4 o = os[p];
+        r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+      }
+      os[p] = r;
+    }
+  }
+  if (kValue) block_reduce_add2(dre, dim_, out_value + 2 * (size_t)b);
+}
+
+int launch_pauli_sum(const void* state, int nbits, int64_t batch, const uint64_t* xmask,
+                     const uint64_t* zmask, const void* coef, int nterms, uint64_t index_base,
+                     void* out_state, int accumulate, double* out_value, cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_pauli_sum: nbits=%d", nbits);
+  TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_pauli_sum: batch=%lld", (long long)batch);
+  TCB_REQUIRE(nterms >= 0, "tcb_sv_pauli_sum: nterms=%d", nterms);
+  TCB_REQUIRE(out_state != nullptr || out_value != nullptr, "tcb_sv_pauli_sum: nothing to compute");
+  TCB_REQUIRE(out_state != state, "tcb_sv_pauli_sum: out_state must not alias state");
+  const uint64_t nvec = 1ull << (nbits - 1);
+  dim3 grid(grid_for(nvec, 256), (unsigned)batch);
+  const float4* st = reinterpret_cast<const float4*>(state);
+  float4* os = reinterpret_cast<float4*>(out_state);
+  const unsigned long long* xs = reinterpret_cast<const unsigned long long*>(xmask);
+  const unsigned long long* zs = reinterpret_cast<const unsigned long long*>(zmask);
+  const float2* cs = reinterpret_cast<const float2*>(coef);
+  bool acc = accumulate != 0;
+  int first = 0;
+  do {  // more terms than one shared-memory table: further launches accumulate
+    const int cnt = nterms - first < PS_MAX_TERMS ? nterms - first : PS_MAX_TERMS;
+    if (os && out_value) {
+      if (acc) pauli_sum_kernel<true, true, true><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
+      else pauli_sum_kernel<true, false, true><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
+    } else if (os) {
+      if (acc) pauli_sum_kernel<true, true, false><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
+      else pauli_sum_kernel<true, false, false><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
+    } else {
+      pauli_sum_kernel<false, false, true><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
+    }
+    TCB_CHECK_CUDA(cudaGetLastError());
+    first += cnt;
+    acc = true;
+  } while (first < nterms);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 // adjoint-mode gate gradient: G[r][c] = sum_rest lam[rest,r] * conj(psi[rest,c])
 template <int K>
 __global__ void __launch_bounds__(256)

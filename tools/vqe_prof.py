@@ -14,6 +14,20 @@ dev = torch.device("cuda", 0)
 torch.set_default_device(dev)
 
 
+ls, ws = [], []
+for q in range(n - 1):
+    t = [0] * n
+    t[q] = t[q + 1] = 3
+    ls.append(t)
+    ws.append(-1.0)
+for q in range(n):
+    t = [0] * n
+    t[q] = 1
+    ls.append(t)
+    ws.append(-1.0)
+ham = tc.quantum.PauliStringSum2COO(ls, ws)
+
+
 def energy(p):
     c = tc.Circuit(n)
     for q in range(n):
@@ -23,12 +37,7 @@ def energy(p):
             c.rzz(q, q + 1, theta=p[l, 0, q])
         for q in range(n):
             c.rx(q, theta=p[l, 1, q])
-    e = 0.0
-    for q in range(n - 1):
-        e = e - c.expectation_ps(z=[q, q + 1]).real
-    for q in range(n):
-        e = e - c.expectation_ps(x=[q]).real
-    return e
+    return tc.templates.measurements.operator_expectation(c, ham)
 
 
 vag = tc.backend.value_and_grad(energy)
