@@ -39,6 +39,105 @@ class Gate(tn.Node):  # gates.py:185-224
         return r  # type: ignore[return-value]
 
 
+# ---- deferred parametrised gates ---------------------------------------------------
+# A differentiated circuit builds hundreds of tiny parametrised matrices per step; one by one that is
+# ~10 torch ops (and ~10 autograd nodes) per gate and dominates a 24-qubit VQE step on the host.  The
+# rotation families below are all  M(theta) = cos(s theta) C0 + sin(s theta) C1 : their nodes carry only
+# (family, theta) and the statevector route builds every member of a family in one batched expression
+# (`svengine.assemble_gatebuf`).  Any other access to `.tensor` materialises that one gate on the spot
+# with the same formula, so the node behaves like the eager one everywhere else.
+lazy_parametrised = True
+
+
+class TrigFamily:
+    _registry: Dict[Any, "TrigFamily"] = {}
+
+    def __init__(self, c0: np.ndarray, c1: np.ndarray, scale: float, kind: Tuple[Any, ...]) -> None:
+        self.k = np.stack([np.asarray(c0).reshape(-1), np.asarray(c1).reshape(-1)]).astype(np.complex64)
+        self.scale, self.kind = float(scale), kind
+        self.numel = int(self.k.shape[1])
+        nleg = int(round(math.log2(self.numel)))
+        self.shape = (2,) * nleg
+
+    @classmethod
+    def get(cls, key: Any, make: Callable[[], "TrigFamily"]) -> "TrigFamily":
+        f = cls._registry.get(key)
+        if f is None:
+            f = cls._registry[key] = make()
+        return f
+
+    def batched(self, thetas: torch.Tensor) -> torch.Tensor:
+        """[m] real parameters -> [m, numel] complex64 row-major matrices."""
+        a = thetas.to(rdtype) * self.scale
+        cs = torch.stack([torch.cos(a), torch.sin(a)], dim=1).to(dtype)
+        return cs @ _const(self.k, thetas.device if thetas.is_cuda else None)
+
+
+class _LazySpec:
+    __slots__ = ("family", "theta", "value")
+
+    def __init__(self, family: TrigFamily, theta: torch.Tensor) -> None:
+        self.family, self.theta, self.value = family, theta, None
+
+
+class LazyGate(Gate):
+    """A `Gate` whose tensor is (family, theta) until somebody asks for it."""
+
+    def __init__(self, spec: _LazySpec, name: Optional[str] = None) -> None:  # pylint: disable=super-init-not-called
+        self._lazy = spec
+        self._own: Optional[torch.Tensor] = None
+        self.name = name if name is not None else "__unnamed_node__"
+        self.edges = [tn.Edge(self, i) for i in range(len(spec.family.shape))]
+        self.backend = None
+        self._stable_id_ = tn._next_id()
+        self._b200_kind = spec.family.kind
+
+    def pending(self) -> bool:
+        return self._own is None and self._lazy.value is None
+
+    @property
+    def tensor(self) -> torch.Tensor:  # type: ignore[override]
+        if self._own is not None:
+            return self._own
+        sp = self._lazy
+        if sp.value is None:
+            sp.value = sp.family.batched(sp.theta.reshape(1))[0].reshape(sp.family.shape)
+        return sp.value
+
+    @tensor.setter
+    def tensor(self, t: torch.Tensor) -> None:
+        self._own = t
+
+    @property
+    def shape(self) -> Tuple[int, ...]:  # type: ignore[override]
+        return tuple(self._own.shape) if self._own is not None else self._lazy.family.shape
+
+    def get_rank(self) -> int:
+        return len(self.shape)
+
+    def copy(self, conjugate: bool = False) -> "Gate":
+        if conjugate or self._own is not None:
+            t = self.tensor
+            g = Gate(t.conj() if conjugate else t, name=self.name)
+            g._b200_kind = self._b200_kind  # type: ignore[attr-defined]
+            return g
+        return LazyGate(self._lazy, name=self.name)  # shares the spec: materialised at most once
+
+
+def _lazy_ok(theta: Any) -> bool:
+    return (
+        lazy_parametrised
+        and type(theta) is torch.Tensor
+        and theta.numel() == 1
+        and theta.dtype in (torch.float32, torch.float64)
+    )
+
+
+def _trig(name: str, c0: np.ndarray, c1: np.ndarray, scale: float, kind: Tuple[Any, ...], theta: torch.Tensor) -> Gate:
+    fam = TrigFamily.get(name, lambda: TrigFamily(c0, c1, scale, kind))
+    return LazyGate(_LazySpec(fam, theta))
+
+
 # ---- constant matrices (gates.py:33-174) ----------------------------------------
 _i00 = np.array([[1.0, 0.0], [0.0, 0.0]])
 _i01 = np.array([[0.0, 1.0], [0.0, 0.0]])
@@ -202,18 +301,24 @@ def r_gate(theta: float = 0.0, alpha: float = 0.0, phi: float = 0.0) -> Gate:  #
 
 
 def rx_gate(theta: float = 0.0) -> Gate:  # gates.py:692-707
+    if _lazy_ok(theta):
+        return _trig("rx", _i_matrix, -1.0j * _x_matrix, 0.5, ("dense",), theta)
     th = _scalar(theta)
     unitary = torch.cos(th / 2.0) * _const(_i_matrix, _dev(th)) - 1.0j * torch.sin(th / 2.0) * _const(_x_matrix, _dev(th))
     return _mk(unitary, ("dense",))
 
 
 def ry_gate(theta: float = 0.0) -> Gate:  # gates.py:710-725
+    if _lazy_ok(theta):
+        return _trig("ry", _i_matrix, -1.0j * _y_matrix, 0.5, ("dense",), theta)
     th = _scalar(theta)
     unitary = torch.cos(th / 2.0) * _const(_i_matrix, _dev(th)) - 1.0j * torch.sin(th / 2.0) * _const(_y_matrix, _dev(th))
     return _mk(unitary, ("dense",))
 
 
 def rz_gate(theta: float = 0.0) -> Gate:  # gates.py:728-743
+    if _lazy_ok(theta):
+        return _trig("rz", _i_matrix, -1.0j * _z_matrix, 0.5, ("diag",), theta)
     th = _scalar(theta)
     unitary = torch.cos(th / 2.0) * _const(_i_matrix, _dev(th)) - 1.0j * torch.sin(th / 2.0) * _const(_z_matrix, _dev(th))
     return _mk(unitary, ("diag",))
@@ -283,6 +388,12 @@ def exponential_gate(unitary: Any, theta: float, name: str = "none") -> Gate:  #
 def exponential_gate_unity(unitary: Any, theta: float, half: bool = False, name: str = "none") -> Gate:
     """cos(theta) I - i sin(theta) U for U^2 = I (gates.py:920-953)."""
     kind = _probe_kind(unitary)
+    if _lazy_ok(theta) and isinstance(unitary, np.ndarray) and unitary.size <= 256:
+        n = int(round(math.log2(unitary.size)))
+        key = ("exp1", unitary.shape, unitary.dtype.str, unitary.tobytes(), bool(half))
+        fam = TrigFamily.get(key, lambda: TrigFamily(_eye_for(n), -1.0j * unitary, 0.5 if half is True else 1.0, kind))
+        g = LazyGate(_LazySpec(fam, theta), name="exp1-" + name)
+        return g
     th = _scalar(theta)
     u = _const(unitary, _dev(th)) if isinstance(unitary, np.ndarray) else num_to_tensor(unitary)
     n = int(round(math.log2(u.numel())))
@@ -385,6 +496,9 @@ def _memo_key(v: Any) -> Any:
 def memoised_gate(gatef: Callable[..., Gate], kws: Dict[str, Any]) -> Gate:
     """gatef(**kws), reusing the tensor of an earlier call with the same parameter elements."""
     parts = []
+    if (getattr(gatef, "_lazy_family", False) and _lazy_ok(kws.get("theta"))
+            and isinstance(kws.get("unitary", _i_matrix), np.ndarray)):  # fmt: skip
+        return gatef(**kws)  # deferred: built with its whole family in one batched expression
     for k in sorted(kws):
         v = kws[k]
         if isinstance(v, torch.Tensor) and v.requires_grad and torch.is_grad_enabled():
@@ -418,6 +532,8 @@ r, u, rx, ry, rz, phase, iswap, any, exp, exp1, cr = (  # noqa: A001
     cr_gate,
 )  # fmt: skip
 rzz, rxx, ryy = rzz_gate, rxx_gate, ryy_gate
+for _f in (rx_gate, ry_gate, rz_gate, exponential_gate_unity, rzz_gate, rxx_gate, ryy_gate):
+    _f._lazy_family = True  # type: ignore[attr-defined]
 cu, crx, cry, crz, cphase, orx, ory, orz = (
     cu_gate, crx_gate, cry_gate, crz_gate, cphase_gate, orx_gate, ory_gate, orz_gate,
 )  # fmt: skip

@@ -11,6 +11,7 @@ i.e. `wavefunction()` / the cached state of `expectation*()`.
 
 from __future__ import annotations
 
+import math
 import ctypes
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -336,16 +337,57 @@ def build_gatebuf(tensors: Sequence[torch.Tensor], device: torch.device) -> torc
     return torch.cat(flat) if flat else torch.zeros(1, dtype=torch.complex64, device=device)
 
 
+_perm_cache: Dict[Any, torch.Tensor] = {}
+
+
+def assemble_gatebuf(gate_nodes: Sequence[Any], device: torch.device) -> torch.Tensor:
+    """The gate buffer (every gate matrix, flat, in program order).  Deferred parametrised gates
+    (`gates.LazyGate`) are built per family in one batched expression — a handful of torch ops and
+    autograd nodes for the whole circuit instead of ~10 per gate — and one cached gather puts the
+    pieces in program order."""
+    pend = [hasattr(g, "pending") and g.pending() for g in gate_nodes]
+    if not any(pend):
+        return build_gatebuf([g.tensor for g in gate_nodes], device)
+    fams: Dict[int, Tuple[Any, List[int]]] = {}
+    eager: List[int] = []
+    for i, g in enumerate(gate_nodes):
+        if pend[i]:
+            fams.setdefault(id(g._lazy.family), (g._lazy.family, []))[1].append(i)
+        else:
+            eager.append(i)
+    pieces = [build_gatebuf([gate_nodes[i].tensor for i in eager], device)] if eager else []
+    order: List[Tuple[int, int]] = [(i, int(gate_nodes[i].tensor.numel())) for i in eager]  # (gate, numel) in cat order
+    for fam, idx in fams.values():
+        thetas = torch.stack([gate_nodes[i]._lazy.theta.reshape(()).to(device=device, dtype=torch.float32) for i in idx])
+        pieces.append(fam.batched(thetas).reshape(-1))
+        order.extend((i, fam.numel) for i in idx)
+    cat = torch.cat(pieces) if len(pieces) > 1 else pieces[0]
+    key = (tuple(order), str(device))
+    perm = _perm_cache.get(key)
+    if perm is None:
+        start = {}
+        off = 0
+        for i, numel in order:
+            start[i] = (off, numel)
+            off += numel
+        host = np.concatenate([np.arange(start[i][0], start[i][0] + start[i][1]) for i in range(len(gate_nodes))])
+        perm = torch.from_numpy(host.astype(np.int64)).to(device)
+        if len(_perm_cache) > 64:
+            _perm_cache.clear()
+        _perm_cache[key] = perm
+    return cat.index_select(0, perm)
+
+
 def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) -> torch.Tensor:
     """Forward statevector for a circuit-shaped network; returns a [2]*n tensor."""
     from . import autograd  # local import (autograd imports this module)
 
     n, init_node, gates = extract_gate_stream(nodes, output_edge_order)
-    tensors = [g[0].tensor for g in gates]
-    device = pick_device(tensors + ([init_node.tensor] if init_node is not None else []))
-    structure = [(g[1], gate_kind(g[0], g[2]), int(g[0].tensor.numel())) for g in gates]
+    probe = [g[0]._lazy.theta if hasattr(g[0], "pending") and g[0].pending() else g[0].tensor for g in gates]
+    device = pick_device(probe + ([init_node.tensor] if init_node is not None else []))
+    structure = [(g[1], gate_kind(g[0], g[2]), int(math.prod(g[0].shape))) for g in gates]
     cc = compile_circuit(n, structure, device, absorb_prefix=init_node is None)
-    gatebuf = build_gatebuf(tensors, device)
+    gatebuf = assemble_gatebuf([g[0] for g in gates], device)
     init = None
     if init_node is not None:
         init = init_node.tensor.to(torch.complex64).to(device).reshape(-1)
