@@ -702,8 +702,9 @@ def run_vqe(args: argparse.Namespace) -> None:
         "dtype": "complex64",
         "data": "synthetic",
         "config": {"workload": f"tfim_vqe_n{n}_depth{depth}_vvag_batch{batch}", "gates_per_sample": n_gates,
-                   "value_definition": "forward gates x batch / s for one value_and_grad step (backward = adjoint "
-                                       "method, one unfused launch per gate; vmap = loop over the batch)",
+                   "value_definition": "forward gates x batch / s for one value_and_grad step (energy = one "
+                                       "Pauli-sum launch; backward = adjoint method, one fused launch per gate over "
+                                       "psi and lambda; vmap = loop over the batch)",
                    "energy_mean": float(vals.mean()), "grad_norm": float(grads.norm())},
         "roofline": None,
         "cpu_baseline": None,

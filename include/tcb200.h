@@ -114,6 +114,14 @@ int tcb_sv_inner(const void* a, const void* b, int nbits, int64_t batch, double*
 int tcb_sv_gate_grad(const void* lam, const void* psi_in, int nbits, int64_t batch,
                      const int* bitpos_host, int k, double* grad, int64_t grad_batch_stride,
                      void* stream);
+/* One gate of the adjoint walk fused into a single pass over both states (what autograd's backward does
+ * with two tensordots and saved intermediates per gate, tensorcircuit/backends/pytorch_backend.py:775-786):
+ *   psi <- U^dagger psi (= psi_in);  grad[b][r][c] += sum_rest lam[rest,r] conj(psi_in[rest,c]);
+ *   lam <- U^dagger lam.     udag: DEVICE, row-major 2^k x 2^k complex64 (k = 1, 2), batch stride in
+ * complex elements (0 = shared); grad as in tcb_sv_gate_grad.                                        */
+int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const int* bitpos_host, int k,
+                        const void* udag, int64_t udag_batch_stride, double* grad,
+                        int64_t grad_batch_stride, void* stream);
 
 /* ---- sharded statevector: local half of a global<->local qubit swap -------
  * Packs the amplitudes whose local bit `local_bit` == `want` into a contiguous

@@ -96,6 +96,10 @@ SYMBOLS = {
         c_int,
         [c_void_p, c_void_p, c_int, c_int64, POINTER(c_int), c_int, c_void_p, c_int64, c_void_p],
     ),
+    "tcb_sv_adjoint_step": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int64, POINTER(c_int), c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
+    ),
     "tcb_sv_pack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tcb_sv_unpack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tcb_sv_pack_bits": (

@@ -6,8 +6,8 @@ pass programs and whose backward is the *adjoint method*: instead of saving ever
 intermediate 2^n state (what autograd over `torch.tensordot` does in the reference,
 tensorcircuit/backends/pytorch_backend.py:775-786), it keeps only the final state and
 walks the gates in reverse, un-computing |psi> with U^dagger while propagating the
-cotangent |lam>, and reducing  dL/dU = sum lam (x) conj(psi_in)  per gate with
-`tcb_sv_gate_grad`.  Memory: 2 states + 1 scratch, independent of depth.
+cotangent |lam>, and reducing  dL/dU = sum lam (x) conj(psi_in)  per gate — all three in one
+pass over the two states per gate (`tcb_sv_adjoint_step`).  Memory: 2 states + 1 scratch, independent of depth.
 
 Valid for unitary gates (every factory in gates.py except user matrices passed to
 `any` / `diagonal`); `assume_unitary = False` switches to recomputing psi_in from the
@@ -123,10 +123,8 @@ class _Evolve(torch.autograd.Function):
         lp, pp, dp, gp = lam.data_ptr(), psi.data_ptr(), dag.data_ptr(), g_all.data_ptr()
         stream = _lib.stream_ptr()
         for k, bp, off in reversed(tabs.items):
-            u = dp + off * 8
-            _lib.call("tcb_sv_apply_dense", pp, nbits, 1, bp, k, u, 0, stream)  # psi_in = U^dagger psi_out
-            _lib.call("tcb_sv_gate_grad", lp, pp, nbits, 1, bp, k, gp + off * 16, 0, stream)
-            _lib.call("tcb_sv_apply_dense", lp, nbits, 1, bp, k, u, 0, stream)  # lam_in = U^dagger lam_out
+            # psi_in = U^dagger psi_out; dL/dU += lam_out (x) conj(psi_in); lam_in = U^dagger lam_out — one pass
+            _lib.call("tcb_sv_adjoint_step", lp, pp, nbits, 1, bp, k, dp + off * 8, 0, gp + off * 16, 0, stream)
         grad_buf = torch.zeros_like(gatebuf)
         torch.view_as_real(grad_buf).index_add_(0, tabs.scat_dst, g_all[tabs.scat_src].to(torch.float32))
         grad_init = lam if ctx.has_init and ctx.needs_input_grad[1] else None

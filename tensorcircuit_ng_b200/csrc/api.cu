@@ -44,6 +44,8 @@ int launch_pauli_sum(const void*, int, int64_t, const uint64_t*, const uint64_t*
                      void*, int, double*, cudaStream_t);
 int launch_gate_grad(const void*, const void*, int, int64_t, const int*, int, void*, int64_t,
                      cudaStream_t);
+int launch_adjoint_step(void*, void*, int, int64_t, const int*, int, const void*, int64_t, void*, int64_t,
+                        cudaStream_t);
 int launch_pack_half(const void*, void*, int, int, int, int, cudaStream_t);
 int launch_pack_bits(void*, void*, int, int, const int*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
 int launch_contract(const void*, int64_t, const void*, int64_t, void*, const tcb_contract_desc*, int,
@@ -166,6 +168,18 @@ int tcb_sv_gate_grad(const void* lam, const void* psi_in, int nbits, int64_t bat
   NOTNULL(bitpos, "tcb_sv_gate_grad");
   NOTNULL(grad, "tcb_sv_gate_grad");
   return launch_gate_grad(lam, psi_in, nbits, batch, bitpos, k, grad, grad_batch_stride, S(stream));
+}
+
+int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const int* bitpos_host, int k,
+                        const void* udag, int64_t udag_batch_stride, double* grad,
+                        int64_t grad_batch_stride, void* stream) {
+  NOTNULL(lam, "tcb_sv_adjoint_step");
+  NOTNULL(psi, "tcb_sv_adjoint_step");
+  NOTNULL(bitpos_host, "tcb_sv_adjoint_step");
+  NOTNULL(udag, "tcb_sv_adjoint_step");
+  NOTNULL(grad, "tcb_sv_adjoint_step");
+  return launch_adjoint_step(lam, psi, nbits, batch, bitpos_host, k, udag, udag_batch_stride, grad,
+                             grad_batch_stride, S(stream));
 }
 
 int tcb_sv_pack_half(const void* state, void* buf, int nbits, int local_bit, int want, void* stream) {

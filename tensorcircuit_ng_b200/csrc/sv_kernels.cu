@@ -690,6 +690,123 @@ int launch_gate_grad(const void* lam, const void* psi, int nbits, int64_t batch,
 }
 
 // ---------------------------------------------------------------------------------
+// One gate of the adjoint walk in ONE pass over the two states (instead of apply / reduce / apply):
+//   psi <- U^dagger psi ;  G[r][c] += sum_rest lam[rest,r] conj(psi_in[rest,c]) ;  lam <- U^dagger lam
+// 2 reads + 2 writes of a state per gate instead of 4 reads + 2 writes and three launches.
+template <int K>
+__global__ void __launch_bounds__(256, K == 2 ? 2 : 4)
+adjoint_step_kernel(float2* __restrict__ lam, float2* __restrict__ psi, int nbits, uint64_t groups_per_state,
+                    BitList bl, const float2* __restrict__ udag, long long udag_bstride, double* grad,
+                    long long grad_bstride) {
+  constexpr int D = 1 << K;
+  const unsigned b = blockIdx.y;
+  float2* pl = lam + ((size_t)b << nbits);
+  float2* pp = psi + ((size_t)b << nbits);
+  __shared__ float2 u[D * D];  // broadcast reads: keeps 2 D^2 registers free for loads in flight
+  if (threadIdx.x < D * D) u[threadIdx.x] = udag[(size_t)b * udag_bstride + threadIdx.x];
+  __syncthreads();
+  // two-level float accumulation per thread (runs of 32), double across threads and blocks
+  float2 acc[D * D], acc2[D * D];
+#pragma unroll
+  for (int e = 0; e < D * D; ++e) acc[e] = acc2[e] = make_float2(0.f, 0.f);
+  int cnt = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups_per_state; g += stride) {
+    uint64_t base = g;
+#pragma unroll
+    for (int i = 0; i < K; ++i) base = insert_zero(base, bl.sorted[i]);
+    float2 l[D], p[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      uint64_t o = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if ((c >> (K - 1 - i)) & 1) o |= 1ull << bl.pos[i];
+      l[c] = pl[base | o];
+      p[c] = pp[base | o];
+    }
+    float2 pin[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      float2 sp = make_float2(0.f, 0.f), sl = sp;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const float2 m = u[r * D + c];
+        sp.x += m.x * p[c].x - m.y * p[c].y;
+        sp.y += m.x * p[c].y + m.y * p[c].x;
+        sl.x += m.x * l[c].x - m.y * l[c].y;
+        sl.y += m.x * l[c].y + m.y * l[c].x;
+      }
+      pin[r] = sp;
+      uint64_t o = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if ((r >> (K - 1 - i)) & 1) o |= 1ull << bl.pos[i];
+      pp[base | o] = sp;
+      pl[base | o] = sl;
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        acc[r * D + c].x += l[r].x * pin[c].x + l[r].y * pin[c].y;
+        acc[r * D + c].y += l[r].y * pin[c].x - l[r].x * pin[c].y;
+      }
+    if ((++cnt & 31) == 0) {
+#pragma unroll
+      for (int e = 0; e < D * D; ++e) {
+        acc2[e].x += acc[e].x;
+        acc2[e].y += acc[e].y;
+        acc[e] = make_float2(0.f, 0.f);
+      }
+    }
+  }
+  double* gout = grad + (size_t)b * grad_bstride * 2;
+#pragma unroll
+  for (int e = 0; e < D * D; ++e) {
+    const double re = (double)acc2[e].x + (double)acc[e].x;
+    const double im = (double)acc2[e].y + (double)acc[e].y;
+    block_reduce_add2(re, im, gout + 2 * e);
+    __syncthreads();
+  }
+}
+
+int launch_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const int* bitpos, int k,
+                        const void* udag, int64_t udag_bstride, void* grad, int64_t grad_bstride,
+                        cudaStream_t stream) {
+  TCB_REQUIRE(k >= 1 && k <= 2, "tcb_sv_adjoint_step: k=%d unsupported (1..2)", k);
+  TCB_REQUIRE(nbits >= k && nbits <= 40, "tcb_sv_adjoint_step: nbits=%d", nbits);
+  TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_adjoint_step: batch=%lld", (long long)batch);
+  TCB_REQUIRE(lam != psi, "tcb_sv_adjoint_step: lam and psi must be different buffers");
+  BitList bl;
+  for (int i = 0; i < k; ++i) {
+    TCB_REQUIRE(bitpos[i] >= 0 && bitpos[i] < nbits, "tcb_sv_adjoint_step: bit %d out of range", bitpos[i]);
+    bl.pos[i] = bitpos[i];
+    bl.sorted[i] = bitpos[i];
+  }
+  if (k == 2) {
+    TCB_REQUIRE(bl.pos[0] != bl.pos[1], "tcb_sv_adjoint_step: repeated bit %d", bl.pos[0]);
+    if (bl.sorted[0] > bl.sorted[1]) {
+      int t = bl.sorted[0];
+      bl.sorted[0] = bl.sorted[1];
+      bl.sorted[1] = t;
+    }
+  }
+  const uint64_t gps = 1ull << (nbits - k);
+  dim3 grid(grid_for(gps, 256, 8), (unsigned)batch);
+  float2* l = reinterpret_cast<float2*>(lam);
+  float2* p = reinterpret_cast<float2*>(psi);
+  const float2* u = reinterpret_cast<const float2*>(udag);
+  double* g = reinterpret_cast<double*>(grad);
+  if (k == 1)
+    adjoint_step_kernel<1><<<grid, 256, 0, stream>>>(l, p, nbits, gps, bl, u, udag_bstride, g, grad_bstride);
+  else
+    adjoint_step_kernel<2><<<grid, 256, 0, stream>>>(l, p, nbits, gps, bl, u, udag_bstride, g, grad_bstride);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 // pack / unpack the half of the state with local bit == want (global<->local qubit swap)
 __global__ void __launch_bounds__(256)
 pack_half_kernel(const float2* __restrict__ state, float2* __restrict__ buf, uint64_t nhalf, int bit,

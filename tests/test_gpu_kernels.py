@@ -181,6 +181,33 @@ def test_gate_grad_and_pack(cuda):
         assert np.array_equal(st2.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("n,qubits", [(1, [0]), (2, [1, 0]), (7, [3]), (12, [11]), (12, [0, 7]), (13, [12, 2]), (16, [5, 6]),
+                                      (20, [19, 0])])  # fmt: skip
+def test_adjoint_step_fused(cuda, n, qubits):
+    """tcb_sv_adjoint_step == apply(U^dagger, psi); gate_grad(lam, psi_in); apply(U^dagger, lam), batch 1 and 3."""
+    from tensorcircuit_ng_b200 import _lib
+
+    k = len(qubits)
+    rng = np.random.default_rng(n * 7 + k)
+    for batch in (1, 3):
+        lam, psi = _rand_c(rng, (batch, 2**n)), _rand_c(rng, (batch, 2**n))
+        ud = _rand_c(rng, (batch, 2**k, 2**k))
+        lt, pt, ut = torch.from_numpy(lam).cuda(), torch.from_numpy(psi).cuda(), torch.from_numpy(ud).cuda()
+        g = torch.zeros(batch * 4**k * 2, dtype=torch.float64, device="cuda")
+        _lib.call("tcb_sv_adjoint_step", lt.data_ptr(), pt.data_ptr(), n, batch, _lib.int_array([n - 1 - q for q in qubits]),
+                  k, ut.data_ptr(), 4**k, g.data_ptr(), 4**k, _lib.stream_ptr())  # fmt: skip
+        got_g = torch.view_as_complex(g.reshape(-1, 2)).cpu().numpy().reshape(batch, 2**k, 2**k)
+        for b in range(batch):
+            psi_in = _apply_np(psi[b].astype(np.complex128), n, qubits, ud[b].astype(np.complex128))
+            lam_in = _apply_np(lam[b].astype(np.complex128), n, qubits, ud[b].astype(np.complex128))
+            L = np.moveaxis(lam[b].reshape([2] * n), qubits, list(range(k))).reshape(2**k, -1).astype(np.complex128)
+            P = np.moveaxis(psi_in.reshape([2] * n), qubits, list(range(k))).reshape(2**k, -1)
+            want_g = L @ P.conj().T
+            assert np.abs(pt[b].cpu().numpy() - psi_in).max() <= 2e-6 * np.abs(psi_in).max()
+            assert np.abs(lt[b].cpu().numpy() - lam_in).max() <= 2e-6 * np.abs(lam_in).max()
+            assert np.abs(got_g[b] - want_g).max() <= 2e-6 * np.abs(want_g).max() + 1e-6 * np.sqrt(2.0**n)
+
+
 def test_error_reporting(cuda):
     from tensorcircuit_ng_b200 import _lib
 
