@@ -123,6 +123,20 @@ int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
                         const void* udag, int64_t udag_batch_stride, double* grad,
                         int64_t grad_batch_stride, void* stream);
 
+/* ---- statevector: sampling ------------------------------
+ * Replaces probability() + cumsum + searchsorted of tensorcircuit/basecircuit.py:1490-1512 /
+ * tensorcircuit/backends/abstract_backend.py:1828-1861 (and, with mode 1, the per-qubit conditional
+ * draws of perfect sampling / measure_jit, basecircuit.py:449-558) without materialising p or its CDF.
+ * prepare: cdf[s] (float64, 2^(nbits-seg_bits) entries) = inclusive cumulative mass of the segments of
+ *          2^seg_bits amplitudes (seg_bits <= 12) — one read of the state.
+ * sample : out_index[shot] (int64), out_prob[shot] (float64, |psi[index]|^2 / total; may be null).
+ *          mode 0: status[shot] uniform in [0,1): first index with cumulative mass >= total (1 - u).
+ *          mode 1: status[shot][nbits]: qubit j (qubit 0 first) reads 1 iff
+ *                  u_j - P(bit_j = 0 | earlier bits) + 0.31415926e-12 > 0  (measure_jit, :516-531). */
+int tcb_sv_sample_prepare(const void* state, int nbits, int seg_bits, double* cdf, void* stream);
+int tcb_sv_sample(const void* state, int nbits, int seg_bits, const double* cdf, const double* status,
+                  int64_t shots, int mode, int64_t* out_index, double* out_prob, void* stream);
+
 /* ---- sharded statevector: local half of a global<->local qubit swap -------
  * Packs the amplitudes whose local bit `local_bit` == `want` into a contiguous
  * send buffer (and the inverse), so the exchange itself is one NCCL send/recv.           */

@@ -355,6 +355,39 @@ class Circuit:
         return contractor(no).tensor
 
 
+def apply_qsim(c: "Circuit", lines: Sequence[str]) -> "Circuit":
+    """abstractcircuit.py:1284-1351: Google qsim text -> gates (line 0 = qubit count, then
+    "<moment> <gate> <qubits> [<params>]"); the alias table of `:1306-1345`."""
+    half, quarter = np.pi / 2, np.pi / 4
+    for ln in lines[1:]:
+        t = ln.strip().split(" ")
+        if len(t) < 2:
+            continue
+        g, a = t[1].lower(), t[2:]
+        if g in ("h", "x", "y", "z"):
+            getattr(c, g)(int(a[0]))
+        elif g in ("s", "t"):
+            c.phase(int(a[0]), theta=half if g == "s" else quarter)
+        elif g in ("x_1_2", "y_1_2", "z_1_2"):
+            getattr(c, "r" + g[0])(int(a[0]), theta=half)
+        elif g == "w_1_2":
+            c.u(int(a[0]), theta=half, phi=-quarter, lbd=quarter)
+        elif g == "hz_1_2":
+            c.wroot(int(a[0]))
+        elif g in ("cnot", "cx", "cy", "cz"):
+            getattr(c, "cnot" if g == "cx" else g)(int(a[0]), int(a[1]))
+        elif g in ("is", "iswap"):
+            c.iswap(int(a[0]), int(a[1]))
+        elif g in ("rx", "ry", "rz"):
+            getattr(c, g)(int(a[0]), theta=float(a[1]))
+        elif g in ("fs", "fsim"):
+            c.iswap(int(a[0]), int(a[1]), theta=-float(a[2]))
+            c.cphase(int(a[0]), int(a[1]), theta=-float(a[3]))
+        else:
+            raise NotImplementedError(g)
+    return c
+
+
 def _register() -> None:  # abstractcircuit.py:242-373 _meta_apply
     def mk(g: str):
         def method(self: Circuit, *index: Any, **vars: Any) -> None:

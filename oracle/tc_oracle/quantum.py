@@ -97,3 +97,43 @@ def heisenberg_hamiltonian_terms(edges: Sequence[Sequence[int]], n: int, hzz: fl
                 ls.append(s)
                 ws.append(w)
     return ls, ws
+
+
+# -- sampling ----------------------------------------------------------------------
+def probability_sample(shots: int, p: Any, status: Any) -> np.ndarray:
+    """tensorcircuit/backends/abstract_backend.py:1828-1861: p /= sum(p); cumsum; r = cuml[-1] (1 - status);
+    searchsorted (left).  float64 here: the boundaries of the reference's float32 cumsum are not reproducible."""
+    p = np.asarray(p, dtype=np.float64)
+    p = p / np.sum(p)
+    cuml = np.cumsum(p)
+    r = cuml[-1] * (1.0 - np.asarray(status, dtype=np.float64))
+    return np.searchsorted(cuml, r)
+
+
+def measure(psi: Any, index: Sequence[int], status: Sequence[float]):
+    """tensorcircuit/basecircuit.py:461-558 (d = 2 branch) on an explicit state: qubit index[k] reads 1 iff
+    status[k] - P(0 | earlier outcomes) + 0.31415926e-12 > 0 (`:516-531`); returns (bits, probability)."""
+    psi = np.asarray(psi).reshape(-1)
+    n = int(round(np.log2(psi.size)))
+    t = (np.abs(psi.astype(np.complex128)) ** 2).reshape([2] * n)
+    t = t / t.sum()
+    bits: List[float] = []
+    prob = 1.0
+    fixed = {}
+    for k, j in enumerate(index):
+        sl = tuple(fixed.get(q, slice(None)) for q in range(n))
+        cond = t[sl]
+        axes = [q for q in range(n) if q not in fixed]
+        ax = axes.index(j)
+        m = cond.sum(axis=tuple(a for a in range(cond.ndim) if a != ax))
+        pu = m[0] / m.sum() if m.sum() > 0 else 1.0
+        one = status[k] - pu + 0.31415926e-12 > 0
+        bits.append(1.0 if one else 0.0)
+        prob *= (1.0 - pu) if one else pu
+        fixed[j] = 1 if one else 0
+    return np.array(bits), prob
+
+
+def sample_int2bin(sample: Any, n: int) -> np.ndarray:  # tensorcircuit/quantum.py:3587-3605
+    sample = np.asarray(sample)
+    return (sample[..., None] >> np.arange(n)[::-1]) % 2

@@ -36,4 +36,5 @@ from . import sharded  # noqa: F401
 from . import experimental  # noqa: F401
 from . import backend  # noqa: F401
 from . import quantum  # noqa: F401
+from . import sampling  # noqa: F401
 from . import templates  # noqa: F401

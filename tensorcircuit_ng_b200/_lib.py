@@ -100,6 +100,11 @@ SYMBOLS = {
         c_int,
         [c_void_p, c_void_p, c_int, c_int64, POINTER(c_int), c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
     ),
+    "tcb_sv_sample_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "tcb_sv_sample": (
+        c_int,
+        [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p],
+    ),
     "tcb_sv_pack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tcb_sv_unpack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tcb_sv_pack_bits": (

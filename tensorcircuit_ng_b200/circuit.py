@@ -341,6 +341,155 @@ class Circuit:
     def to_qir(self) -> List[Dict[str, Any]]:
         return self._qir
 
+    # basecircuit.py:626-640 ---------------------------------------------------------------------
+    def probability(self) -> torch.Tensor:
+        s = self.wavefunction().reshape(-1)
+        return s.real**2 + s.imag**2
+
+    def _sampler(self) -> Any:
+        from . import sampling
+
+        nodes, _ = self._copy_state_tensor()  # the cached state (contracted once per circuit)
+        return sampling.StateSampler(nodes[0].tensor.reshape(-1), self._nqubits)
+
+    # basecircuit.py:449-558 ---------------------------------------------------------------------
+    def perfect_sampling(self, status: Optional[Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One bitstring ([n] float32 of 0/1) and its probability; `status`: n uniforms (qubit 0 first)."""
+        return self.measure(*range(self._nqubits), with_prob=True, status=status)
+
+    def measure(self, *index: int, with_prob: bool = False, status: Optional[Tensor] = None) -> Tuple[torch.Tensor, Any]:
+        """`measure_jit` (`:461-558`): qubits are read in the order given, qubit `index[k]` gives 1 iff
+        status[k] - P(0 | earlier outcomes) + eps > 0.  All qubits in natural order: one conditional walk
+        over the resident state (`tcb_sv_sample` mode 1); a subset: the same rule on its marginal."""
+        from . import sampling
+
+        n = self._nqubits
+        idx = [i if i >= 0 else n + i for i in index]
+        sampler = self._sampler()
+        dev = sampler.psi.device
+        st = sampling.uniforms([len(idx)], None, dev) if status is None else torch.as_tensor(status).reshape(-1)
+        if len(st) != len(idx):
+            raise ValueError(f"status must have one entry per measured qubit ({len(idx)})")
+        if idx == list(range(n)):
+            flat, prob = sampler.draw(st.reshape(1, n), mode=1)
+            bits = ((flat.reshape(1, 1) >> torch.arange(n - 1, -1, -1, device=dev)) & 1).reshape(n).to(torch.float32)
+            return bits, (prob[0].to(torch.float32) if with_prob else -1.0)
+        if len(set(idx)) != len(idx) or len(idx) > 24:
+            raise ValueError("measure: qubits must be distinct (and at most 24 for a subset)")
+        p = (sampler.psi.real.double() ** 2 + sampler.psi.imag.double() ** 2).reshape([2] * n)
+        rest = [q for q in range(n) if q not in idx]
+        marg = p.sum(dim=rest) if rest else p  # axes = the measured qubits in ascending order
+        if len(idx) > 1:
+            marg = marg.permute(*np.argsort(np.argsort(idx)).tolist())  # ... now in the order they are read
+        marg = (marg / marg.sum()).cpu().numpy().reshape(-1)
+        u = st.detach().cpu().numpy().astype(np.float64)
+        lo, hi, out, pr = 0, len(marg), [], 1.0
+        cum = np.concatenate([[0.0], np.cumsum(marg)])
+        for k in range(len(idx)):
+            mid = (lo + hi) // 2
+            m0, m1 = cum[mid] - cum[lo], cum[hi] - cum[mid]
+            p0 = m0 / (m0 + m1) if m0 + m1 > 0 else 1.0
+            one = u[k] - p0 + 0.31415926e-12 > 0
+            out.append(1.0 if one else 0.0)
+            pr *= (1.0 - p0) if one else p0
+            lo, hi = (mid, hi) if one else (lo, mid)
+        bits = torch.tensor(out, dtype=torch.float32, device=dev)
+        return bits, (torch.tensor(pr, dtype=torch.float32, device=dev) if with_prob else -1.0)
+
+    measure_jit = measure
+
+    # basecircuit.py:1401-1512 -------------------------------------------------------------------
+    def sample(self, batch: Optional[int] = None, allow_state: bool = False, readout_error: Optional[Any] = None,
+               format: Optional[str] = None, random_generator: Optional[Any] = None, status: Optional[Tensor] = None,
+               jittable: bool = True, format_: Optional[str] = None) -> Any:  # fmt: skip
+        """Batched sampling.  `allow_state=True`: CDF inversion with one uniform per shot
+        (`probability_sample`); `allow_state=False`: the perfect-sampling rule with n uniforms per shot.
+        Both read the resident state (one segment-mass pass + one segment per shot); formats as in
+        `quantum.sample2all`."""
+        from . import quantum, sampling
+
+        if readout_error is not None:
+            raise NotImplementedError("readout_error is outside the B200 hot-path scope (SURVEY §2.1)")
+        format = format if format is not None else format_
+        n = self._nqubits
+        nbatch = 1 if batch is None else int(batch)
+        sampler = self._sampler()
+        dev = sampler.psi.device
+        if allow_state:
+            st = sampling.uniforms([nbatch], random_generator, dev) if status is None else torch.as_tensor(status)
+            if st.reshape(-1).shape[0] != nbatch:
+                raise ValueError(f"status must have shape [{nbatch}]")
+            ch, prob = sampler.draw(st.reshape(nbatch), mode=0)
+        else:
+            st = sampling.uniforms([nbatch, n], random_generator, dev) if status is None else torch.as_tensor(status)
+            st = st.reshape(1, n) if st.dim() == 1 else st
+            if tuple(st.shape) != (nbatch, n):
+                raise ValueError(f"status must have shape [{nbatch}, {n}]")
+            ch, prob = sampler.draw(st, mode=1)
+        if format is None:  # backward-compatible form: (configuration, probability) per shot
+            confg = quantum.sample_int2bin(ch, n)
+            if allow_state:
+                r = list(zip(confg, prob.to(torch.float32)))
+            else:
+                r = [(c.to(torch.float32), p) for c, p in zip(confg, prob.to(torch.float32))]
+            return r[0] if batch is None else r
+        if n > 32:
+            if format == "sample_bin":
+                return quantum.sample_int2bin(ch, n)
+            if format == "count_dict_bin":
+                from collections import Counter
+
+                return dict(Counter("".join(str(int(b)) for b in row) for row in quantum.sample_int2bin(ch, n).cpu().tolist()))
+            raise ValueError(f"n={n} is too large for measurement representaion: {format}")
+        return quantum.sample2all(ch, n, format=format, jittable=jittable)
+
+    # abstractcircuit.py:1269-1351 ----------------------------------------------------------------
+    # Google qsim text format (the public RCS circuit files that feed config 5): line 1 = qubit count,
+    # then "<moment> <gate> <qubits...> [<params...>]".  gate -> (method, number of qubits, fixed
+    # parameters, names of the trailing numeric parameters); `fs` / `fsim` expands to iswap(-theta) +
+    # cphase(-phi) as in the reference (`:1340-1343`).
+    _QSIM: Dict[str, Tuple[str, int, Dict[str, float], Tuple[str, ...]]] = {
+        "h": ("h", 1, {}, ()), "x": ("x", 1, {}, ()), "y": ("y", 1, {}, ()), "z": ("z", 1, {}, ()),
+        "s": ("phase", 1, {"theta": np.pi / 2}, ()), "t": ("phase", 1, {"theta": np.pi / 4}, ()),
+        "x_1_2": ("rx", 1, {"theta": np.pi / 2}, ()), "y_1_2": ("ry", 1, {"theta": np.pi / 2}, ()),
+        "z_1_2": ("rz", 1, {"theta": np.pi / 2}, ()),
+        "w_1_2": ("u", 1, {"theta": np.pi / 2, "phi": -np.pi / 4, "lbd": np.pi / 4}, ()),
+        "hz_1_2": ("wroot", 1, {}, ()),
+        "cnot": ("cnot", 2, {}, ()), "cx": ("cx", 2, {}, ()), "cy": ("cy", 2, {}, ()), "cz": ("cz", 2, {}, ()),
+        "is": ("iswap", 2, {}, ()), "iswap": ("iswap", 2, {}, ()),
+        "rx": ("rx", 1, {}, ("theta",)), "ry": ("ry", 1, {}, ("theta",)), "rz": ("rz", 1, {}, ("theta",)),
+    }  # fmt: skip
+
+    @classmethod
+    def from_qsim_file(cls, file: str, circuit_params: Optional[Dict[str, Any]] = None) -> "Circuit":
+        with open(file, "r") as f:
+            lines = f.readlines()
+        params = dict(circuit_params or {})
+        params.setdefault("nqubits", int(lines[0]))
+        return cls._apply_qsim(cls(**params), lines)
+
+    @staticmethod
+    def _apply_qsim(c: "Circuit", qsim_str: Sequence[str]) -> "Circuit":
+        for line in qsim_str[1:]:
+            tok = line.strip().split()
+            if not tok:
+                continue
+            name = tok[1].lower()
+            if name in ("fs", "fsim"):
+                i, j, theta, phi = int(tok[2]), int(tok[3]), float(tok[4]), float(tok[5])
+                c.iswap(i, j, theta=-theta)
+                c.cphase(i, j, theta=-phi)
+                continue
+            spec = Circuit._QSIM.get(name)
+            if spec is None:
+                raise NotImplementedError(f"qsim gate `{tok[1]}` is not supported")
+            method, nq, fixed, pnames = spec
+            kws: Dict[str, Any] = dict(fixed)
+            for pn, v in zip(pnames, tok[2 + nq :]):
+                kws[pn] = float(v)
+            getattr(c, method)(*[int(t) for t in tok[2 : 2 + nq]], **kws)
+        return c
+
 
 _ZERO = np.array([1.0, 0.0])
 

@@ -46,6 +46,9 @@ int launch_gate_grad(const void*, const void*, int, int64_t, const int*, int, vo
                      cudaStream_t);
 int launch_adjoint_step(void*, void*, int, int64_t, const int*, int, const void*, int64_t, void*, int64_t,
                         cudaStream_t);
+int launch_sample_prepare(const void*, int, int, double*, cudaStream_t);
+int launch_sample(const void*, int, int, const double*, const double*, int64_t, int, long long*, double*,
+                  cudaStream_t);
 int launch_pack_half(const void*, void*, int, int, int, int, cudaStream_t);
 int launch_pack_bits(void*, void*, int, int, const int*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
 int launch_contract(const void*, int64_t, const void*, int64_t, void*, const tcb_contract_desc*, int,
@@ -180,6 +183,22 @@ int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
   NOTNULL(grad, "tcb_sv_adjoint_step");
   return launch_adjoint_step(lam, psi, nbits, batch, bitpos_host, k, udag, udag_batch_stride, grad,
                              grad_batch_stride, S(stream));
+}
+
+int tcb_sv_sample_prepare(const void* state, int nbits, int seg_bits, double* cdf, void* stream) {
+  NOTNULL(state, "tcb_sv_sample_prepare");
+  NOTNULL(cdf, "tcb_sv_sample_prepare");
+  return launch_sample_prepare(state, nbits, seg_bits, cdf, S(stream));
+}
+
+int tcb_sv_sample(const void* state, int nbits, int seg_bits, const double* cdf, const double* status,
+                  int64_t shots, int mode, int64_t* out_index, double* out_prob, void* stream) {
+  NOTNULL(state, "tcb_sv_sample");
+  NOTNULL(cdf, "tcb_sv_sample");
+  NOTNULL(status, "tcb_sv_sample");
+  NOTNULL(out_index, "tcb_sv_sample");
+  return launch_sample(state, nbits, seg_bits, cdf, status, shots, mode,
+                       reinterpret_cast<long long*>(out_index), out_prob, S(stream));
 }
 
 int tcb_sv_pack_half(const void* state, void* buf, int nbits, int local_bit, int want, void* stream) {

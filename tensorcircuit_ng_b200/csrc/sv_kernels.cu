@@ -598,6 +598,192 @@ int launch_pauli_sum(const void* state, int nbits, int64_t batch, const uint64_t
 }
 
 // ---------------------------------------------------------------------------------
+// Sampling from the resident state.  The reference materialises p = |psi|^2 and its
+// cumulative sum (2 x 2^n floats) and searches it (backends/abstract_backend.py:1828-1861); here neither
+// exists: one read of the state leaves the mass of every 2^SB-amplitude segment (float64), a one-CTA scan
+// turns that into the segment CDF, and every shot re-reads only the one segment it lands in.
+constexpr int SAMPLE_PER = 16;  // amplitudes per thread of the resolving CTA
+
+__global__ void __launch_bounds__(256)
+segment_mass_kernel(const float2* __restrict__ state, int seg_bits, uint64_t nseg, double* __restrict__ mass) {
+  // one warp per segment (segments of >= 32 amplitudes), grid-stride over segments
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t len = 1ull << seg_bits;
+  for (uint64_t sgm = warp; sgm < nseg; sgm += nwarp) {
+    const float2* st = state + (sgm << seg_bits);
+    double acc = 0.0;
+    for (uint64_t i = lane; i < len; i += 32 * 4) {
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t x = i + 32ull * j;
+        if (x < len) {
+          const float2 a = st[x];
+          part += a.x * a.x + a.y * a.y;
+        }
+      }
+      acc += (double)part;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) mass[sgm] = acc;
+  }
+}
+
+// inclusive scan of n float64 values in place, one CTA (n is at most a few hundred thousand)
+__global__ void __launch_bounds__(1024)
+scan_inplace_kernel(double* __restrict__ v, uint64_t n) {
+  __shared__ double tot[1024];
+  const uint64_t per = (n + blockDim.x - 1) / blockDim.x;
+  const uint64_t lo = (uint64_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+  double s = 0.0;
+  for (uint64_t i = lo; i < hi; ++i) s += v[i];
+  tot[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    for (unsigned t = 0; t < blockDim.x; ++t) {
+      const double x = tot[t];
+      tot[t] = run;
+      run += x;
+    }
+  }
+  __syncthreads();
+  double run = tot[threadIdx.x];
+  for (uint64_t i = lo; i < hi; ++i) {
+    run += v[i];
+    v[i] = run;
+  }
+}
+
+// mode 0: CDF inversion with ONE uniform per shot (probability_sample): first index whose inclusive
+//         cumulative mass reaches total * (1 - u).
+// mode 1: conditional walk with nbits uniforms per shot, qubit 0 first (the order and the decision rule of
+//         the reference's perfect sampling = measure_jit on every qubit, basecircuit.py:449-459,:516-531):
+//         bit_j = 1 iff u_j - p(bit_j = 0 | bits before) + eps > 0.
+constexpr double kMeasureEps = 0.31415926e-12;  // basecircuit.py:524
+__global__ void __launch_bounds__(256)
+sample_resolve_kernel(const float2* __restrict__ state, int nbits, int seg_bits, const double* __restrict__ cdf,
+                      const double* __restrict__ status, int mode, long long* __restrict__ out_index,
+                      double* __restrict__ out_prob) {
+  __shared__ double pre[1 << 12];   // per-thread-chunk inclusive prefix of |psi|^2 in the segment
+  __shared__ double tcum[257];      // exclusive prefix of the chunk totals
+  __shared__ unsigned long long s_seg;
+  __shared__ double s_target;
+  const uint64_t shot = blockIdx.x;
+  const uint64_t nseg = 1ull << (nbits - seg_bits);
+  const uint64_t len = 1ull << seg_bits;
+  const int per = len < (uint64_t)SAMPLE_PER ? (int)len : SAMPLE_PER;
+  const int nthr = (int)(len / per);
+  const double total = cdf[nseg - 1];
+  auto seg_cdf = [&](uint64_t i) -> double { return i == 0 ? 0.0 : cdf[i - 1]; };  // exclusive
+  if (threadIdx.x == 0) {
+    uint64_t seg = 0;
+    double target = 0.0;
+    if (mode == 0) {
+      const double r = total * (1.0 - status[shot]);
+      uint64_t lo = 0, hi = nseg - 1;  // first segment with inclusive cdf >= r
+      while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (cdf[mid] >= r) hi = mid; else lo = mid + 1;
+      }
+      seg = lo;
+      target = r - seg_cdf(seg);
+    } else {
+      uint64_t lo = 0, hi = nseg;
+      for (int j = 0; j < nbits - seg_bits; ++j) {
+        const uint64_t mid = (lo + hi) >> 1;
+        const double m0 = seg_cdf(mid) - seg_cdf(lo), m1 = seg_cdf(hi) - seg_cdf(mid);
+        const double p0 = m0 + m1 > 0.0 ? m0 / (m0 + m1) : 1.0;
+        if (status[shot * nbits + j] - p0 + kMeasureEps > 0.0) lo = mid; else hi = mid;
+      }
+      seg = lo;
+    }
+    s_seg = seg;
+    s_target = target;
+  }
+  __syncthreads();
+  const float2* st = state + ((uint64_t)s_seg << seg_bits);
+  if ((int)threadIdx.x < nthr) {
+    double run = 0.0;
+    for (int e = 0; e < per; ++e) {
+      const float2 a = st[(uint64_t)threadIdx.x * per + e];
+      run += (double)(a.x * a.x + a.y * a.y);
+      pre[threadIdx.x * per + e] = run;
+    }
+    tcum[threadIdx.x + 1] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    tcum[0] = 0.0;
+    for (int t = 1; t <= nthr; ++t) {
+      run += tcum[t];
+      tcum[t] = run;  // tcum[t] = mass of chunks [0, t)
+    }
+    uint64_t idx;
+    if (mode == 0) {
+      const double tgt = s_target;
+      int lo = 0, hi = nthr - 1;  // first chunk whose inclusive mass reaches the target
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tcum[mid + 1] >= tgt) hi = mid; else lo = mid + 1;
+      }
+      const double rem = tgt - tcum[lo];
+      int e = 0;
+      while (e < per - 1 && pre[lo * per + e] < rem) ++e;
+      idx = (uint64_t)lo * per + e;
+    } else {
+      // mass of [a, b) inside the segment from the two-level prefix
+      auto cum = [&](uint64_t x) -> double {  // mass of [0, x)
+        if (x == 0) return 0.0;
+        const uint64_t c = (x - 1) / per;
+        return tcum[c] + pre[x - 1];
+      };
+      uint64_t lo = 0, hi = len;
+      for (int j = nbits - seg_bits; j < nbits; ++j) {
+        const uint64_t mid = (lo + hi) >> 1;
+        const double m0 = cum(mid) - cum(lo), m1 = cum(hi) - cum(mid);
+        const double p0 = m0 + m1 > 0.0 ? m0 / (m0 + m1) : 1.0;
+        if (status[shot * nbits + j] - p0 + kMeasureEps > 0.0) lo = mid; else hi = mid;
+      }
+      idx = lo;
+    }
+    const float2 a = st[idx];
+    out_index[shot] = (long long)(((uint64_t)s_seg << seg_bits) | idx);
+    if (out_prob) out_prob[shot] = (double)(a.x * a.x + a.y * a.y) / total;
+  }
+}
+
+int launch_sample_prepare(const void* state, int nbits, int seg_bits, double* cdf, cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_sample_prepare: nbits=%d", nbits);
+  TCB_REQUIRE(seg_bits >= 0 && seg_bits <= 12 && seg_bits <= nbits, "tcb_sv_sample_prepare: seg_bits=%d", seg_bits);
+  TCB_REQUIRE(nbits - seg_bits <= 28, "tcb_sv_sample_prepare: too many segments (nbits - seg_bits = %d)", nbits - seg_bits);
+  const uint64_t nseg = 1ull << (nbits - seg_bits);
+  segment_mass_kernel<<<grid_for(nseg * 32, 256), 256, 0, stream>>>(reinterpret_cast<const float2*>(state), seg_bits,
+                                                                   nseg, cdf);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  scan_inplace_kernel<<<1, 1024, 0, stream>>>(cdf, nseg);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_sample(const void* state, int nbits, int seg_bits, const double* cdf, const double* status,
+                  int64_t shots, int mode, long long* out_index, double* out_prob, cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_sample: nbits=%d", nbits);
+  TCB_REQUIRE(seg_bits >= 0 && seg_bits <= 12 && seg_bits <= nbits, "tcb_sv_sample: seg_bits=%d", seg_bits);
+  TCB_REQUIRE(mode == 0 || mode == 1, "tcb_sv_sample: mode=%d (0 = cdf, 1 = conditional walk)", mode);
+  TCB_REQUIRE(shots >= 0 && shots <= (1ll << 31) - 1, "tcb_sv_sample: shots=%lld", (long long)shots);
+  if (shots == 0) return 0;
+  sample_resolve_kernel<<<(unsigned)shots, 256, 0, stream>>>(reinterpret_cast<const float2*>(state), nbits, seg_bits,
+                                                            cdf, status, mode, out_index, out_prob);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 // adjoint-mode gate gradient: G[r][c] = sum_rest lam[rest,r] * conj(psi[rest,c])
 template <int K>
 __global__ void __launch_bounds__(256)

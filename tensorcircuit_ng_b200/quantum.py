@@ -244,3 +244,64 @@ def heisenberg_hamiltonian(g: Any, hzz: float = 1.0, hxx: float = 1.0, hyy: floa
     if sparse:
         return PauliStringSum2COO(ls, ws, numpy=numpy)
     return PauliStringSum2Dense(ls, ws, numpy=numpy)
+
+
+# -- measurement result formats (`tensorcircuit/quantum.py:3587-3902`) -------------------------------
+def sample_int2bin(sample: torch.Tensor, n: int, dim: Optional[int] = None) -> torch.Tensor:
+    """[shots] flat indices -> [shots, n] bits, qubit 0 first (`:3587-3613`)."""
+    if dim not in (None, 2):
+        raise NotImplementedError("qudits are outside the B200 hot-path scope (SURVEY §2.1)")
+    shifts = torch.arange(n - 1, -1, -1, device=sample.device, dtype=torch.int64)
+    return (sample.to(torch.int64)[..., None] >> shifts) & 1
+
+
+def sample_bin2int(sample: torch.Tensor, n: int, dim: Optional[int] = None) -> torch.Tensor:
+    """[shots, n] bits -> [shots] flat indices."""
+    if dim not in (None, 2):
+        raise NotImplementedError("qudits are outside the B200 hot-path scope (SURVEY §2.1)")
+    w = 2 ** torch.arange(n - 1, -1, -1, device=sample.device, dtype=torch.int64)
+    return (sample.to(torch.int64) * w).sum(-1)
+
+
+def sample2count(sample: torch.Tensor, n: int, jittable: bool = True, dim: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """count_tuple: (distinct flat indices, their counts)."""
+    return torch.unique(sample.to(torch.int64), return_counts=True)
+
+
+def count_s2d(srepr: Tuple[torch.Tensor, torch.Tensor], n: int, dim: Optional[int] = None) -> torch.Tensor:
+    """count_tuple -> count_vector of length 2^n."""
+    idx, cnt = srepr
+    out = torch.zeros(1 << n, dtype=cnt.dtype, device=cnt.device)
+    out[idx] = cnt
+    return out
+
+
+def count_tuple2dict(count_tuple: Tuple[torch.Tensor, torch.Tensor], n: int, key: str = "bin", dim: Optional[int] = None) -> Dict[Any, int]:
+    idx, cnt = (t.cpu().tolist() for t in count_tuple)
+    if key == "int":
+        return {int(i): int(c) for i, c in zip(idx, cnt)}
+    return {format(int(i), f"0{n}b"): int(c) for i, c in zip(idx, cnt)}
+
+
+def sample2all(sample: torch.Tensor, n: int, format: str = "count_vector", jittable: bool = False, dim: Optional[int] = None) -> Any:
+    """`:3840-3902`: sample_int / sample_bin / count_vector / count_tuple / count_dict_bin / count_dict_int."""
+    if sample.dim() == 1:
+        s_int, s_bin = sample, None
+    elif sample.dim() == 2:
+        s_int, s_bin = sample_bin2int(sample, n), sample
+    else:
+        raise ValueError("unrecognized tensor shape for sample")
+    if format == "sample_int":
+        return s_int
+    if format == "sample_bin":
+        return s_bin if s_bin is not None else sample_int2bin(s_int, n)
+    ct = sample2count(s_int, n, jittable=jittable)
+    if format == "count_tuple":
+        return ct
+    if format == "count_vector":
+        return count_s2d(ct, n)
+    if format == "count_dict_bin":
+        return count_tuple2dict(ct, n, key="bin")
+    if format == "count_dict_int":
+        return count_tuple2dict(ct, n, key="int")
+    raise ValueError("unsupported format %s for finite shots measurement" % format)
