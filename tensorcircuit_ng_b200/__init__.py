@@ -37,4 +37,7 @@ from . import experimental  # noqa: F401
 from . import backend  # noqa: F401
 from . import quantum  # noqa: F401
 from . import sampling  # noqa: F401
+from . import interfaces  # noqa: F401
+from . import torchnn  # noqa: F401
+from .torchnn import QuantumNet, TorchLayer  # noqa: F401
 from . import templates  # noqa: F401

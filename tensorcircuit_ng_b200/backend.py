@@ -95,3 +95,37 @@ def vectorized_value_and_grad(f: Callable[..., Any], argnums: Union[int, Sequenc
 
 
 vvag = vectorized_value_and_grad
+
+
+# -- the handful of array helpers callers of the path write their losses with (pytorch_backend.py) --------
+name = "pytorch"
+stack = torch.stack
+real = torch.real
+imag = torch.imag
+sum = torch.sum  # noqa: A001  (the reference's backend.sum)
+mean = torch.mean
+reshape = torch.reshape
+ones = torch.ones
+zeros = torch.zeros
+cast = lambda a, dtype: a.to(getattr(torch, dtype) if isinstance(dtype, str) else dtype)  # noqa: E731
+
+
+def convert_to_tensor(a: Any) -> torch.Tensor:
+    return a if isinstance(a, torch.Tensor) else torch.as_tensor(a)
+
+
+def numpy(a: Any) -> Any:  # noqa: A001
+    return a.detach().resolve_conj().cpu().numpy() if isinstance(a, torch.Tensor) else a
+
+
+def get_random_state(seed: Any = None) -> torch.Generator:
+    """pytorch_backend.py `get_random_state`: a torch.Generator (host side; draws are moved to the GPU)."""
+    g = torch.Generator(device="cpu")
+    if seed is not None:
+        g.manual_seed(int(seed))
+    return g
+
+
+def jit(f: Callable[..., Any], **kws: Any) -> Callable[..., Any]:
+    """No tracing compiler on this engine: plans are cached by circuit structure instead (svengine)."""
+    return f
