@@ -43,7 +43,8 @@ def test_quantumnet_values_and_training_gradients(cuda):
     loss = ql(x[None, :])[0].sum()
     loss.backward()
     g = ql.q_weights[0].grad.cpu().numpy()
-    f0 = lambda ww: float(np.sum(oracle(x.numpy().astype(np.float64), ww)))
+    xh = x.cpu().numpy().astype(np.float64)
+    f0 = lambda ww: float(np.sum(oracle(xh, ww)))
     for (a, b) in [(0, 0), (1, 3), (3, 5), (2, 2)]:
         wp, wm = w.copy(), w.copy()
         wp[a, b] += 1e-4
