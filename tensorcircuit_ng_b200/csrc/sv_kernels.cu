@@ -497,69 +497,140 @@ int launch_inner(const void* a, const void* b, int nbits, int64_t batch, double*
 //   (H psi)[i] = sum_t c_t (-1)^popc((i ^ x_t) & z_t) psi[i ^ x_t],   c_t = w_t i^{ny_t}
 // Terms arrive sorted by flip mask; every run of equal x_t is one load of psi[i ^ x] and its
 // coefficients fold into one complex factor per amplitude before the multiply.  One launch writes
-// H psi and / or accumulates <psi|H|psi>; each thread owns two neighbouring amplitudes (16-byte
-// accesses; flips of bit 0 swap the halves in registers).
+// H psi and / or accumulates <psi|H|psi>; each thread owns eight neighbouring amplitudes (64 contiguous
+// bytes per access; flips of the three low bits permute registers) and the sign of a term is one popc for
+// the high bits plus a per-term 8-bit table for the low ones, applied as +-1.0f in an FFMA.
 constexpr int PS_MAX_TERMS = 1024;
 
-template <bool kWrite, bool kAccum, bool kValue>
+// LB = log2(amplitudes per thread): 3 (64 contiguous bytes per access) or 1 for states of fewer than 8 amplitudes.
+template <int LB, bool kWrite, bool kAccum, bool kValue>
 __global__ void __launch_bounds__(256)
-pauli_sum_kernel(const float4* __restrict__ state, uint64_t nvec_per_state,
+pauli_sum_kernel(const float4* __restrict__ state, uint64_t nblk_per_state,
                  const unsigned long long* __restrict__ xs, const unsigned long long* __restrict__ zs,
                  const float2* __restrict__ cs, int nterms, unsigned long long index_base,
                  float4* __restrict__ out_state, double* out_value) {
+  constexpr int A = 1 << LB;   // amplitudes per thread
+  constexpr int V = A / 2;     // float4 per thread
   __shared__ unsigned long long sx[PS_MAX_TERMS], sz[PS_MAX_TERMS];
   __shared__ float2 sc[PS_MAX_TERMS];
+  __shared__ unsigned slm[PS_MAX_TERMS];  // bit j: parity of ((j ^ x) & z) over the low LB bits
   for (int t = threadIdx.x; t < nterms; t += blockDim.x) {
-    sx[t] = xs[t];
-    sz[t] = zs[t];
+    const unsigned long long x = xs[t], z = zs[t];
+    sx[t] = x;
+    sz[t] = z;
     sc[t] = cs[t];
+    unsigned lm = 0;
+#pragma unroll
+    for (int jj = 0; jj < A; ++jj) lm |= (unsigned)(__popc((jj ^ (unsigned)(x & (A - 1))) & (unsigned)(z & (A - 1))) & 1) << jj;
+    slm[t] = lm;
   }
   __syncthreads();
   const unsigned b = blockIdx.y;
-  const float4* st = state + (size_t)b * nvec_per_state;
-  float4* os = kWrite ? out_state + (size_t)b * nvec_per_state : nullptr;
+  const float4* st = state + (size_t)b * nblk_per_state * V;
+  float4* os = kWrite ? out_state + (size_t)b * nblk_per_state * V : nullptr;
   double dre = 0.0, dim_ = 0.0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nvec_per_state; p += stride) {
-    const unsigned long long i0 = (p << 1) | index_base;
-    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nblk_per_state; p += stride) {
+    const unsigned long long ihi = ((p << LB) | index_base) >> LB;
+    float2 acc[A];
+#pragma unroll
+    for (int jj = 0; jj < A; ++jj) acc[jj] = make_float2(0.f, 0.f);
     int t = 0;
     while (t < nterms) {
       const unsigned long long x = sx[t];
-      float4 v = st[p ^ (x >> 1)];
-      if (x & 1ull) v = make_float4(v.z, v.w, v.x, v.y);
-      float2 d0 = make_float2(0.f, 0.f), d1 = d0;
+      const float4* src = st + ((p ^ (x >> LB)) * V);
+      float2 v[A];
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const float4 w = src[q];
+        v[2 * q] = make_float2(w.x, w.y);
+        v[2 * q + 1] = make_float2(w.z, w.w);
+      }
+      // v[j] <- v[j ^ (x & (A-1))]: uniform branches (every thread walks the same term list)
+#pragma unroll
+      for (int bit = 0; bit < LB; ++bit) {
+        if ((x >> bit) & 1ull) {
+#pragma unroll
+          for (int jj = 0; jj < A; ++jj)
+            if (!(jj & (1 << bit))) {
+              const float2 tmp = v[jj];
+              v[jj] = v[jj | (1 << bit)];
+              v[jj | (1 << bit)] = tmp;
+            }
+        }
+      }
+      float2 d[A];
+#pragma unroll
+      for (int jj = 0; jj < A; ++jj) d[jj] = make_float2(0.f, 0.f);
       do {
         const unsigned long long z = sz[t];
         const float2 c = sc[t];
-        const bool odd0 = __popcll((i0 ^ x) & z) & 1;
-        const bool odd1 = odd0 != bool(z & 1ull);
-        d0.x += odd0 ? -c.x : c.x;
-        d0.y += odd0 ? -c.y : c.y;
-        d1.x += odd1 ? -c.x : c.x;
-        d1.y += odd1 ? -c.y : c.y;
+        unsigned m = slm[t];
+        if (__popcll((ihi ^ (x >> LB)) & (z >> LB)) & 1) m = ~m;
+#pragma unroll
+        for (int jj = 0; jj < A; ++jj) {
+          const float sg = __uint_as_float(0x3f800000u | ((m << (31 - jj)) & 0x80000000u));
+          d[jj].x = fmaf(sg, c.x, d[jj].x);
+          d[jj].y = fmaf(sg, c.y, d[jj].y);
+        }
         ++t;
       } while (t < nterms && sx[t] == x);
-      a0.x += d0.x * v.x - d0.y * v.y;
-      a0.y += d0.x * v.y + d0.y * v.x;
-      a1.x += d1.x * v.z - d1.y * v.w;
-      a1.y += d1.x * v.w + d1.y * v.z;
+#pragma unroll
+      for (int jj = 0; jj < A; ++jj) {
+        acc[jj].x += d[jj].x * v[jj].x - d[jj].y * v[jj].y;
+        acc[jj].y += d[jj].x * v[jj].y + d[jj].y * v[jj].x;
+      }
     }
     if (kValue) {
-      const float4 u = st[p];  // conj(psi) . (H psi)
-      dre += (double)(u.x * a0.x + u.y * a0.y + u.z * a1.x + u.w * a1.y);
-      dim_ += (double)(u.x * a0.y - u.y * a0.x + u.z * a1.y - u.w * a1.x);
+      float re = 0.f, im = 0.f;
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const float4 u = st[p * V + q];  // conj(psi) . (H psi)
+        re += u.x * acc[2 * q].x + u.y * acc[2 * q].y + u.z * acc[2 * q + 1].x + u.w * acc[2 * q + 1].y;
+        im += u.x * acc[2 * q].y - u.y * acc[2 * q].x + u.z * acc[2 * q + 1].y - u.w * acc[2 * q + 1].x;
+      }
+      dre += (double)re;
+      dim_ += (double)im;
     }
     if (kWrite) {
-      float4 r = make_float4(a0.x, a0.y, a1.x, a1.y);
-      if (kAccum) {
-        const float4 o = os[p];
-        r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        float4 r = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+        if (kAccum) {
+          const float4 o = os[p * V + q];
+          r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+        }
+        os[p * V + q] = r;
       }
-      os[p] = r;
     }
   }
   if (kValue) block_reduce_add2(dre, dim_, out_value + 2 * (size_t)b);
+}
+
+template <int LB>
+static int pauli_sum_dispatch(const float4* st, int nbits, int64_t batch, const unsigned long long* xs,
+                              const unsigned long long* zs, const float2* cs, int nterms, uint64_t index_base,
+                              float4* os, bool acc, double* out_value, cudaStream_t stream) {
+  const uint64_t nblk = 1ull << (nbits - LB);
+  dim3 grid(grid_for(nblk, 256), (unsigned)batch);
+  int first = 0;
+  do {  // more terms than one shared-memory table: further launches accumulate
+    const int cnt = nterms - first < PS_MAX_TERMS ? nterms - first : PS_MAX_TERMS;
+#define TCB_PS_LAUNCH(W, AC, VAL) \
+  pauli_sum_kernel<LB, W, AC, VAL><<<grid, 256, 0, stream>>>(st, nblk, xs + first, zs + first, cs + first, cnt, index_base, os, out_value)
+    if (os && out_value) {
+      if (acc) TCB_PS_LAUNCH(true, true, true); else TCB_PS_LAUNCH(true, false, true);
+    } else if (os) {
+      if (acc) TCB_PS_LAUNCH(true, true, false); else TCB_PS_LAUNCH(true, false, false);
+    } else {
+      TCB_PS_LAUNCH(false, false, true);
+    }
+#undef TCB_PS_LAUNCH
+    TCB_CHECK_CUDA(cudaGetLastError());
+    first += cnt;
+    acc = true;
+  } while (first < nterms);
+  return 0;
 }
 
 int launch_pauli_sum(const void* state, int nbits, int64_t batch, const uint64_t* xmask,
@@ -570,31 +641,14 @@ int launch_pauli_sum(const void* state, int nbits, int64_t batch, const uint64_t
   TCB_REQUIRE(nterms >= 0, "tcb_sv_pauli_sum: nterms=%d", nterms);
   TCB_REQUIRE(out_state != nullptr || out_value != nullptr, "tcb_sv_pauli_sum: nothing to compute");
   TCB_REQUIRE(out_state != state, "tcb_sv_pauli_sum: out_state must not alias state");
-  const uint64_t nvec = 1ull << (nbits - 1);
-  dim3 grid(grid_for(nvec, 256), (unsigned)batch);
   const float4* st = reinterpret_cast<const float4*>(state);
   float4* os = reinterpret_cast<float4*>(out_state);
   const unsigned long long* xs = reinterpret_cast<const unsigned long long*>(xmask);
   const unsigned long long* zs = reinterpret_cast<const unsigned long long*>(zmask);
   const float2* cs = reinterpret_cast<const float2*>(coef);
-  bool acc = accumulate != 0;
-  int first = 0;
-  do {  // more terms than one shared-memory table: further launches accumulate
-    const int cnt = nterms - first < PS_MAX_TERMS ? nterms - first : PS_MAX_TERMS;
-    if (os && out_value) {
-      if (acc) pauli_sum_kernel<true, true, true><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
-      else pauli_sum_kernel<true, false, true><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
-    } else if (os) {
-      if (acc) pauli_sum_kernel<true, true, false><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
-      else pauli_sum_kernel<true, false, false><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
-    } else {
-      pauli_sum_kernel<false, false, true><<<grid, 256, 0, stream>>>(st, nvec, xs + first, zs + first, cs + first, cnt, index_base, os, out_value);
-    }
-    TCB_CHECK_CUDA(cudaGetLastError());
-    first += cnt;
-    acc = true;
-  } while (first < nterms);
-  return 0;
+  if (nbits >= 3)
+    return pauli_sum_dispatch<3>(st, nbits, batch, xs, zs, cs, nterms, index_base, os, accumulate != 0, out_value, stream);
+  return pauli_sum_dispatch<1>(st, nbits, batch, xs, zs, cs, nterms, index_base, os, accumulate != 0, out_value, stream);
 }
 
 // ---------------------------------------------------------------------------------

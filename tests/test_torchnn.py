@@ -47,9 +47,9 @@ def test_quantumnet_values_and_training_gradients(cuda):
     f0 = lambda ww: float(np.sum(oracle(xh, ww)))
     for (a, b) in [(0, 0), (1, 3), (3, 5), (2, 2)]:
         wp, wm = w.copy(), w.copy()
-        wp[a, b] += 1e-4
-        wm[a, b] -= 1e-4
-        assert abs(g[a, b] - (f0(wp) - f0(wm)) / 2e-4) < 2e-3
+        wp[a, b] += 1e-2  # (the oracle computes in complex64: a smaller step drowns in rounding)
+        wm[a, b] -= 1e-2
+        assert abs(g[a, b] - (f0(wp) - f0(wm)) / 2e-2) < 5e-3
     torch.optim.SGD(ql.parameters(), lr=0.1).step()
 
 
