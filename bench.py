@@ -462,6 +462,34 @@ def rcs_plan_path(rows: int, cols: int, depth: int, log2_target: int) -> str:
     return os.path.join(ROOT, "plans", f"rcs_{rows}x{cols}_d{depth}_t{log2_target}.pkl")
 
 
+def cpu_contraction_sample(tc: Any, DistributedContractor: Any, planner: Any) -> Any:
+    """CPU leg of the contraction workload: the reference's pairwise tree execution restated on numpy
+    (oracle/tc_oracle/treeexec.py, `tensorcircuit/cons.py:937-953`) on a BOUNDED sample of the same family — the
+    whole (unsliced) amplitude of the 6x6 depth-14 circuit with its committed plan; TFLOP/s is a rate."""
+    import pickle
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from tc_oracle.treeexec import contract_tree_numpy
+
+    rows = cols = 6
+    depth, lt = 14, 26
+    path = rcs_plan_path(rows, cols, depth, lt)
+    if not os.path.exists(path):
+        return None
+    td = pickle.load(open(path, "rb"))
+    nodes_fn = lambda _: build_rcs(tc, rows, cols, depth).amplitude_before("0" * (rows * cols))  # noqa: E731
+    _, _, _, tensors, _ = DistributedContractor._network(nodes_fn, None, True)
+    arrays = [t.detach().cpu().numpy() for t in tensors]
+    st = planner.path_stats(td["inputs"], td["output"], td["size_dict"], td["path"], list(td["sliced_inds"]))
+    t0 = time.perf_counter()
+    contract_tree_numpy(arrays, td["inputs"], td["output"], td["path"])
+    sec = time.perf_counter() - t0
+    return {"value": 8.0 * st["flops"] / sec / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"numpy restatement of the reference's pairwise tree loop on the whole {rows}x{cols} depth-{depth} "
+                      f"amplitude ({os.path.relpath(path, ROOT)}, 10^{math.log10(st['flops']):.2f} complex MACs, "
+                      f"{sec:.1f} s)"}  # fmt: skip
+
+
 def run_contraction(args: argparse.Namespace) -> None:
     """BASELINE.json configs[4]: one amplitude of the 7x7 depth-20 random circuit as a sliced tensor
     network.  A step contracts `--slices` slices per GPU of the full plan (the full job has
@@ -565,6 +593,9 @@ def run_contraction(args: argparse.Namespace) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_s = float(t[0]), float(t[1])
     ms_per_step = ms_total / args.steps
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_contraction_sample(tc, DistributedContractor, planner)
     tflops = flops_slice * nsl * world / (ms_per_step * 1e-3) / 1e12
     gbs = bytes_slice * nsl / (ms_per_step * 1e-3) / 1e9  # per GPU
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -611,7 +642,7 @@ def run_contraction(args: argparse.Namespace) -> None:
                 "alg_bytes_per_slice": bytes_slice,
                 "plan_bytes_per_slice_unfused": plan_bytes_slice,
             },
-            "cpu_baseline": None,
+            "cpu_baseline": cpu_baseline,
             "e2e": {
                 "value": flops_slice * nsl * world / e2e_s / 1e12,
                 "unit": "TFLOP/s",

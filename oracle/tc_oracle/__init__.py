@@ -11,6 +11,6 @@ tests/test_oracle_golden.py).  Contraction-plan bit-exactness against
 opt_einsum / cotengra is PARITY UNPINNED: those planners are third-party
 packages absent from this image and no reference test fixes a concrete path.
 """
-from . import tn, gates, paths, cons, circuit, quantum  # noqa: F401
+from . import tn, gates, paths, cons, circuit, quantum, treeexec  # noqa: F401
 from .circuit import Circuit  # noqa: F401
 from .cons import set_contractor, runtime_contractor  # noqa: F401

@@ -150,3 +150,29 @@ def test_schedule_fusion_halves_the_traffic_of_the_committed_plan(built):
     s1 = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sl, fuse=True)
     traffic = lambda st: sum(8.0 * (2 ** len(ta) + 2 ** len(tb) + 2 ** len(k)) for _, _, ta, tb, k, _ in st)  # noqa: E731
     assert traffic(s1) < 0.6 * traffic(s0)
+
+
+def test_numpy_tree_executor_matches_oracle_statevector():
+    """oracle/tc_oracle/treeexec.py (the CPU leg of the contraction bench): sliced pairwise execution of a
+    planner tree_data == the oracle statevector's amplitude, hyper-indices and slicing included."""
+    import bench
+    import tc_oracle as otc
+    import tensorcircuit_ng_b200 as tc
+    from tc_oracle.treeexec import contract_tree_numpy
+    from tensorcircuit_ng_b200 import planner
+    from tensorcircuit_ng_b200.experimental import DistributedContractor
+
+    rows, cols, depth = 3, 4, 8
+    bits = "010011010110"
+    nodes_fn = lambda _: bench.build_rcs(tc, rows, cols, depth).amplitude_before(bits)  # noqa: E731
+    inp, out, sd, tensors, groups = DistributedContractor._network(nodes_fn, None, True)
+    td = planner.search_elimination(inp, out, sd, target_size=2**4, groups=groups)
+    assert len(td["sliced_inds"]) >= 1
+    arrs = [t.detach().cpu().numpy() for t in tensors]
+    nsl = int(np.prod([sd[x] for x in td["sliced_inds"]]))
+    val = 0.0
+    for s in range(nsl):
+        fixed = planner.slice_values(s, list(td["sliced_inds"]), td["size_dict"])
+        val = val + contract_tree_numpy(arrs, td["inputs"], td["output"], td["path"], fixed=fixed)
+    ref = bench.build_rcs(otc, rows, cols, depth).wavefunction()[int(bits, 2)]
+    assert abs(complex(val) - complex(ref)) < 1e-6
