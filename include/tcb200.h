@@ -171,6 +171,50 @@ typedef struct tcb_contract_desc {
 int tcb_tn_contract(const void* a, int64_t a_offset, const void* b, int64_t b_offset, void* c,
                     const tcb_contract_desc* desc_host, int accumulate, void* stream);
 
+/* ---- plan objects (plan create / destroy, execute, vjp, workspace_size) ---------------
+ * The host planner (passplan.py / planner.py + tnengine.build_schedule; any producer of the same tables)
+ * lowers a gate stream or a `tree_data` plan (tensorcircuit/experimental.py:947-953) to the tables below;
+ * the library owns the plan from then on and replays it with one call per circuit / per slice — what the
+ * reference's contractor loop does pair by pair in Python (tensorcircuit/cons.py:937-953).
+ *
+ * Statevector plan.  programs_host: all pass programs concatenated (int32 words, copied to the device).
+ * steps: nsteps x 16 int64 = {kind (0 fused pass | 1 dense gate | 2 diagonal gate), program offset,
+ *   program words, tile_bits, low_bits, pool_elems, k, matrix offset in the gate buffer (elements),
+ *   diagonal stride, bitpos[0..6]}.   gates: ngates x 4 int64 = {k (1|2), bitpos0, bitpos1, offset of the
+ *   gate's dense 2^k x 2^k block in the udag / grad buffers (elements)} in program order.
+ * execute: the whole circuit in place on `state`.  vjp: the adjoint walk (tcb_sv_adjoint_step per gate,
+ *   last gate first): psi (final state) is un-computed to the initial state, lam becomes the cotangent of
+ *   the initial state, grad (complex128 pairs, +=) receives dL/dU of every gate.                       */
+typedef struct tcb_sv_plan tcb_sv_plan;
+int tcb_sv_plan_create(int nbits, const int32_t* programs_host, int64_t program_words, const int64_t* steps,
+                       int nsteps, const int64_t* gates, int ngates, tcb_sv_plan** out);
+int tcb_sv_plan_destroy(tcb_sv_plan* plan);
+int64_t tcb_sv_plan_workspace_size(const tcb_sv_plan* plan); /* 0: every step is in place */
+int tcb_sv_plan_execute(const tcb_sv_plan* plan, void* state, int64_t batch, const void* gatebuf,
+                        int64_t gate_batch_stride, uint64_t index_base, void* stream);
+int tcb_sv_plan_vjp(const tcb_sv_plan* plan, void* lam, void* psi, const void* udag, double* grad,
+                    void* stream);
+int tcb_sv_plan_launches(const tcb_sv_plan* plan, int vjp); /* kernels one execute / vjp launches */
+
+/* Tensor-network plan: one contraction tree as an SSA list of pairwise steps.  Ids 0..nleaves-1 are the
+ * input tensors, nleaves+s is the result of step s.  step_ids: nsteps x {a, b, out}; descs[s]: the modes
+ * of step s as bit positions of the (sliced) operands; out_elems[s]: elements of its result.  Slicing:
+ * leaf_slice_counts[l] pairs {sliced index number i, bit position of that index in leaf l} per leaf (all
+ * pairs concatenated in leaf_slice_pairs); execute(slice_bits) reads leaf l at element offset
+ * sum_i ((slice_bits >> i) & 1) << bitpos — no sliced copies (tensorcircuit/experimental.py:999-1009).
+ * Intermediates live in the caller's workspace (liveness-packed at create time); the last step writes
+ * `out` (tcb_tn_plan_output_elems complex64 values).                                                   */
+typedef struct tcb_tn_plan tcb_tn_plan;
+int tcb_tn_plan_create(int nleaves, const int64_t* leaf_elems, int nsteps, const int32_t* step_ids,
+                       const tcb_contract_desc* descs, const int64_t* out_elems, int nsliced,
+                       const int32_t* leaf_slice_counts, const int32_t* leaf_slice_pairs, tcb_tn_plan** out);
+int tcb_tn_plan_destroy(tcb_tn_plan* plan);
+int64_t tcb_tn_plan_workspace_size(const tcb_tn_plan* plan); /* bytes */
+int64_t tcb_tn_plan_output_elems(const tcb_tn_plan* plan);
+int tcb_tn_plan_execute(const tcb_tn_plan* plan, const void* const* inputs, uint64_t slice_bits, void* out,
+                        void* workspace, int64_t ws_bytes, void* stream);
+int tcb_tn_plan_launches(const tcb_tn_plan* plan);
+
 #ifdef __cplusplus
 }
 #endif

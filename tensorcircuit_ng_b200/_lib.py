@@ -119,6 +119,25 @@ SYMBOLS = {
         c_int,
         [c_void_p, c_int64, c_void_p, c_int64, c_void_p, POINTER(ContractDesc), c_int, c_void_p],
     ),
+    "tcb_sv_plan_create": (
+        c_int,
+        [c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, POINTER(c_void_p)],
+    ),
+    "tcb_sv_plan_destroy": (c_int, [c_void_p]),
+    "tcb_sv_plan_workspace_size": (c_int64, [c_void_p]),
+    "tcb_sv_plan_execute": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_uint64, c_void_p]),
+    "tcb_sv_plan_vjp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tcb_sv_plan_launches": (c_int, [c_void_p, c_int]),
+    "tcb_tn_plan_create": (
+        c_int,
+        [c_int, c_void_p, c_int, c_void_p, POINTER(ContractDesc), c_void_p, c_int, c_void_p, c_void_p,
+         POINTER(c_void_p)],
+    ),  # fmt: skip
+    "tcb_tn_plan_destroy": (c_int, [c_void_p]),
+    "tcb_tn_plan_workspace_size": (c_int64, [c_void_p]),
+    "tcb_tn_plan_output_elems": (c_int64, [c_void_p]),
+    "tcb_tn_plan_execute": (c_int, [c_void_p, POINTER(c_void_p), c_uint64, c_void_p, c_void_p, c_int64, c_void_p]),
+    "tcb_tn_plan_launches": (c_int, [c_void_p]),
 }
 
 
