@@ -120,11 +120,9 @@ class _Evolve(torch.autograd.Function):
         src = torch.cat([gatebuf.conj().resolve_conj(), torch.zeros(1, dtype=gatebuf.dtype, device=gatebuf.device)])
         dag = src[tabs.dag_idx].contiguous()  # every U^dagger, dense row-major, in program order
         g_all = torch.zeros(max(tabs.total, 1), 2, dtype=torch.float64, device=gatebuf.device)
-        lp, pp, dp, gp = lam.data_ptr(), psi.data_ptr(), dag.data_ptr(), g_all.data_ptr()
-        stream = _lib.stream_ptr()
-        for k, bp, off in reversed(tabs.items):
-            # psi_in = U^dagger psi_out; dL/dU += lam_out (x) conj(psi_in); lam_in = U^dagger lam_out — one pass
-            _lib.call("tcb_sv_adjoint_step", lp, pp, nbits, 1, bp, k, dp + off * 8, 0, gp + off * 16, 0, stream)
+        # psi_in = U^dagger psi_out; dL/dU += lam_out (x) conj(psi_in); lam_in = U^dagger lam_out — one pass per
+        # gate over both states, the whole walk one call (tcb_sv_plan_vjp)
+        cc.vjp(lam, psi, dag, g_all)
         grad_buf = torch.zeros_like(gatebuf)
         torch.view_as_real(grad_buf).index_add_(0, tabs.scat_dst, g_all[tabs.scat_src].to(torch.float32))
         grad_init = lam if ctx.has_init and ctx.needs_input_grad[1] else None

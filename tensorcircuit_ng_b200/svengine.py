@@ -226,7 +226,72 @@ class CompiledCircuit:
             host = np.concatenate(chunks).astype(np.int32)
             self.programs = torch.from_numpy(host).to(device)
         else:
+            host = np.zeros(0, dtype=np.int32)
             self.programs = torch.zeros(1, dtype=torch.int32, device=device)
+        self._programs_host = host
+        self._handle: Optional[ctypes.c_void_p] = None
+        self.has_vjp = all(g.k <= 2 for g in ops)
+
+    # -- the native plan object (include/tcb200.h: tcb_sv_plan_*) ------------------------------------
+    def handle(self) -> ctypes.c_void_p:
+        """Created on first use: the library copies the pass programs to the device and keeps the step /
+        gate tables, so a circuit execution (or its whole adjoint walk) is ONE call through the C ABI."""
+        if self._handle is not None:
+            return self._handle
+        rows: List[List[int]] = []
+        pi = 0
+        for step in self.plan.steps:
+            if isinstance(step, PassStep):
+                rows.append([0, self.offsets[pi], len(step.program), step.tile_bits, step.low_bits, step.pool_elems,
+                             0, 0, 0] + [0] * 7)  # fmt: skip
+                pi += 1
+            else:
+                g = step.gate
+                bp = list(step.bitpos) + [0] * (7 - len(step.bitpos))
+                if g.is_diag:
+                    stride = 1 if g.kind[0] == "diagvec" else (1 << g.k) + 1
+                    rows.append([2, 0, 0, 0, 0, 0, g.k, g.mat_off, stride] + bp)
+                else:
+                    rows.append([1, 0, 0, 0, 0, 0, g.k, g.mat_off, 0] + bp)
+        steps = np.asarray(rows, dtype=np.int64).reshape(-1, 16) if rows else np.zeros((0, 16), np.int64)
+        grows, off = [], 0
+        if self.has_vjp:
+            nb = self.plan.nbits
+            for g in self.ops:
+                bp = [nb - 1 - q for q in g.qubits]
+                grows.append([g.k, bp[0], bp[1] if g.k > 1 else 0, off])
+                off += (1 << g.k) ** 2
+        gates = np.asarray(grows, dtype=np.int64).reshape(-1, 4) if grows else np.zeros((0, 4), np.int64)
+        h = ctypes.c_void_p()
+        host = np.ascontiguousarray(self._programs_host)
+        _lib.check(_lib.load().tcb_sv_plan_create(
+            self.plan.nbits, host.ctypes.data if len(host) else None, len(host),
+            steps.ctypes.data if len(steps) else None, len(steps),
+            gates.ctypes.data if len(gates) else None, len(gates), ctypes.byref(h)))  # fmt: skip
+        self._handle = h
+        self._n_launch = int(_lib.load().tcb_sv_plan_launches(h, 0))
+        self._n_launch_vjp = int(_lib.load().tcb_sv_plan_launches(h, 1))
+        return h
+
+    def __del__(self) -> None:
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.load().tcb_sv_plan_destroy(h)
+            except Exception:  # pylint: disable=broad-except  (interpreter shutdown)
+                pass
+            self._handle = None
+
+    def vjp(self, lam: torch.Tensor, psi: torch.Tensor, udag: torch.Tensor, grad: torch.Tensor) -> None:
+        """The whole adjoint walk (last gate first) in one call: psi is un-computed in place, lam becomes the
+        cotangent of the initial state, grad (float64 pairs, dense block per gate) accumulates dL/dU."""
+        if not self.has_vjp:
+            k = max(g.k for g in self.ops)
+            raise _lib.EngineError(f"gradient through a {k}-qubit gate is not supported yet (tcb_sv_adjoint_step: k <= 2)")
+        h = self.handle()
+        _lib.check(_lib.load().tcb_sv_plan_vjp(h, lam.data_ptr(), psi.data_ptr(), udag.data_ptr(), grad.data_ptr(),
+                                               _lib.stream_ptr()))  # fmt: skip
+        _lib.launch_count += self._n_launch_vjp
 
     def start(self, state: torch.Tensor, gatebuf: torch.Tensor) -> None:
         """Write the initial state of the compiled part: |0...0>, or the product state that the
@@ -249,6 +314,13 @@ class CompiledCircuit:
         the GPU).  With absorbed leading gates the state must come from `start`."""
         _lib.require_cuda(state, "state")
         _lib.require_cuda(gatebuf, "gate buffer")
+        if use_native_plans:
+            h = self.handle()
+            _lib.check(_lib.load().tcb_sv_plan_execute(h, state.data_ptr(), batch, gatebuf.data_ptr(),
+                                                       gate_batch_stride, index_base, _lib.stream_ptr()))  # fmt: skip
+            _lib.launch_count += self._n_launch
+            return
+        # step by step through the kernel-level entry points (TCB_NATIVE_PLANS=0; same launches)
         nbits = self.plan.nbits
         stream = _lib.stream_ptr()
         sp = state.data_ptr()
@@ -274,6 +346,8 @@ class CompiledCircuit:
 
 _plan_cache: Dict[Any, CompiledCircuit] = {}
 import os as _os
+
+use_native_plans = _os.environ.get("TCB_NATIVE_PLANS", "1") != "0"
 
 plan_options: Dict[str, Any] = {
     "tile_bits": int(_os.environ.get("TCB_TILE_BITS", "12")),

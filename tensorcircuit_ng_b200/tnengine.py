@@ -57,34 +57,21 @@ def _physical(t: torch.Tensor) -> Tuple[torch.Tensor, List[int], int, int]:
     return t, pos, conj, 0
 
 
-def contract_raw(a: torch.Tensor, modes_a: Sequence[Mode], b: torch.Tensor, modes_b: Sequence[Mode],
-                 modes_out: Sequence[Mode], conj_a: bool = False, conj_b: bool = False,
-                 fixed: Optional[Dict[Mode, int]] = None, out: Optional[torch.Tensor] = None,
-                 accumulate: bool = False) -> torch.Tensor:  # fmt: skip
-    """out[modes_out] (+)= sum over shared non-output modes of a[modes_a] * b[modes_b].
-
-    `fixed` pins modes to a value (slicing, K7): a pinned mode is neither summed nor output.
-    No autograd; see `contract` for the differentiable entry point.
-    """
-    fixed = fixed or {}
-    # the larger free side becomes the row side (A): streaming / 128-row tiles run along it
+def row_side_first(modes_a: Sequence[Mode], modes_b: Sequence[Mode], modes_out: Sequence[Mode]) -> bool:
+    """True when (a, b) may stay in this order: the larger free side is the row side (A) — streaming and the
+    128-row tensor-core tiles run along it."""
     out_set = set(modes_out)
     free_a = sum(1 for m in modes_a if m in out_set and m not in modes_b)
     free_b = sum(1 for m in modes_b if m in out_set and m not in modes_a)
-    if free_b > free_a:
-        a, b, modes_a, modes_b, conj_a, conj_b = b, a, modes_b, modes_a, conj_b, conj_a
-    a, pos_a, cja, _ = _physical(a)
-    b, pos_b, cjb, _ = _physical(b)
-    _lib.require_cuda(a, "left operand")
-    _lib.require_cuda(b, "right operand")
-    pa = dict(zip(modes_a, pos_a))
-    pb = dict(zip(modes_b, pos_b))
-    if len(pa) != len(modes_a) or len(pb) != len(modes_b):
-        raise _lib.EngineError("repeated mode inside one operand (trace) is not a pairwise contraction")
+    return free_b <= free_a
+
+
+def make_desc(pa: Dict[Mode, int], pb: Dict[Mode, int], modes_a: Sequence[Mode], modes_b: Sequence[Mode],
+              modes_out: Sequence[Mode], fixed: Any, conj_a: bool, conj_b: bool) -> "_lib.ContractDesc":  # fmt: skip
+    """The `tcb_contract_desc` of one pairwise step from the bit position of every mode in the two operands
+    (`pa`, `pb`); the result is contiguous in `modes_out` order; modes in `fixed` are sliced (skipped)."""
     n_out = len(modes_out)
     pc = {m: n_out - 1 - i for i, m in enumerate(modes_out)}
-    a_off = sum(fixed[m] << p for m, p in pa.items() if m in fixed)
-    b_off = sum(fixed[m] << p for m, p in pb.items() if m in fixed)
     d = _lib.ContractDesc()
     lists: Dict[str, List[int]] = {k: [] for k in ("batch_a", "batch_b", "batch_c", "m_a", "m_c", "n_b", "n_c", "k_a", "k_b")}
     for m in modes_out:
@@ -128,8 +115,36 @@ def contract_raw(a: torch.Tensor, modes_a: Sequence[Mode], b: torch.Tensor, mode
         for i, x in enumerate(v):
             arr[i] = x
     d.n_batch, d.n_m, d.n_n, d.n_k = len(lists["batch_c"]), len(lists["m_c"]), len(lists["n_c"]), len(lists["k_a"])
-    d.conj_a = int(bool(conj_a) ^ bool(cja))
-    d.conj_b = int(bool(conj_b) ^ bool(cjb))
+    d.conj_a = int(bool(conj_a))
+    d.conj_b = int(bool(conj_b))
+    return d
+
+
+def contract_raw(a: torch.Tensor, modes_a: Sequence[Mode], b: torch.Tensor, modes_b: Sequence[Mode],
+                 modes_out: Sequence[Mode], conj_a: bool = False, conj_b: bool = False,
+                 fixed: Optional[Dict[Mode, int]] = None, out: Optional[torch.Tensor] = None,
+                 accumulate: bool = False) -> torch.Tensor:  # fmt: skip
+    """out[modes_out] (+)= sum over shared non-output modes of a[modes_a] * b[modes_b].
+
+    `fixed` pins modes to a value (slicing, K7): a pinned mode is neither summed nor output.
+    No autograd; see `contract` for the differentiable entry point.
+    """
+    fixed = fixed or {}
+    # the larger free side becomes the row side (A): streaming / 128-row tiles run along it
+    if not row_side_first(modes_a, modes_b, modes_out):
+        a, b, modes_a, modes_b, conj_a, conj_b = b, a, modes_b, modes_a, conj_b, conj_a
+    a, pos_a, cja, _ = _physical(a)
+    b, pos_b, cjb, _ = _physical(b)
+    _lib.require_cuda(a, "left operand")
+    _lib.require_cuda(b, "right operand")
+    pa = dict(zip(modes_a, pos_a))
+    pb = dict(zip(modes_b, pos_b))
+    if len(pa) != len(modes_a) or len(pb) != len(modes_b):
+        raise _lib.EngineError("repeated mode inside one operand (trace) is not a pairwise contraction")
+    n_out = len(modes_out)
+    a_off = sum(fixed[m] << p for m, p in pa.items() if m in fixed)
+    b_off = sum(fixed[m] << p for m, p in pb.items() if m in fixed)
+    d = make_desc(pa, pb, modes_a, modes_b, modes_out, fixed, bool(conj_a) ^ bool(cja), bool(conj_b) ^ bool(cjb))
     if out is None:
         out = torch.empty([2] * n_out, dtype=torch.complex64, device=a.device)
         accumulate = False
@@ -363,6 +378,9 @@ def contract_tree(arrays: Sequence[torch.Tensor], inputs: Sequence[Sequence[str]
     `build_schedule` (cached; skinny absorption chains fused).
     """
     fixed = dict(fixed or {})
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in arrays)
+    if use_native_plans and len(arrays) > 1 and not needs_grad and len(fixed) <= 62:
+        return tree_plan(inputs, output, path, sorted(fixed)).execute(arrays, fixed)
     tens: Dict[int, torch.Tensor] = {}
     for i, (t, modes) in enumerate(zip(arrays, inputs)):
         if fixed:
@@ -381,3 +399,119 @@ def contract_tree(arrays: Sequence[torch.Tensor], inputs: Sequence[Sequence[str]
         tens[o] = r
     assert r is not None
     return r
+
+
+# ------------------------------------------------------------------------------------------------
+class TreePlan:
+    """One contraction tree as a native plan object (`tcb_tn_plan_*`, include/tcb200.h): the SSA schedule,
+    every step's descriptor, a liveness-packed workspace layout and the slice-offset tables of the leaves
+    are fixed once; `execute` is ONE C call per slice (no per-step Python, no per-step allocation).
+    Forward only — differentiated contractions go through `contract_tree`'s autograd steps."""
+
+    def __init__(self, inputs: Sequence[Sequence[str]], output: Sequence[str], path: Sequence[Tuple[int, ...]],
+                 sliced: Sequence[str] = ()) -> None:  # fmt: skip
+        import ctypes
+
+        self.sliced = sorted(sliced)
+        if len(self.sliced) > 62:
+            raise _lib.EngineError("TreePlan: more than 62 sliced indices")
+        sl = set(self.sliced)
+        steps = build_schedule(inputs, output, path, self.sliced)
+        n = len(inputs)
+        self.nleaves = n
+        self.output = list(output)
+        # layouts: leaves are contiguous [2]*rank arrays of ALL their modes; intermediates contiguous in `keep` order
+        layout: Dict[int, Dict[str, int]] = {}
+        counts, pairs = [], []
+        for i, t in enumerate(inputs):
+            r = len(t)
+            if len(set(t)) != r:
+                raise _lib.EngineError("TreePlan: repeated index inside one tensor")
+            layout[i] = {m: r - 1 - ax for ax, m in enumerate(t)}
+            mine = [(self.sliced.index(m), layout[i][m]) for m in t if m in sl]
+            counts.append(len(mine))
+            pairs.extend(mine)
+        remap = {i: i for i in range(n)}
+        ids, descs, out_elems = [], [], []
+        for k, (a, b, ta, tb, keep, o) in enumerate(steps):
+            if not row_side_first(ta, tb, keep):
+                a, b, ta, tb = b, a, tb, ta
+            descs.append(make_desc(layout[a], layout[b], ta, tb, keep, sl, False, False))
+            remap[o] = n + k
+            ids.extend((remap[a], remap[b], n + k))
+            layout[o] = {m: len(keep) - 1 - ax for ax, m in enumerate(keep)}
+            out_elems.append(1 << len(keep))
+        self.nsteps = len(steps)
+        if self.nsteps == 0:
+            raise _lib.EngineError("TreePlan needs at least one pairwise step")
+        arr_desc = (_lib.ContractDesc * self.nsteps)(*descs)
+        leaf_elems = (ctypes.c_int64 * n)(*[1 << len(t) for t in inputs])
+        step_ids = (ctypes.c_int32 * len(ids))(*ids)
+        oe = (ctypes.c_int64 * self.nsteps)(*out_elems)
+        cnt = (ctypes.c_int32 * n)(*counts)
+        flat = [x for pr in pairs for x in pr]
+        prs = (ctypes.c_int32 * max(1, len(flat)))(*flat)
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.load().tcb_tn_plan_create(n, leaf_elems, self.nsteps, step_ids, arr_desc, oe, len(self.sliced),
+                                                  cnt, prs, ctypes.byref(handle)))  # fmt: skip
+        self._handle = handle
+        self.ws_bytes = int(_lib.load().tcb_tn_plan_workspace_size(handle))
+        self._ws: Dict[str, torch.Tensor] = {}
+
+    def __del__(self) -> None:
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.load().tcb_tn_plan_destroy(h)
+            except Exception:  # pylint: disable=broad-except  (interpreter shutdown)
+                pass
+            self._handle = None
+
+    def execute(self, arrays: Sequence[torch.Tensor], fixed: Optional[Dict[str, int]] = None) -> torch.Tensor:
+        import ctypes
+
+        fixed = fixed or {}
+        if sorted(fixed) != self.sliced:
+            raise _lib.EngineError("TreePlan.execute: the pinned indices differ from the plan's sliced indices")
+        if len(arrays) != self.nleaves:
+            raise _lib.EngineError("TreePlan.execute: wrong number of input tensors")
+        keep = []  # (keeps converted leaves alive until the launches are queued)
+        ptrs = (ctypes.c_void_p * self.nleaves)()
+        dev = None
+        for i, t in enumerate(arrays):
+            if t.dtype != torch.complex64 or t.is_conj() or not t.is_contiguous():
+                t = t.to(torch.complex64).resolve_conj().contiguous()
+            _lib.require_cuda(t, "input tensor")
+            keep.append(t)
+            ptrs[i] = t.data_ptr()
+            dev = t.device
+        ws = self._ws.get(str(dev))
+        if ws is None:
+            ws = torch.empty(max(1, self.ws_bytes // 8), dtype=torch.complex64, device=dev)
+            self._ws[str(dev)] = ws
+        out = torch.empty([2] * len(self.output), dtype=torch.complex64, device=dev)
+        bits = 0
+        for i, m in enumerate(self.sliced):
+            bits |= (int(fixed[m]) & 1) << i
+        lib = _lib.load()
+        _lib.check(lib.tcb_tn_plan_execute(self._handle, ptrs, bits, out.data_ptr(), ws.data_ptr(), self.ws_bytes,
+                                           _lib.stream_ptr()))  # fmt: skip
+        _lib.launch_count += self.nsteps
+        return out
+
+
+_tree_plans: Dict[Any, TreePlan] = {}
+use_native_plans = True
+
+
+def tree_plan(inputs: Sequence[Sequence[str]], output: Sequence[str], path: Sequence[Tuple[int, ...]],
+              sliced: Sequence[str] = ()) -> TreePlan:  # fmt: skip
+    key = (tuple(tuple(t) for t in inputs), tuple(output), tuple(tuple(p) for p in path), tuple(sorted(sliced)),
+           fuse_skinny_chains)  # fmt: skip
+    tp = _tree_plans.get(key)
+    if tp is None:
+        tp = TreePlan(inputs, output, path, sliced)
+        if len(_tree_plans) > 16:
+            _tree_plans.clear()
+        _tree_plans[key] = tp
+    return tp

@@ -1,0 +1,148 @@
+"""The plan objects of the C ABI (include/tcb200.h `tcb_sv_plan_*`, `tcb_tn_plan_*`; SURVEY §8b export list).
+CPU tier: creation / validation / workspace packing of tensor-network plans (no device needed).
+GPU tier: plan execution == the step-by-step executors == the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import tc_oracle as otc
+
+
+def _tree(rows, cols, depth, bits, target):
+    import bench
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import planner
+    from tensorcircuit_ng_b200.experimental import DistributedContractor
+
+    nodes_fn = lambda _: bench.build_rcs(tc, rows, cols, depth).amplitude_before(bits)  # noqa: E731
+    inp, out, sd, tensors, groups = DistributedContractor._network(nodes_fn, None, True)
+    td = planner.search_elimination(inp, out, sd, target_size=target, groups=groups)
+    return td, tensors, sd
+
+
+def test_tn_plan_create_workspace_and_validation(built):
+    from tensorcircuit_ng_b200 import _lib, tnengine
+
+    td, _, _ = _tree(3, 4, 8, "0" * 12, 2**4)
+    assert len(td["sliced_inds"]) >= 1
+    tp = tnengine.TreePlan(td["inputs"], td["output"], td["path"], list(td["sliced_inds"]))
+    steps = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sorted(td["sliced_inds"]))
+    assert tp.nsteps == len(steps) == int(_lib.load().tcb_tn_plan_launches(tp._handle))
+    assert int(_lib.load().tcb_tn_plan_output_elems(tp._handle)) == 1
+    # liveness packing: the workspace is far smaller than the sum of all intermediates, and at least as large
+    # as the biggest one
+    td2, _, _ = _tree(4, 5, 8, "0" * 20, 2**12)
+    tp2 = tnengine.TreePlan(td2["inputs"], td2["output"], td2["path"], list(td2["sliced_inds"]))
+    steps2 = tnengine.build_schedule(td2["inputs"], td2["output"], td2["path"], sorted(td2["sliced_inds"]))
+    sizes = [8 * 2 ** len(keep) for *_, keep, _ in steps2[:-1]]
+    assert max(sizes) <= tp2.ws_bytes < 0.6 * sum(max(256, x) for x in sizes)
+    # malformed SSA tables are rejected with a message, not executed
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    leaf = (ctypes.c_int64 * 2)(2, 2)
+    ids = (ctypes.c_int32 * 3)(0, 0, 2)  # a == b
+    d = (_lib.ContractDesc * 1)()
+    oe = (ctypes.c_int64 * 1)(1)
+    rc = lib.tcb_tn_plan_create(2, leaf, 1, ids, d, oe, 0, None, None, ctypes.byref(h))
+    assert rc != 0 and b"not a valid SSA step" in lib.tcb_last_error()
+    ids = (ctypes.c_int32 * 3)(0, 1, 1)  # writes over a leaf
+    assert lib.tcb_tn_plan_create(2, leaf, 1, ids, d, oe, 0, None, None, ctypes.byref(h)) != 0
+    assert lib.tcb_tn_plan_workspace_size(None) == 0 and lib.tcb_tn_plan_destroy(None) == 0
+    assert lib.tcb_sv_plan_workspace_size(None) == 0 and lib.tcb_sv_plan_destroy(None) == 0
+    # a statevector plan with no device programs can be created and destroyed without a GPU
+    gates = np.array([[1, 0, 0, 0], [2, 1, 0, 4]], dtype=np.int64)
+    assert lib.tcb_sv_plan_create(3, None, 0, None, 0, gates.ctypes.data, 2, ctypes.byref(h)) == 0
+    assert lib.tcb_sv_plan_launches(h, 1) == 2 and lib.tcb_sv_plan_launches(h, 0) == 0
+    assert lib.tcb_sv_plan_destroy(h) == 0
+    bad = np.array([[3, 0, 0, 0]], dtype=np.int64)
+    assert lib.tcb_sv_plan_create(3, None, 0, None, 0, bad.ctypes.data, 1, ctypes.byref(h)) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,depth,target", [(3, 3, 6, 2**3), (3, 4, 8, 2**4), (4, 4, 8, 2**6), (4, 5, 6, 2**8)])
+def test_gpu_tn_plan_matches_stepwise_executor_and_oracle(cuda, rows, cols, depth, target):
+    import bench
+    import torch
+
+    from tensorcircuit_ng_b200 import planner, tnengine
+
+    n = rows * cols
+    bits = "".join(str(int(b)) for b in np.random.default_rng(n).integers(0, 2, n))
+    td, tensors, sd = _tree(rows, cols, depth, bits, target)
+    sliced = list(td["sliced_inds"])
+    nsl = int(np.prod([sd[x] for x in sliced])) if sliced else 1
+    native = stepwise = 0.0
+    with torch.no_grad():
+        for s in range(nsl):
+            fixed = planner.slice_values(s, sliced, td["size_dict"]) if sliced else None
+            tnengine.use_native_plans = True
+            a = tnengine.contract_tree(tensors, td["inputs"], td["output"], td["path"], fixed=fixed)
+            tnengine.use_native_plans = False
+            try:
+                b = tnengine.contract_tree(tensors, td["inputs"], td["output"], td["path"], fixed=fixed)
+            finally:
+                tnengine.use_native_plans = True
+            assert abs(complex(a.cpu()) - complex(b.cpu())) <= 1e-7 + 1e-5 * abs(complex(b.cpu()))
+            native, stepwise = native + complex(a.cpu()), stepwise + complex(b.cpu())
+    ref = bench.build_rcs(otc, rows, cols, depth).wavefunction()[int(bits, 2)]
+    assert abs(native - complex(ref)) < 2e-6
+
+
+@pytest.mark.gpu
+def test_gpu_sv_plan_execute_and_vjp_match_per_step_calls(cuda):
+    """tcb_sv_plan_execute == the per-pass calls; tcb_sv_plan_vjp == the per-gate adjoint steps."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import _lib, svengine
+    from tensorcircuit_ng_b200.passplan import PassStep
+
+    n = 14
+    rng = np.random.default_rng(4)
+    c = tc.Circuit(n)
+    for q in range(n):
+        c.h(q)
+    for l in range(3):
+        for q in range(n - 1):
+            c.rzz(q, q + 1, theta=float(rng.uniform(0, 3)))
+        for q in range(n):
+            c.rx(q, theta=float(rng.uniform(0, 3)))
+        c.cnot(0, n - 1)
+    nodes, edges = c._copy()
+    nn, init, gates = svengine.extract_gate_stream(nodes, edges)
+    structure = [(g[1], svengine.gate_kind(g[0], g[2]), int(g[0].tensor.numel())) for g in gates]
+    cc = svengine.compile_circuit(nn, structure, torch.device("cuda:0"), absorb_prefix=False)
+    gatebuf = svengine.assemble_gatebuf([g[0] for g in gates], torch.device("cuda:0"))
+    s1 = svengine.new_zero_state(n, 1, torch.device("cuda:0"))
+    cc.run(s1, gatebuf)  # native plan
+    s2 = svengine.new_zero_state(n, 1, torch.device("cuda:0"))
+    pi = 0
+    for step in cc.plan.steps:  # the same passes, one C call each
+        assert isinstance(step, PassStep)
+        _lib.call("tcb_sv_run_pass", s2.data_ptr(), n, 1, cc.programs.data_ptr() + 4 * cc.offsets[pi], len(step.program),
+                  step.tile_bits, step.low_bits, step.pool_elems, gatebuf.data_ptr(), 0, 0, _lib.stream_ptr())  # fmt: skip
+        pi += 1
+    assert torch.equal(s1, s2)
+    want = c.wavefunction()
+    assert float((s1 - want.reshape(-1)).abs().max()) < 1e-6
+    # vjp: plan walk vs explicit adjoint steps
+    from tensorcircuit_ng_b200 import autograd
+
+    tabs = autograd._adjoint_tables(cc, gatebuf)
+    src = torch.cat([gatebuf.conj().resolve_conj(), torch.zeros(1, dtype=gatebuf.dtype, device=gatebuf.device)])
+    dag = src[tabs.dag_idx].contiguous()
+    lam0 = torch.view_as_complex(torch.randn(1 << n, 2, device="cuda"))
+    g1 = torch.zeros(tabs.total, 2, dtype=torch.float64, device="cuda")
+    lam1, psi1 = lam0.clone(), s1.clone()
+    cc.vjp(lam1, psi1, dag, g1)
+    g2 = torch.zeros_like(g1)
+    lam2, psi2 = lam0.clone(), s1.clone()
+    for k, bp, off in reversed(tabs.items):
+        _lib.call("tcb_sv_adjoint_step", lam2.data_ptr(), psi2.data_ptr(), n, 1, bp, k, dag.data_ptr() + off * 8, 0,
+                  g2.data_ptr() + off * 16, 0, _lib.stream_ptr())  # fmt: skip
+    assert torch.equal(lam1, lam2) and torch.equal(psi1, psi2)
+    assert float((g1 - g2).abs().max()) <= 1e-9 * float(g2.abs().max())
+    zero = torch.zeros(1 << n, dtype=torch.complex64, device="cuda")
+    zero[0] = 1
+    assert float((psi1 - zero).abs().max()) < 1e-5  # the walk un-computes the state back to |0...0>
