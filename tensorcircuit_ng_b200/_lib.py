@@ -24,7 +24,7 @@ from ctypes import (
 from typing import Any, Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtcb200.so")
+LIB_PATH = os.environ.get("TCB_LIB_PATH") or os.path.join(_HERE, "lib", "libtcb200.so")
 
 _lib: Optional[ctypes.CDLL] = None
 

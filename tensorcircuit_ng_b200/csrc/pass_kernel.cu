@@ -284,7 +284,11 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
 
 template <int LT>
 static int launch_pass_lt(const PassArgs& a, uint64_t tiles_total, size_t smem, cudaStream_t stream) {
+#ifdef TCB_PASS_MINB  // (experiments: another CTAs-per-SM / registers-per-thread trade for every tile size)
+  constexpr int MINB = TCB_PASS_MINB;
+#else
   constexpr int MINB = (512 >> LT) < 1 ? 1 : ((512 >> LT) > 8 ? 8 : (512 >> LT));  // <= 128 registers / thread
+#endif
   static bool attr_set = false;
   if (!attr_set) {
     TCB_CHECK_CUDA(cudaFuncSetAttribute(pass_kernel<PASS_R, LT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
