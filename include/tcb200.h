@@ -180,11 +180,12 @@ int tcb_tn_contract(const void* a, int64_t a_offset, const void* b, int64_t b_of
  * Statevector plan.  programs_host: all pass programs concatenated (int32 words, copied to the device).
  * steps: nsteps x 16 int64 = {kind (0 fused pass | 1 dense gate | 2 diagonal gate), program offset,
  *   program words, tile_bits, low_bits, pool_elems, k, matrix offset in the gate buffer (elements),
- *   diagonal stride, bitpos[0..6]}.   gates: ngates x 4 int64 = {k (1|2), bitpos0, bitpos1, offset of the
- *   gate's dense 2^k x 2^k block in the udag / grad buffers (elements)} in program order.
- * execute: the whole circuit in place on `state`.  vjp: the adjoint walk (tcb_sv_adjoint_step per gate,
- *   last gate first): psi (final state) is un-computed to the initial state, lam becomes the cotangent of
- *   the initial state, grad (complex128 pairs, +=) receives dL/dU of every gate.                       */
+ *   diagonal stride, bitpos[0..6]}.   gates: ngates x 10 int64 = {k (1..7), offset of the gate's dense
+ *   2^k x 2^k block in the udag / grad buffers (elements), bitpos[0..6], 0} in program order.
+ * execute: the whole circuit in place on `state`.  vjp: the adjoint walk, last gate first
+ *   (tcb_sv_adjoint_step per 1- / 2-qubit gate; wider gates are constants: U^dagger on both states, no
+ *   gradient): psi (final state) is un-computed to the initial state, lam becomes the cotangent of the
+ *   initial state, grad (complex128 pairs, +=) receives dL/dU of every 1- / 2-qubit gate.              */
 typedef struct tcb_sv_plan tcb_sv_plan;
 int tcb_sv_plan_create(int nbits, const int32_t* programs_host, int64_t program_words, const int64_t* steps,
                        int nsteps, const int64_t* gates, int ngates, tcb_sv_plan** out);

@@ -67,22 +67,20 @@ class _AdjointTables:
         self.items: List[Any] = []  # (k, bit positions, dense offset) in program order
         for op in cc.ops:
             d = 1 << op.k
-            if op.k > 2:
-                raise _lib.EngineError(
-                    f"gradient through a {op.k}-qubit gate is not supported yet (tcb_sv_gate_grad: k <= 2)"
-                )
+            wide = op.k > 2  # constants (toffoli, fredkin ...): un-applied on both states, no gradient block
             off = len(dag_idx)
             for r in range(d):
                 for c in range(d):
                     if op.kind[0] == "diagvec":  # U^dagger[r, c] = conj(v[r]) on the diagonal, else the zero sentinel
                         dag_idx.append(op.mat_off + r if r == c else nelem)
-                        if r == c:
+                        if r == c and not wide:
                             scat_src.append(off + r * d + c)
                             scat_dst.append(op.mat_off + r)
                     else:  # U^dagger[r, c] = conj(U[c, r])
                         dag_idx.append(op.mat_off + c * d + r)
-                        scat_src.append(off + r * d + c)
-                        scat_dst.append(op.mat_off + r * d + c)
+                        if not wide:
+                            scat_src.append(off + r * d + c)
+                            scat_dst.append(op.mat_off + r * d + c)
             self.items.append((op.k, _lib.int_array([nq - 1 - q for q in op.qubits]), off))
         self.total = len(dag_idx)
         self.dag_idx = torch.tensor(dag_idx, dtype=torch.long, device=device)

@@ -44,7 +44,7 @@ struct tcb_sv_plan {
   };
   struct Gate {
     int k;
-    int bitpos[2];
+    int bitpos[8];
     int64_t dense_off;
   };
   std::vector<Step> steps;
@@ -100,11 +100,15 @@ int tcb_sv_plan_create(int nbits, const int32_t* programs_host, int64_t program_
     p->steps.push_back(s);
   }
   for (int i = 0; i < ngates; ++i) {
-    const int64_t* r = gates + 4 * (size_t)i;
-    tcb_sv_plan::Gate g{(int)r[0], {(int)r[1], (int)r[2]}, r[3]};
-    if (g.k < 1 || g.k > 2 || g.dense_off < 0) {
+    const int64_t* r = gates + 10 * (size_t)i;
+    tcb_sv_plan::Gate g;
+    g.k = (int)r[0];
+    g.dense_off = r[1];
+    for (int j = 0; j < 7; ++j) g.bitpos[j] = (int)r[2 + j];
+    g.bitpos[7] = 0;
+    if (g.k < 1 || g.k > 7 || g.dense_off < 0) {
       delete p;
-      TCB_REQUIRE(false, "tcb_sv_plan_create: gate %d has k=%d (the adjoint walk supports k = 1, 2)", i, g.k);
+      TCB_REQUIRE(false, "tcb_sv_plan_create: gate %d has k=%d (1..7)", i, g.k);
     }
     p->gates.push_back(g);
   }
@@ -165,15 +169,25 @@ int tcb_sv_plan_vjp(const tcb_sv_plan* plan, void* lam, void* psi, const void* u
   NOTNULL(grad, "tcb_sv_plan_vjp");
   const char* ud = reinterpret_cast<const char*>(udag);
   for (auto it = plan->gates.rbegin(); it != plan->gates.rend(); ++it) {
-    const int rc = launch_adjoint_step(lam, psi, plan->nbits, 1, it->bitpos, it->k, ud + 8 * it->dense_off, 0,
-                                       grad + 2 * it->dense_off, 0, S(stream));
+    int rc;
+    if (it->k <= 2) {
+      rc = launch_adjoint_step(lam, psi, plan->nbits, 1, it->bitpos, it->k, ud + 8 * it->dense_off, 0,
+                               grad + 2 * it->dense_off, 0, S(stream));
+    } else {  // a constant multi-qubit gate (toffoli, fredkin ...): un-apply it on both states, no gradient
+      rc = launch_dense(psi, plan->nbits, 1, it->bitpos, it->k, ud + 8 * it->dense_off, 0, S(stream));
+      if (!rc) rc = launch_dense(lam, plan->nbits, 1, it->bitpos, it->k, ud + 8 * it->dense_off, 0, S(stream));
+    }
     if (rc) return rc;
   }
   return 0;
 }
 
 int tcb_sv_plan_launches(const tcb_sv_plan* plan, int vjp) {
-  return plan ? (int)(vjp ? plan->gates.size() : plan->steps.size()) : 0;
+  if (!plan) return 0;
+  if (!vjp) return (int)plan->steps.size();
+  int n = 0;
+  for (const auto& g : plan->gates) n += g.k <= 2 ? 1 : 2;
+  return n;
 }
 
 // ---- tensor-network plans ---------------------------------------------------------------------------

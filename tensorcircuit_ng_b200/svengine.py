@@ -230,7 +230,7 @@ class CompiledCircuit:
             self.programs = torch.zeros(1, dtype=torch.int32, device=device)
         self._programs_host = host
         self._handle: Optional[ctypes.c_void_p] = None
-        self.has_vjp = all(g.k <= 2 for g in ops)
+        self.has_vjp = all(g.k <= 7 for g in ops)
 
     # -- the native plan object (include/tcb200.h: tcb_sv_plan_*) ------------------------------------
     def handle(self) -> ctypes.c_void_p:
@@ -259,9 +259,9 @@ class CompiledCircuit:
             nb = self.plan.nbits
             for g in self.ops:
                 bp = [nb - 1 - q for q in g.qubits]
-                grows.append([g.k, bp[0], bp[1] if g.k > 1 else 0, off])
+                grows.append([g.k, off] + bp + [0] * (8 - len(bp)))
                 off += (1 << g.k) ** 2
-        gates = np.asarray(grows, dtype=np.int64).reshape(-1, 4) if grows else np.zeros((0, 4), np.int64)
+        gates = np.asarray(grows, dtype=np.int64).reshape(-1, 10) if grows else np.zeros((0, 10), np.int64)
         h = ctypes.c_void_p()
         host = np.ascontiguousarray(self._programs_host)
         _lib.check(_lib.load().tcb_sv_plan_create(
@@ -287,7 +287,7 @@ class CompiledCircuit:
         cotangent of the initial state, grad (float64 pairs, dense block per gate) accumulates dL/dU."""
         if not self.has_vjp:
             k = max(g.k for g in self.ops)
-            raise _lib.EngineError(f"gradient through a {k}-qubit gate is not supported yet (tcb_sv_adjoint_step: k <= 2)")
+            raise _lib.EngineError(f"the adjoint walk supports gates of up to 7 qubits (found {k})")
         h = self.handle()
         _lib.check(_lib.load().tcb_sv_plan_vjp(h, lam.data_ptr(), psi.data_ptr(), udag.data_ptr(), grad.data_ptr(),
                                                _lib.stream_ptr()))  # fmt: skip
@@ -461,6 +461,13 @@ def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) 
     device = pick_device(probe + ([init_node.tensor] if init_node is not None else []))
     structure = [(g[1], gate_kind(g[0], g[2]), int(math.prod(g[0].shape))) for g in gates]
     cc = compile_circuit(n, structure, device, absorb_prefix=init_node is None)
+    if torch.is_grad_enabled():
+        for g in gates:
+            if len(g[1]) > 2 and not (hasattr(g[0], "pending") and g[0].pending()) and g[0].tensor.requires_grad:
+                raise _lib.EngineError(
+                    f"gradient with respect to a {len(g[1])}-qubit gate matrix is not supported (the adjoint walk "
+                    "differentiates 1- and 2-qubit gates; wider gates must be constants)"
+                )
     gatebuf = assemble_gatebuf([g[0] for g in gates], device)
     init = None
     if init_node is not None:

@@ -51,11 +51,12 @@ def test_tn_plan_create_workspace_and_validation(built):
     assert lib.tcb_tn_plan_workspace_size(None) == 0 and lib.tcb_tn_plan_destroy(None) == 0
     assert lib.tcb_sv_plan_workspace_size(None) == 0 and lib.tcb_sv_plan_destroy(None) == 0
     # a statevector plan with no device programs can be created and destroyed without a GPU
-    gates = np.array([[1, 0, 0, 0], [2, 1, 0, 4]], dtype=np.int64)
-    assert lib.tcb_sv_plan_create(3, None, 0, None, 0, gates.ctypes.data, 2, ctypes.byref(h)) == 0
-    assert lib.tcb_sv_plan_launches(h, 1) == 2 and lib.tcb_sv_plan_launches(h, 0) == 0
+    gates = np.array([[1, 0, 0, 0, 0, 0, 0, 0, 0, 0], [2, 4, 1, 0, 0, 0, 0, 0, 0, 0], [3, 20, 2, 1, 0, 0, 0, 0, 0, 0]],
+                     dtype=np.int64)  # fmt: skip
+    assert lib.tcb_sv_plan_create(3, None, 0, None, 0, gates.ctypes.data, 3, ctypes.byref(h)) == 0
+    assert lib.tcb_sv_plan_launches(h, 1) == 4 and lib.tcb_sv_plan_launches(h, 0) == 0  # a 3-qubit gate: 2 launches
     assert lib.tcb_sv_plan_destroy(h) == 0
-    bad = np.array([[3, 0, 0, 0]], dtype=np.int64)
+    bad = np.array([[8, 0, 0, 0, 0, 0, 0, 0, 0, 0]], dtype=np.int64)
     assert lib.tcb_sv_plan_create(3, None, 0, None, 0, bad.ctypes.data, 1, ctypes.byref(h)) != 0
 
 
@@ -146,3 +147,48 @@ def test_gpu_sv_plan_execute_and_vjp_match_per_step_calls(cuda):
     zero = torch.zeros(1 << n, dtype=torch.complex64, device="cuda")
     zero[0] = 1
     assert float((psi1 - zero).abs().max()) < 1e-5  # the walk un-computes the state back to |0...0>
+
+
+@pytest.mark.gpu
+def test_gpu_gradient_through_constant_three_qubit_gates(cuda):
+    """toffoli / fredkin inside a differentiated circuit: un-applied as constants by the adjoint walk; a
+    trainable 3-qubit matrix is refused with a message."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+
+    n = 5
+
+    def energy(mod, p, real):
+        c = mod.Circuit(n)
+        for q in range(n):
+            c.h(q)
+        for q in range(n):
+            c.rx(q, theta=p[q])
+        c.toffoli(0, 1, 2)
+        for q in range(n - 1):
+            c.rzz(q, q + 1, theta=p[n + q])
+        c.fredkin(4, 2, 3)
+        for q in range(n):
+            c.ry(q, theta=p[2 * n - 1 + q])
+        return real(c.expectation_ps(z=[0, 3])) + real(c.expectation_ps(x=[2]))
+
+    p0 = np.linspace(0.2, 1.7, 3 * n - 1)
+    v, g = tc.backend.value_and_grad(lambda p: energy(tc, p, torch.real))(torch.tensor(p0, dtype=torch.float32))
+    f = lambda x: float(energy(otc, x, np.real))
+    assert abs(float(v) - f(p0)) < 1e-5
+    for k in (0, 3, n + 1, 2 * n + 2):
+        xp, xm = p0.copy(), p0.copy()
+        xp[k] += 1e-2
+        xm[k] -= 1e-2
+        assert abs(float(g[k]) - (f(xp) - f(xm)) / 2e-2) < 5e-3
+    w = torch.eye(8, dtype=torch.complex64, device="cuda").requires_grad_(True)
+
+    def bad(u):
+        c = tc.Circuit(3)
+        c.h(0)
+        c.any(0, 1, 2, unitary=u)
+        return c.expectation_ps(z=[0]).real
+
+    with pytest.raises(tc._lib.EngineError):
+        tc.backend.value_and_grad(bad)(w)
