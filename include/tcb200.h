@@ -123,6 +123,14 @@ int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
                         const void* udag, int64_t udag_batch_stride, double* grad,
                         int64_t grad_batch_stride, void* stream);
 
+/* Gradients of a run of consecutive DIAGONAL gates from one read of the two states (they commute: with
+ * psi, lam the states after the run, dL/dd_j[c] = d_j[c] * out[j][c]):
+ *   out[j][c] (complex128 pairs, +=) = sum over amplitudes i whose gate-j bits read c of lam[i] conj(psi[i]),
+ * c = bit_a(i) for a one-qubit gate (gate_bits = {a, -1}), (bit_a(i) << 1) | bit_b(i) for two qubits; out has
+ * 4 slots per gate.                                                                                      */
+int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int ngates, const int* gate_bits_host,
+                           double* out, void* stream);
+
 /* ---- statevector: sampling ------------------------------
  * Replaces probability() + cumsum + searchsorted of tensorcircuit/basecircuit.py:1490-1512 /
  * tensorcircuit/backends/abstract_backend.py:1828-1861 (and, with mode 1, the per-qubit conditional
@@ -195,6 +203,10 @@ int tcb_sv_plan_execute(const tcb_sv_plan* plan, void* state, int64_t batch, con
                         int64_t gate_batch_stride, uint64_t index_base, void* stream);
 int tcb_sv_plan_vjp(const tcb_sv_plan* plan, void* lam, void* psi, const void* udag, double* grad,
                     void* stream);
+/* the same walk over gates [first_gate, last_gate) only (last first): lets the host interleave it with
+ * run-level shortcuts such as tcb_sv_cross_marginals                                                   */
+int tcb_sv_plan_vjp_range(const tcb_sv_plan* plan, int first_gate, int last_gate, void* lam, void* psi,
+                          const void* udag, double* grad, void* stream);
 int tcb_sv_plan_launches(const tcb_sv_plan* plan, int vjp); /* kernels one execute / vjp launches */
 
 /* Tensor-network plan: one contraction tree as an SSA list of pairwise steps.  Ids 0..nleaves-1 are the

@@ -100,6 +100,7 @@ SYMBOLS = {
         c_int,
         [c_void_p, c_void_p, c_int, c_int64, POINTER(c_int), c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
     ),
+    "tcb_sv_cross_marginals": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_void_p, c_void_p]),
     "tcb_sv_sample_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "tcb_sv_sample": (
         c_int,
@@ -127,6 +128,10 @@ SYMBOLS = {
     "tcb_sv_plan_workspace_size": (c_int64, [c_void_p]),
     "tcb_sv_plan_execute": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_uint64, c_void_p]),
     "tcb_sv_plan_vjp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tcb_sv_plan_vjp_range": (
+        c_int,
+        [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "tcb_sv_plan_launches": (c_int, [c_void_p, c_int]),
     "tcb_tn_plan_create": (
         c_int,

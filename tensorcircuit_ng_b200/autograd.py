@@ -54,6 +54,53 @@ def _dense_matrix(gatebuf: torch.Tensor, op: GateOp) -> torch.Tensor:
     return gatebuf[op.mat_off : op.mat_off + d * d].reshape(d, d)
 
 
+diag_run_min = 3  # shorter runs of diagonal gates are walked gate by gate
+layered_adjoint = True
+
+
+class _DiagRun:
+    """A run [first, last) of consecutive diagonal gates of the circuit (program order) for the backward walk."""
+
+    def __init__(self, cc: "svengine.CompiledCircuit", first: int, last: int, dense_offs: List[int],
+                 device: torch.device) -> None:  # fmt: skip
+        nq = cc.plan.nbits
+        ops = cc.ops[first:last]
+        self.first, self.last = first, last
+        bits: List[int] = []
+        gidx: List[int] = []   # per (gate, c): index of U^dagger[c, c] in the dense dag buffer
+        ok: List[bool] = []
+        for op, off in zip(ops, dense_offs):
+            d = 1 << op.k
+            bp = [nq - 1 - q for q in op.qubits]
+            bits += [bp[0], bp[1] if op.k == 2 else -1]
+            for c in range(4):
+                ok.append(c < d)
+                gidx.append(off + c * (d + 1) if c < d else 0)
+        self.ngates = len(ops)
+        self.gate_bits = _lib.int_array(bits)
+        self.gidx = torch.tensor(gidx, dtype=torch.long, device=device)
+        self.ok = torch.tensor(ok, dtype=torch.bool, device=device)
+        # the daggered run as a circuit of its own: fused passes un-apply it on psi and on lam
+        structure = [(op.qubits, ("diag",), (1 << op.k) ** 2) for op in reversed(ops)]
+        self.sub = svengine.compile_circuit(nq, structure, device, absorb_prefix=False)
+        sub_idx: List[int] = []
+        for op, off in zip(reversed(ops), reversed(dense_offs)):
+            sub_idx += list(range(off, off + (1 << op.k) ** 2))
+        self.sub_idx = torch.tensor(sub_idx, dtype=torch.long, device=device)
+
+    def backward(self, nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor, g_all: torch.Tensor) -> None:
+        bins = torch.zeros(self.ngates * 4, 2, dtype=torch.float64, device=psi.device)
+        _lib.call("tcb_sv_cross_marginals", lam.data_ptr(), psi.data_ptr(), nbits, self.ngates, self.gate_bits,
+                  bins.data_ptr(), _lib.stream_ptr())  # fmt: skip
+        # dL/dd_j[c] = d_j[c] * bins_j[c];  d_j[c] = conj(U^dagger[c, c])
+        dvals = dag[self.gidx].conj().to(torch.complex128)
+        grad = torch.view_as_real(dvals * torch.view_as_complex(bins))
+        g_all.index_put_((self.gidx[self.ok],), grad[self.ok], accumulate=True)
+        sub_gb = dag[self.sub_idx]
+        self.sub.run(psi, sub_gb)
+        self.sub.run(lam, sub_gb)
+
+
 class _AdjointTables:
     """Per-circuit index tables for the backward walk, built once and cached on the compiled circuit:
     a dense row-major U^dagger for every gate comes from ONE gather of conj(gate buffer), and the
@@ -83,6 +130,26 @@ class _AdjointTables:
                             scat_dst.append(op.mat_off + r * d + c)
             self.items.append((op.k, _lib.int_array([nq - 1 - q for q in op.qubits]), off))
         self.total = len(dag_idx)
+        # program-order segments: ("G", first, last) = gates walked one by one; ("D", first, last) = a run of at
+        # least `diag_run_min` consecutive diagonal 1- / 2-qubit gates, differentiated from ONE read of the two
+        # states (they commute) and un-applied as one fused sub-circuit.
+        self.segments: List[Any] = []
+        ops = cc.ops
+        i = 0
+        while i < len(ops):
+            j = i
+            while j < len(ops) and ops[j].kind[0] in ("diag", "diagvec") and ops[j].k <= 2:
+                j += 1
+            if j - i >= diag_run_min:
+                self.segments.append(_DiagRun(cc, i, j, [it[2] for it in self.items[i:j]], device))
+                i = j
+                continue
+            j = max(j, i + 1)
+            if self.segments and isinstance(self.segments[-1], tuple):
+                self.segments[-1] = ("G", self.segments[-1][1], j)
+            else:
+                self.segments.append(("G", i, j))
+            i = j
         self.dag_idx = torch.tensor(dag_idx, dtype=torch.long, device=device)
         self.scat_src = torch.tensor(scat_src, dtype=torch.long, device=device)
         self.scat_dst = torch.tensor(scat_dst, dtype=torch.long, device=device)
@@ -120,7 +187,14 @@ class _Evolve(torch.autograd.Function):
         g_all = torch.zeros(max(tabs.total, 1), 2, dtype=torch.float64, device=gatebuf.device)
         # psi_in = U^dagger psi_out; dL/dU += lam_out (x) conj(psi_in); lam_in = U^dagger lam_out — one pass per
         # gate over both states, the whole walk one call (tcb_sv_plan_vjp)
-        cc.vjp(lam, psi, dag, g_all)
+        if layered_adjoint and len(tabs.segments) > 1:
+            for seg in reversed(tabs.segments):
+                if isinstance(seg, _DiagRun):
+                    seg.backward(nbits, lam, psi, dag, g_all)
+                else:
+                    cc.vjp(lam, psi, dag, g_all, seg[1], seg[2])
+        else:
+            cc.vjp(lam, psi, dag, g_all)
         grad_buf = torch.zeros_like(gatebuf)
         torch.view_as_real(grad_buf).index_add_(0, tabs.scat_dst, g_all[tabs.scat_src].to(torch.float32))
         grad_init = lam if ctx.has_init and ctx.needs_input_grad[1] else None

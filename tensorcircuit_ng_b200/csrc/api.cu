@@ -46,6 +46,7 @@ int launch_gate_grad(const void*, const void*, int, int64_t, const int*, int, vo
                      cudaStream_t);
 int launch_adjoint_step(void*, void*, int, int64_t, const int*, int, const void*, int64_t, void*, int64_t,
                         cudaStream_t);
+int launch_cross_marginals(const void*, const void*, int, int, const int*, double*, cudaStream_t);
 int launch_sample_prepare(const void*, int, int, double*, cudaStream_t);
 int launch_sample(const void*, int, int, const double*, const double*, int64_t, int, long long*, double*,
                   cudaStream_t);
@@ -183,6 +184,15 @@ int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
   NOTNULL(grad, "tcb_sv_adjoint_step");
   return launch_adjoint_step(lam, psi, nbits, batch, bitpos_host, k, udag, udag_batch_stride, grad,
                              grad_batch_stride, S(stream));
+}
+
+int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int ngates, const int* gate_bits_host,
+                           double* out, void* stream) {
+  NOTNULL(lam, "tcb_sv_cross_marginals");
+  NOTNULL(psi, "tcb_sv_cross_marginals");
+  NOTNULL(out, "tcb_sv_cross_marginals");
+  if (ngates > 0) NOTNULL(gate_bits_host, "tcb_sv_cross_marginals");
+  return launch_cross_marginals(lam, psi, nbits, ngates, gate_bits_host, out, S(stream));
 }
 
 int tcb_sv_sample_prepare(const void* state, int nbits, int seg_bits, double* cdf, void* stream) {

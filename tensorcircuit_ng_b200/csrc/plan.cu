@@ -161,14 +161,19 @@ int tcb_sv_plan_execute(const tcb_sv_plan* plan, void* state, int64_t batch, con
   return 0;
 }
 
-int tcb_sv_plan_vjp(const tcb_sv_plan* plan, void* lam, void* psi, const void* udag, double* grad, void* stream) {
+int tcb_sv_plan_vjp_range(const tcb_sv_plan* plan, int first_gate, int last_gate, void* lam, void* psi,
+                          const void* udag, double* grad, void* stream) {
   NOTNULL(plan, "tcb_sv_plan_vjp");
   NOTNULL(lam, "tcb_sv_plan_vjp");
   NOTNULL(psi, "tcb_sv_plan_vjp");
   NOTNULL(udag, "tcb_sv_plan_vjp");
   NOTNULL(grad, "tcb_sv_plan_vjp");
+  TCB_REQUIRE(first_gate >= 0 && first_gate <= last_gate && last_gate <= (int)plan->gates.size(),
+              "tcb_sv_plan_vjp: gate range [%d, %d) outside the plan's %d gates", first_gate, last_gate,
+              (int)plan->gates.size());
   const char* ud = reinterpret_cast<const char*>(udag);
-  for (auto it = plan->gates.rbegin(); it != plan->gates.rend(); ++it) {
+  for (int i = last_gate - 1; i >= first_gate; --i) {
+    const auto* it = &plan->gates[i];
     int rc;
     if (it->k <= 2) {
       rc = launch_adjoint_step(lam, psi, plan->nbits, 1, it->bitpos, it->k, ud + 8 * it->dense_off, 0,
@@ -180,6 +185,11 @@ int tcb_sv_plan_vjp(const tcb_sv_plan* plan, void* lam, void* psi, const void* u
     if (rc) return rc;
   }
   return 0;
+}
+
+int tcb_sv_plan_vjp(const tcb_sv_plan* plan, void* lam, void* psi, const void* udag, double* grad, void* stream) {
+  NOTNULL(plan, "tcb_sv_plan_vjp");
+  return tcb_sv_plan_vjp_range(plan, 0, (int)plan->gates.size(), lam, psi, udag, grad, stream);
 }
 
 int tcb_sv_plan_launches(const tcb_sv_plan* plan, int vjp) {

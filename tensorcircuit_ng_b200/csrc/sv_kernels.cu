@@ -1047,6 +1047,91 @@ int launch_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
 }
 
 // ---------------------------------------------------------------------------------
+// Gradients of a RUN of consecutive diagonal gates in one read of the two states.  Diagonal gates commute,
+// so with psi_L / lam_L the states AFTER the run,  dL/dd_j[c] = d_j[c] * sum_{i in c} lam_L[i] conj(psi_L[i])
+// for every gate j of the run (unit-modulus d): the only state-sized work is the marginal of the
+// elementwise product over the gate's one or two bits.  Up to CM_G gates per launch (register bins,
+// predicated adds; two-level float accumulation, double across threads).
+constexpr int CM_G = 8;
+
+struct CmGates {
+  int a[CM_G], b[CM_G];  // bit of matrix-index MSB / LSB; b = -1 for a one-qubit gate
+};
+
+__global__ void __launch_bounds__(256)
+cross_marginals_kernel(const float4* __restrict__ lam, const float4* __restrict__ psi, uint64_t nvec, CmGates g,
+                       int ngates, double* out) {
+  float2 acc[CM_G][4], acc2[CM_G][4];
+#pragma unroll
+  for (int j = 0; j < CM_G; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = acc2[j][c] = make_float2(0.f, 0.f);
+  int cnt = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nvec; p += stride) {
+    const float4 l = ldg_stream(lam + p), s = ldg_stream(psi + p);
+    // q = lam * conj(psi) for the two amplitudes 2p, 2p + 1
+    const float2 q0 = make_float2(l.x * s.x + l.y * s.y, l.y * s.x - l.x * s.y);
+    const float2 q1 = make_float2(l.z * s.z + l.w * s.w, l.w * s.z - l.z * s.w);
+    const uint64_t i0 = p << 1;
+#pragma unroll
+    for (int j = 0; j < CM_G; ++j) {
+      const int hi0 = (int)((i0 >> g.a[j]) & 1ull), hi1 = g.a[j] == 0 ? 1 : hi0;
+      const int lo0 = g.b[j] < 0 ? 0 : (int)((i0 >> g.b[j]) & 1ull), lo1 = g.b[j] == 0 ? 1 : lo0;
+      const int c0 = g.b[j] < 0 ? hi0 : (hi0 << 1) | lo0, c1 = g.b[j] < 0 ? hi1 : (hi1 << 1) | lo1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[j][c].x += (c == c0 ? q0.x : 0.f) + (c == c1 ? q1.x : 0.f);
+        acc[j][c].y += (c == c0 ? q0.y : 0.f) + (c == c1 ? q1.y : 0.f);
+      }
+    }
+    if ((++cnt & 31) == 0) {
+#pragma unroll
+      for (int j = 0; j < CM_G; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc2[j][c].x += acc[j][c].x;
+          acc2[j][c].y += acc[j][c].y;
+          acc[j][c] = make_float2(0.f, 0.f);
+        }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CM_G; ++j) {
+    if (j < ngates) {  // (uniform)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        block_reduce_add2((double)acc2[j][c].x + (double)acc[j][c].x, (double)acc2[j][c].y + (double)acc[j][c].y,
+                          out + 2 * (4 * j + c));
+        __syncthreads();
+      }
+    }
+  }
+}
+
+int launch_cross_marginals(const void* lam, const void* psi, int nbits, int ngates, const int* gate_bits,
+                           double* out, cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_cross_marginals: nbits=%d", nbits);
+  TCB_REQUIRE(ngates >= 0, "tcb_sv_cross_marginals: ngates=%d", ngates);
+  const uint64_t nvec = 1ull << (nbits - 1);
+  for (int first = 0; first < ngates; first += CM_G) {
+    const int cnt = ngates - first < CM_G ? ngates - first : CM_G;
+    CmGates g;
+    for (int j = 0; j < CM_G; ++j) {
+      const int src = first + (j < cnt ? j : 0);  // padding repeats a real gate; its bins are not written
+      g.a[j] = gate_bits[2 * src];
+      g.b[j] = gate_bits[2 * src + 1];
+      TCB_REQUIRE(g.a[j] >= 0 && g.a[j] < nbits && g.b[j] >= -1 && g.b[j] < nbits && g.a[j] != g.b[j],
+                  "tcb_sv_cross_marginals: gate %d has bits (%d, %d)", src, g.a[j], g.b[j]);
+    }
+    cross_marginals_kernel<<<grid_for(nvec, 256, 4), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(lam), reinterpret_cast<const float4*>(psi), nvec, g, cnt, out + 8 * first);
+    TCB_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 // pack / unpack the half of the state with local bit == want (global<->local qubit swap)
 __global__ void __launch_bounds__(256)
 pack_half_kernel(const float2* __restrict__ state, float2* __restrict__ buf, uint64_t nhalf, int bit,

@@ -282,16 +282,18 @@ class CompiledCircuit:
                 pass
             self._handle = None
 
-    def vjp(self, lam: torch.Tensor, psi: torch.Tensor, udag: torch.Tensor, grad: torch.Tensor) -> None:
+    def vjp(self, lam: torch.Tensor, psi: torch.Tensor, udag: torch.Tensor, grad: torch.Tensor,
+            first: int = 0, last: Optional[int] = None) -> None:  # fmt: skip
         """The whole adjoint walk (last gate first) in one call: psi is un-computed in place, lam becomes the
         cotangent of the initial state, grad (float64 pairs, dense block per gate) accumulates dL/dU."""
         if not self.has_vjp:
             k = max(g.k for g in self.ops)
             raise _lib.EngineError(f"the adjoint walk supports gates of up to 7 qubits (found {k})")
         h = self.handle()
-        _lib.check(_lib.load().tcb_sv_plan_vjp(h, lam.data_ptr(), psi.data_ptr(), udag.data_ptr(), grad.data_ptr(),
-                                               _lib.stream_ptr()))  # fmt: skip
-        _lib.launch_count += self._n_launch_vjp
+        last = len(self.ops) if last is None else last
+        _lib.check(_lib.load().tcb_sv_plan_vjp_range(h, first, last, lam.data_ptr(), psi.data_ptr(), udag.data_ptr(),
+                                                     grad.data_ptr(), _lib.stream_ptr()))  # fmt: skip
+        _lib.launch_count += sum(1 if g.k <= 2 else 2 for g in self.ops[first:last])
 
     def start(self, state: torch.Tensor, gatebuf: torch.Tensor) -> None:
         """Write the initial state of the compiled part: |0...0>, or the product state that the

@@ -208,6 +208,34 @@ def test_adjoint_step_fused(cuda, n, qubits):
             assert np.abs(got_g[b] - want_g).max() <= 2e-6 * np.abs(want_g).max() + 1e-6 * np.sqrt(2.0**n)
 
 
+@pytest.mark.parametrize("n", [1, 2, 6, 13, 18])
+def test_cross_marginals(cuda, n):
+    """tcb_sv_cross_marginals: per gate, the marginal of lam * conj(psi) over the gate's bits (>= 2 launches' worth)."""
+    from tensorcircuit_ng_b200 import _lib
+
+    rng = np.random.default_rng(n)
+    lam, psi = _rand_c(rng, 2**n), _rand_c(rng, 2**n)
+    gates = []
+    for _ in range(11):
+        if n >= 2 and rng.integers(0, 2):
+            a, b = (int(x) for x in rng.permutation(n)[:2])
+            gates.append((a, b))
+        else:
+            gates.append((int(rng.integers(0, n)), -1))
+    out = torch.zeros(len(gates) * 4, 2, dtype=torch.float64, device="cuda")
+    lt, pt = torch.from_numpy(lam).cuda(), torch.from_numpy(psi).cuda()
+    _lib.call("tcb_sv_cross_marginals", lt.data_ptr(), pt.data_ptr(), n, len(gates),
+              _lib.int_array([x for g in gates for x in g]), out.data_ptr(), _lib.stream_ptr())  # fmt: skip
+    got = torch.view_as_complex(out).cpu().numpy().reshape(len(gates), 4)
+    q = lam.astype(np.complex128) * np.conj(psi.astype(np.complex128))
+    idx = np.arange(2**n)
+    for j, (a, b) in enumerate(gates):
+        c = (idx >> a) & 1 if b < 0 else (((idx >> a) & 1) << 1) | ((idx >> b) & 1)
+        for cc in range(4):
+            want = q[c == cc].sum()
+            assert abs(got[j, cc] - want) <= 2e-6 * np.abs(q).sum() ** 0.5 + 1e-6 * abs(want), (j, cc)
+
+
 def test_error_reporting(cuda):
     from tensorcircuit_ng_b200 import _lib
 

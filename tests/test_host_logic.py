@@ -366,3 +366,50 @@ def test_lazy_parametrised_gates_match_eager_values_and_gradients():
     assert not lz.pending() and tuple(t.shape) == lz.shape
     cj = lz.copy(conjugate=True)
     assert not isinstance(cj, gates.LazyGate) and torch.equal(cj.tensor.resolve_conj(), t.conj().resolve_conj())
+
+
+def test_diagonal_only_subcircuit_plans(built):
+    """The backward walk un-applies a run of diagonal gates as a circuit of its own (autograd._DiagRun): a plan
+    made of diagonal gates only, applied to an arbitrary state, must equal the elementwise product."""
+    from tensorcircuit_ng_b200 import passplan
+
+    emu = _emu()
+    for n, seed in [(6, 0), (13, 1), (15, 2)]:
+        rng = np.random.default_rng(seed)
+        gops, mats, off = [], [], 0
+        pairs = [(q, q + 1) for q in range(n - 1)] + [(int(rng.integers(0, n)),) for _ in range(4)] + [(n - 1, 0)]
+        for gi, qs in enumerate(pairs):
+            d = np.exp(1j * rng.uniform(0, 2 * np.pi, size=2 ** len(qs))).astype(np.complex64)
+            mats.append(np.diag(d).astype(np.complex64).reshape(-1))
+            gops.append(passplan.GateOp(tuple(qs), ("diag",), off, gi))
+            off += 4 ** len(qs)
+        buf = np.concatenate(mats)
+        plan = passplan.compile_plan(gops, n)
+        state = (rng.normal(size=2**n) + 1j * rng.normal(size=2**n)).astype(np.complex64)
+        want = state.astype(np.complex128).reshape([2] * n)
+        for g, m in zip(gops, mats):
+            k = g.k
+            dd = np.diag(m.reshape(2**k, 2**k)).reshape([2] * k)
+            shape = [1] * n
+            for ax, q in enumerate(g.qubits):
+                shape[q] = 2
+            want = want * np.transpose(dd, np.argsort(np.argsort(g.qubits))).reshape(shape) if k > 1 else want * dd.reshape(shape)
+        npass = 0
+        for st in plan.steps:
+            if not isinstance(st, passplan.PassStep):  # (tiny states: one launch per gate)
+                g = st.gate
+                dd = np.diag(buf[g.mat_off : g.mat_off + 4**g.k].reshape(2**g.k, 2**g.k)).reshape([2] * g.k)
+                shape = [1] * n
+                for q in g.qubits:
+                    shape[q] = 2
+                dd = np.transpose(dd, np.argsort(np.argsort(g.qubits))) if g.k > 1 else dd
+                state = (state.reshape([2] * n) * dd.reshape(shape)).reshape(-1).astype(np.complex64)
+                continue
+            npass += 1
+            prog = np.ascontiguousarray(st.program)
+            rc = emu.emu_run_pass(state.ctypes.data_as(ctypes.c_void_p), n, ctypes.c_longlong(1),
+                                  prog.ctypes.data_as(ctypes.c_void_p), len(prog), st.tile_bits, st.low_bits,
+                                  buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(0), ctypes.c_ulonglong(0))  # fmt: skip
+            assert rc == 0
+        assert n < 12 or 1 <= npass <= 3
+        assert np.abs(state - want.reshape(-1)).max() < 2e-5 * np.abs(want).max()

@@ -192,3 +192,48 @@ def test_gpu_gradient_through_constant_three_qubit_gates(cuda):
 
     with pytest.raises(tc._lib.EngineError):
         tc.backend.value_and_grad(bad)(w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [5, 13, 16])
+def test_gpu_layered_adjoint_equals_gate_by_gate_walk(cuda, n):
+    """Runs of diagonal gates differentiated from one read of the two states (tcb_sv_cross_marginals + fused
+    un-apply) give the gradients of the gate-by-gate adjoint walk."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import autograd
+
+    def energy(p):
+        c = tc.Circuit(n)
+        for q in range(n):
+            c.h(q)
+        k = 0
+        for l in range(2):
+            for q in range(n - 1):
+                c.rzz(q, q + 1, theta=p[k])
+                k += 1
+            for q in range(0, n, 2):
+                c.rz(q, theta=p[k])
+                k += 1
+            c.cz(0, n - 1)
+            for q in range(n):
+                c.rx(q, theta=p[k])
+                k += 1
+            c.cnot(1, 2)
+            c.rz(0, theta=p[k])  # a short diagonal run (walked gate by gate)
+            k += 1
+        return c.expectation_ps(z=[0, 1]).real + c.expectation_ps(x=[n - 1]).real + c.expectation_ps(y=[2]).real
+
+    nparam = 2 * ((n - 1) + len(range(0, n, 2)) + n + 1)
+    p0 = torch.linspace(0.1, 2.9, nparam)
+    autograd.layered_adjoint = True
+    v1, g1 = tc.backend.value_and_grad(energy)(p0)
+    autograd.layered_adjoint = False
+    try:
+        v2, g2 = tc.backend.value_and_grad(energy)(p0)
+    finally:
+        autograd.layered_adjoint = True
+    assert abs(float(v1) - float(v2)) < 1e-6
+    assert float((g1 - g2).abs().max()) < 2e-5
+    assert float(g2.abs().max()) > 1e-2
