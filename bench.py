@@ -734,8 +734,10 @@ def run_vqe(args: argparse.Namespace) -> None:
         "data": "synthetic",
         "config": {"workload": f"tfim_vqe_n{n}_depth{depth}_vvag_batch{batch}", "gates_per_sample": n_gates,
                    "value_definition": "forward gates x batch / s for one value_and_grad step (energy = one "
-                                       "Pauli-sum launch; backward = adjoint method, one fused launch per gate over "
-                                       "psi and lambda; vmap = loop over the batch)",
+                                       "Pauli-sum launch; backward = layered adjoint walk: runs of diagonal gates and "
+                                       "of one-qubit gates are differentiated from a few reads of psi and lambda and "
+                                       "un-applied as fused sub-circuits, other gates one fused launch each; vmap = "
+                                       "loop over the batch, host-bound)",
                    "energy_mean": float(vals.mean()), "grad_norm": float(grads.norm())},
         "roofline": None,
         "cpu_baseline": None,

@@ -131,6 +131,14 @@ int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
 int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int ngates, const int* gate_bits_host,
                            double* out, void* stream);
 
+/* Cross reduced density matrices of single qubits between two states, up to 10 qubits per read of both:
+ *   out[t][r][c] (complex128 pairs, +=) = sum_rest lam[rest, bit_t = r] conj(psi[rest, bit_t = c])
+ * for the tile bits t = 0..min(3,nbits)-1 (the lowest address bits, always in the tile) followed by the nsel
+ * (<= 7) selected bits (ascending, >= 3).  With lam, psi the states BEFORE a layer of one-qubit gates on
+ * distinct qubits, dL/dU_q = U_q out[q] for every gate of the layer (same convention as tcb_sv_gate_grad). */
+int tcb_sv_cross_rdm(const void* lam, const void* psi, int nbits, int nsel, const int* sel_bits_host, double* out,
+                     void* stream);
+
 /* ---- statevector: sampling ------------------------------
  * Replaces probability() + cumsum + searchsorted of tensorcircuit/basecircuit.py:1490-1512 /
  * tensorcircuit/backends/abstract_backend.py:1828-1861 (and, with mode 1, the per-qubit conditional

@@ -55,6 +55,7 @@ def _dense_matrix(gatebuf: torch.Tensor, op: GateOp) -> torch.Tensor:
 
 
 diag_run_min = 3  # shorter runs of diagonal gates are walked gate by gate
+one_qubit_run_min = 4  # likewise for runs of one-qubit gates on distinct qubits
 layered_adjoint = True
 
 
@@ -101,6 +102,60 @@ class _DiagRun:
         self.sub.run(lam, sub_gb)
 
 
+class _OneQubitRun:
+    """A run [first, last) of consecutive one-qubit gates on DISTINCT qubits.  They commute and every other gate
+    of the run is a unitary on another qubit, so it drops out of the partial trace:
+    dL/dU_q = U_q C_q  with  C_q[r][c] = sum_rest lam_0[rest, r] conj(psi_0[rest, c])  of the states BEFORE the
+    run.  The run is un-applied as one fused sub-circuit, then all C_q come from ceil((m - 3) / 7) reads of the
+    two states (`tcb_sv_cross_rdm`) instead of one adjoint step per gate."""
+
+    def __init__(self, cc: "svengine.CompiledCircuit", first: int, last: int, dense_offs: List[int],
+                 device: torch.device) -> None:  # fmt: skip
+        nq = cc.plan.nbits
+        ops = cc.ops[first:last]
+        self.first, self.last = first, last
+        low = min(3, nq)
+        bitpos = [nq - 1 - op.qubits[0] for op in ops]
+        high = sorted(b for b in bitpos if b >= low)
+        self.groups: List[Any] = []  # int arrays of selected bits, one cross_rdm call each
+        chunks = [high[i : i + 7] for i in range(0, len(high), 7)] or [[]]
+        where = {}
+        for gi, ch in enumerate(chunks):
+            self.groups.append((len(ch), _lib.int_array(ch) if ch else None))
+            for t, b in enumerate(ch):
+                where[b] = (gi * 10 + low + t) * 4
+        for b in range(low):
+            where[b] = b * 4  # the low bits are in every tile: read them from the first call
+        src = []
+        for b in bitpos:
+            src += [where[b] + c for c in range(4)]
+        self.src = torch.tensor(src, dtype=torch.long, device=device)
+        dst = []
+        for off in dense_offs:
+            dst += [off + c for c in range(4)]
+        self.dst = torch.tensor(dst, dtype=torch.long, device=device)
+        self.m = len(ops)
+        structure = [(op.qubits, ("diag",) if op.kind[0] in ("diag", "diagvec") else ("dense",), 4) for op in reversed(ops)]
+        self.sub = svengine.compile_circuit(nq, structure, device, absorb_prefix=False)
+        sub_idx: List[int] = []
+        for off in reversed(dense_offs):
+            sub_idx += list(range(off, off + 4))
+        self.sub_idx = torch.tensor(sub_idx, dtype=torch.long, device=device)
+
+    def backward(self, nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor, g_all: torch.Tensor) -> None:
+        sub_gb = dag[self.sub_idx]
+        self.sub.run(psi, sub_gb)  # psi_0, lam_0: the states before the run
+        self.sub.run(lam, sub_gb)
+        cr = torch.zeros(len(self.groups) * 40, 2, dtype=torch.float64, device=psi.device)
+        for gi, (nsel, sel) in enumerate(self.groups):
+            _lib.call("tcb_sv_cross_rdm", lam.data_ptr(), psi.data_ptr(), nbits, nsel, sel,
+                      cr.data_ptr() + gi * 40 * 16, _lib.stream_ptr())  # fmt: skip
+        c = torch.view_as_complex(cr[self.src]).reshape(self.m, 2, 2)
+        u = dag[self.dst].reshape(self.m, 2, 2).conj().transpose(1, 2).to(torch.complex128)  # U = (U^dagger)^dagger
+        g = torch.bmm(u, c).reshape(-1)
+        g_all.index_put_((self.dst,), torch.view_as_real(g), accumulate=True)
+
+
 class _AdjointTables:
     """Per-circuit index tables for the backward walk, built once and cached on the compiled circuit:
     a dense row-major U^dagger for every gate comes from ONE gather of conj(gate buffer), and the
@@ -135,21 +190,43 @@ class _AdjointTables:
         # states (they commute) and un-applied as one fused sub-circuit.
         self.segments: List[Any] = []
         ops = cc.ops
-        i = 0
+        offs = [it[2] for it in self.items]
+
+        def add_plain(a: int, b: int) -> None:
+            if a >= b:
+                return
+            if self.segments and isinstance(self.segments[-1], tuple) and self.segments[-1][2] == a:
+                self.segments[-1] = ("G", self.segments[-1][1], b)
+            else:
+                self.segments.append(("G", a, b))
+
+        def add_general(a: int, b: int) -> None:
+            """[a, b) holds no long diagonal run: carve out runs of one-qubit gates on distinct qubits."""
+            i = a
+            while i < b:
+                j, seen = i, set()
+                while j < b and ops[j].k == 1 and ops[j].qubits[0] not in seen:
+                    seen.add(ops[j].qubits[0])
+                    j += 1
+                if j - i >= one_qubit_run_min:
+                    self.segments.append(_OneQubitRun(cc, i, j, offs[i:j], device))
+                    i = j
+                else:
+                    add_plain(i, i + 1)
+                    i += 1
+
+        i = start = 0
         while i < len(ops):
             j = i
             while j < len(ops) and ops[j].kind[0] in ("diag", "diagvec") and ops[j].k <= 2:
                 j += 1
             if j - i >= diag_run_min:
-                self.segments.append(_DiagRun(cc, i, j, [it[2] for it in self.items[i:j]], device))
-                i = j
-                continue
-            j = max(j, i + 1)
-            if self.segments and isinstance(self.segments[-1], tuple):
-                self.segments[-1] = ("G", self.segments[-1][1], j)
+                add_general(start, i)
+                self.segments.append(_DiagRun(cc, i, j, offs[i:j], device))
+                i = start = j
             else:
-                self.segments.append(("G", i, j))
-            i = j
+                i = max(j, i + 1)
+        add_general(start, len(ops))
         self.dag_idx = torch.tensor(dag_idx, dtype=torch.long, device=device)
         self.scat_src = torch.tensor(scat_src, dtype=torch.long, device=device)
         self.scat_dst = torch.tensor(scat_dst, dtype=torch.long, device=device)
@@ -189,7 +266,7 @@ class _Evolve(torch.autograd.Function):
         # gate over both states, the whole walk one call (tcb_sv_plan_vjp)
         if layered_adjoint and len(tabs.segments) > 1:
             for seg in reversed(tabs.segments):
-                if isinstance(seg, _DiagRun):
+                if isinstance(seg, (_DiagRun, _OneQubitRun)):
                     seg.backward(nbits, lam, psi, dag, g_all)
                 else:
                     cc.vjp(lam, psi, dag, g_all, seg[1], seg[2])

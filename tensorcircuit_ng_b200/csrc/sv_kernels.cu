@@ -1132,6 +1132,111 @@ int launch_cross_marginals(const void* lam, const void* psi, int nbits, int ngat
 }
 
 // ---------------------------------------------------------------------------------
+// Cross reduced density matrices of single qubits between two states, many qubits per read:
+//   C_q[r][c] = sum_rest lam[rest, q = r] conj(psi[rest, q = c])
+// for every qubit of a tile of up to 10 bits (the three lowest address bits + up to seven chosen ones; a tile
+// of 1024 amplitudes of each state sits in shared memory).  With lam_0 / psi_0 the states BEFORE a layer of
+// one-qubit gates on distinct qubits, dL/dU_q = U_q C_q for every gate of the layer at once (the other
+// gates of the layer are unitaries on other qubits and drop out of the partial trace).
+constexpr int CR_MAXB = 10;
+
+struct CrBits {
+  int nlow, nsel;
+  int sel[7];
+};
+
+__global__ void __launch_bounds__(256)
+cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi, int nbits, CrBits cb, double* out) {
+  __shared__ float2 sl[1 << CR_MAXB], sp[1 << CR_MAXB];
+  __shared__ double sacc[CR_MAXB * 4 * 2];
+  const int tb = cb.nlow + cb.nsel;          // tile bits
+  const int tsize = 1 << tb;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < CR_MAXB * 8; e += blockDim.x) sacc[e] = 0.0;
+  float2 acc[CR_MAXB][4];
+#pragma unroll
+  for (int t = 0; t < CR_MAXB; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[t][c] = make_float2(0.f, 0.f);
+  auto flush = [&]() {
+#pragma unroll
+    for (int t = 0; t < CR_MAXB; ++t)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float re = acc[t][c].x, im = acc[t][c].y;
+        acc[t][c] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          re += __shfl_xor_sync(0xffffffffu, re, o);
+          im += __shfl_xor_sync(0xffffffffu, im, o);
+        }
+        if ((tid & 31) == 0 && t < tb) {
+          atomicAdd(&sacc[(t * 4 + c) * 2], (double)re);
+          atomicAdd(&sacc[(t * 4 + c) * 2 + 1], (double)im);
+        }
+      }
+  };
+  const uint64_t ntiles = 1ull << (nbits - tb);
+  int it = 0;
+  __syncthreads();
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // tile base: spread the tile counter over the bits that are NOT in the tile
+    uint64_t base = tile << cb.nlow;
+    for (int j = 0; j < cb.nsel; ++j) base = insert_zero(base, cb.sel[j]);  // sel ascending
+    for (int e = tid; e < tsize; e += blockDim.x) {
+      uint64_t a = base | (uint64_t)(e & ((1 << cb.nlow) - 1));
+      for (int j = 0; j < cb.nsel; ++j) a |= (uint64_t)((e >> (cb.nlow + j)) & 1) << cb.sel[j];
+      sl[e] = lam[a];
+      sp[e] = psi[a];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < CR_MAXB; ++t) {
+      if (t < tb) {
+        for (int j = tid; j < (tsize >> 1); j += blockDim.x) {
+          const int i0 = (int)insert_zero((uint64_t)j, t), i1 = i0 | (1 << t);
+          const float2 l0 = sl[i0], l1 = sl[i1], p0 = sp[i0], p1 = sp[i1];
+          acc[t][0].x += l0.x * p0.x + l0.y * p0.y;  acc[t][0].y += l0.y * p0.x - l0.x * p0.y;  // [0][0]
+          acc[t][1].x += l0.x * p1.x + l0.y * p1.y;  acc[t][1].y += l0.y * p1.x - l0.x * p1.y;  // [0][1]
+          acc[t][2].x += l1.x * p0.x + l1.y * p0.y;  acc[t][2].y += l1.y * p0.x - l1.x * p0.y;  // [1][0]
+          acc[t][3].x += l1.x * p1.x + l1.y * p1.y;  acc[t][3].y += l1.y * p1.x - l1.x * p1.y;  // [1][1]
+        }
+      }
+    }
+    __syncthreads();
+    if (++it == 32) {
+      flush();
+      it = 0;
+    }
+  }
+  flush();
+  __syncthreads();
+  for (int e = tid; e < tb * 8; e += blockDim.x) atomicAdd(out + e, sacc[e]);
+}
+
+int launch_cross_rdm(const void* lam, const void* psi, int nbits, int nsel, const int* sel_bits, double* out,
+                     cudaStream_t stream) {
+  TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_cross_rdm: nbits=%d", nbits);
+  CrBits cb;
+  cb.nlow = nbits < 3 ? nbits : 3;
+  cb.nsel = nsel;
+  TCB_REQUIRE(nsel >= 0 && nsel <= 7 && cb.nlow + nsel <= nbits, "tcb_sv_cross_rdm: nsel=%d", nsel);
+  for (int j = 0; j < 7; ++j) cb.sel[j] = 0;
+  for (int j = 0; j < nsel; ++j) {
+    cb.sel[j] = sel_bits[j];
+    TCB_REQUIRE(sel_bits[j] >= cb.nlow && sel_bits[j] < nbits && (j == 0 || sel_bits[j] > sel_bits[j - 1]),
+                "tcb_sv_cross_rdm: selected bits must be ascending, >= %d and < nbits (bit %d)", cb.nlow, sel_bits[j]);
+  }
+  const uint64_t ntiles = 1ull << (nbits - cb.nlow - nsel);
+  uint64_t grid = (uint64_t)sm_count() * 4;
+  if (grid > ntiles) grid = ntiles;
+  cross_rdm_kernel<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const float2*>(lam),
+                                                      reinterpret_cast<const float2*>(psi), nbits, cb, out);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 // pack / unpack the half of the state with local bit == want (global<->local qubit swap)
 __global__ void __launch_bounds__(256)
 pack_half_kernel(const float2* __restrict__ state, float2* __restrict__ buf, uint64_t nhalf, int bit,

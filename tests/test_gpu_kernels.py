@@ -236,6 +236,32 @@ def test_cross_marginals(cuda, n):
             assert abs(got[j, cc] - want) <= 2e-6 * np.abs(q).sum() ** 0.5 + 1e-6 * abs(want), (j, cc)
 
 
+@pytest.mark.parametrize("n,sel", [(1, []), (2, []), (3, []), (5, [3, 4]), (12, [3, 5, 6, 8, 9, 10, 11]), (15, [4, 14]),
+                                   (19, [7, 9, 11, 13, 15, 17, 18])])  # fmt: skip
+def test_cross_rdm(cuda, n, sel):
+    """tcb_sv_cross_rdm: out[t][r][c] = sum_rest lam[rest, bit_t = r] conj(psi[rest, bit_t = c]) for the low bits + sel."""
+    from tensorcircuit_ng_b200 import _lib
+
+    rng = np.random.default_rng(n + len(sel))
+    lam, psi = _rand_c(rng, 2**n), _rand_c(rng, 2**n)
+    low = min(3, n)
+    bits = list(range(low)) + sel
+    out = torch.zeros(40, 2, dtype=torch.float64, device="cuda")
+    lt, pt = torch.from_numpy(lam).cuda(), torch.from_numpy(psi).cuda()
+    _lib.call("tcb_sv_cross_rdm", lt.data_ptr(), pt.data_ptr(), n, len(sel), _lib.int_array(sel) if sel else None,
+              out.data_ptr(), _lib.stream_ptr())  # fmt: skip
+    got = torch.view_as_complex(out).cpu().numpy().reshape(10, 2, 2)
+    L = lam.astype(np.complex128).reshape([2] * n)
+    P = psi.astype(np.complex128).reshape([2] * n)
+    for t, b in enumerate(bits):
+        ax = n - 1 - b  # flat bit b is axis n-1-b
+        Lm = np.moveaxis(L, ax, 0).reshape(2, -1)
+        Pm = np.moveaxis(P, ax, 0).reshape(2, -1)
+        want = Lm @ Pm.conj().T
+        assert np.abs(got[t] - want).max() <= 2e-6 * np.abs(want).max() + 1e-6 * np.sqrt(2.0**n), (t, b)
+    assert len(bits) == 10 or np.abs(got[len(bits):]).max() == 0
+
+
 def test_error_reporting(cuda):
     from tensorcircuit_ng_b200 import _lib
 
