@@ -264,21 +264,107 @@ class _Evolve(torch.autograd.Function):
         g_all = torch.zeros(max(tabs.total, 1), 2, dtype=torch.float64, device=gatebuf.device)
         # psi_in = U^dagger psi_out; dL/dU += lam_out (x) conj(psi_in); lam_in = U^dagger lam_out — one pass per
         # gate over both states, the whole walk one call (tcb_sv_plan_vjp)
-        if layered_adjoint and len(tabs.segments) > 1:
-            for seg in reversed(tabs.segments):
-                if isinstance(seg, (_DiagRun, _OneQubitRun)):
-                    seg.backward(nbits, lam, psi, dag, g_all)
-                else:
-                    cc.vjp(lam, psi, dag, g_all, seg[1], seg[2])
-        else:
-            cc.vjp(lam, psi, dag, g_all)
+        _walk(cc, tabs, nbits, lam, psi, dag, g_all)
         grad_buf = torch.zeros_like(gatebuf)
         torch.view_as_real(grad_buf).index_add_(0, tabs.scat_dst, g_all[tabs.scat_src].to(torch.float32))
         grad_init = lam if ctx.has_init and ctx.needs_input_grad[1] else None
         return grad_buf, grad_init, None
 
 
+# ---- batched evolution under torch.vmap ------------------------------------------------------------
+# `backend.vmap / vvag` run the user's function ONCE under torch.vmap: every torch op on the parameters is
+# batched by functorch, and at the engine boundary the batched gate buffer is unwrapped to its physical
+# [B, elems] tensor, the kernels run with batch = B (one circuit build, one plan, B states side by side in
+# HBM), and the result is wrapped again.  Plain autograd runs on the physical tensors.
+_ft = torch._C._functorch
+
+
+def is_batched(t: Any) -> bool:
+    return isinstance(t, torch.Tensor) and _ft.is_batchedtensor(t)
+
+
+def unwrap_batched(t: torch.Tensor) -> Any:
+    """(physical tensor with the batch dimension first, vmap level)."""
+    lvl, bd = _ft.maybe_get_level(t), _ft.maybe_get_bdim(t)
+    phys = _ft.get_unwrapped(t)
+    if is_batched(phys):
+        raise _lib.EngineError("nested vmap is not supported by the batched engine path")
+    return phys.movedim(bd, 0), lvl
+
+
+def outside_vmap() -> Any:
+    from torch._functorch import pyfunctorch
+
+    return pyfunctorch.temporarily_pop_interpreter_stack()
+
+
+def rewrap_batched(t: torch.Tensor, lvl: int) -> torch.Tensor:
+    return _ft._add_batch_dim(t, 0, lvl)
+
+
+class _EvolveBatched(torch.autograd.Function):
+    """B independent parameter sets of one circuit: states [B, 2^n], gate buffers [B, elems]."""
+
+    @staticmethod
+    def forward(ctx: Any, gatebuf: torch.Tensor, cc: Any) -> torch.Tensor:
+        gb = gatebuf.detach().to(torch.complex64).contiguous()
+        nb, nelem = gb.shape
+        nbits = cc.plan.nbits
+        if gb.is_cuda:
+            free, _ = torch.cuda.mem_get_info(gb.device)
+            need = 5 * (nb << nbits) * 8  # state, saved copy, lam, psi, H psi / cotangents
+            if need > 0.9 * free:
+                raise _lib.EngineError(f"a batch of {nb} {nbits}-qubit states does not fit in free HBM ({free >> 30} GiB)")
+        state = torch.empty(nb << nbits, dtype=torch.complex64, device=gb.device)
+        _lib.require_cuda(state, "state")
+        _lib.call("tcb_sv_init_zero", state.data_ptr(), nbits, nb, _lib.stream_ptr())
+        cc.run(state, gb, batch=nb, gate_batch_stride=nelem)
+        state = state.reshape(nb, 1 << nbits)
+        ctx.cc = cc
+        ctx.save_for_backward(gb, state)
+        return state
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore[override]
+        gb, psi_out = ctx.saved_tensors
+        cc = ctx.cc
+        nbits = cc.plan.nbits
+        nb, nelem = gb.shape
+        tabs = _adjoint_tables(cc, gb[0])
+        lam = grad_out.to(torch.complex64).resolve_conj().contiguous().clone()
+        psi = psi_out.clone()
+        src = torch.cat([gb.conj().resolve_conj(), torch.zeros(nb, 1, dtype=gb.dtype, device=gb.device)], dim=1)
+        dag = src[:, tabs.dag_idx].contiguous()
+        g_all = torch.zeros(nb, max(tabs.total, 1), 2, dtype=torch.float64, device=gb.device)
+        for b in range(nb):  # the walk itself is per sample (two states each); everything around it is batched
+            _walk(cc, tabs, nbits, lam[b], psi[b], dag[b], g_all[b])
+        grad_buf = torch.zeros(nb, nelem, 2, dtype=torch.float32, device=gb.device)
+        grad_buf.index_add_(1, tabs.scat_dst, g_all[:, tabs.scat_src].to(torch.float32))
+        return torch.view_as_complex(grad_buf), None
+
+
+def _walk(cc: Any, tabs: "_AdjointTables", nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor,
+          g_all: torch.Tensor) -> None:  # fmt: skip
+    """The adjoint walk over one sample: psi is un-computed in place, lam becomes the cotangent of the initial
+    state, g_all (float64 pairs, one dense block per gate) receives dL/dU."""
+    if layered_adjoint and len(tabs.segments) > 1:
+        for seg in reversed(tabs.segments):
+            if isinstance(seg, (_DiagRun, _OneQubitRun)):
+                seg.backward(nbits, lam, psi, dag, g_all)
+            else:
+                cc.vjp(lam, psi, dag, g_all, seg[1], seg[2])
+    else:
+        cc.vjp(lam, psi, dag, g_all)
+
+
 def evolve(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor, init: Optional[torch.Tensor]) -> torch.Tensor:
+    if is_batched(gatebuf) or is_batched(init):
+        if init is not None or cc.prefix_levels:
+            raise _lib.EngineError("the batched engine path starts from |0...0> (no `inputs`, no absorbed prefix)")
+        phys, lvl = unwrap_batched(gatebuf)
+        with outside_vmap():
+            out = _EvolveBatched.apply(phys, cc)
+        return rewrap_batched(out, lvl)
     needs = torch.is_grad_enabled() and (gatebuf.requires_grad or (init is not None and init.requires_grad))
     if not needs:
         return _forward(cc, gatebuf, init)

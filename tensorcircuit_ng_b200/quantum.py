@@ -116,10 +116,12 @@ class PauliStringSum:
 
     # -- raw launches -----------------------------------------------------------------------------
     def _launch(self, psi: torch.Tensor, want_state: bool, want_value: bool) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:  # fmt: skip
+        """psi: [2^n] or a batch [B, 2^n] (contiguous); value: float64 [2] or [B, 2]."""
         xs, zs, cs = self._tables(psi.device)
+        nb = 1 if psi.dim() == 1 else int(psi.shape[0])
         out = torch.empty_like(psi) if want_state else None
-        val = torch.zeros(2, dtype=torch.float64, device=psi.device) if want_value else None
-        _lib.call("tcb_sv_pauli_sum", psi.data_ptr(), self.n, 1, xs.data_ptr(), zs.data_ptr(), cs.data_ptr(),
+        val = torch.zeros((2,) if psi.dim() == 1 else (nb, 2), dtype=torch.float64, device=psi.device) if want_value else None
+        _lib.call("tcb_sv_pauli_sum", psi.data_ptr(), self.n, nb, xs.data_ptr(), zs.data_ptr(), cs.data_ptr(),
                   self.nterms, 0, out.data_ptr() if out is not None else None, 0,
                   val.data_ptr() if val is not None else None, _lib.stream_ptr())  # fmt: skip
         return out, val
@@ -134,6 +136,16 @@ class PauliStringSum:
 
     def expectation(self, psi: torch.Tensor) -> torch.Tensor:
         """<psi|H|psi> as a complex64 scalar (real up to rounding for a Hermitian sum)."""
+        from . import autograd
+
+        if autograd.is_batched(psi):  # under torch.vmap: one launch for the whole batch
+            phys, lvl = autograd.unwrap_batched(psi)
+            with autograd.outside_vmap():
+                p2 = phys.to(torch.complex64).resolve_conj().reshape(phys.shape[0], -1).contiguous()
+                if p2.shape[1] != (1 << self.n):
+                    raise ValueError(f"state has {p2.shape[1]} amplitudes, the Pauli sum acts on {self.n} qubits")
+                out = _Expect.apply(p2, self)
+            return autograd.rewrap_batched(out, lvl)
         return _Expect.apply(self._check(psi), self)
 
     # -- small-n conversions (tests, interop) -----------------------------------------------------
@@ -176,6 +188,8 @@ class _Expect(torch.autograd.Function):
         ctx.h = h
         ctx.save_for_backward(psi)
         _, val = h._launch(psi, False, True)
+        if psi.dim() == 2:
+            return torch.view_as_complex(val).to(torch.complex64)
         return torch.view_as_complex(val.reshape(1, 2)).reshape(()).to(torch.complex64)
 
     @staticmethod
@@ -184,6 +198,8 @@ class _Expect(torch.autograd.Function):
         h: PauliStringSum = ctx.h
         # s = psi^H H psi:  grad_psi = conj(g) H psi + g H^dagger psi   (= 2 Re(g) H psi when H is Hermitian)
         hp, _ = h._launch(psi, True, False)
+        if psi.dim() == 2:
+            g = g.reshape(-1, 1)
         if h.hermitian:
             return (2.0 * g.real.to(torch.float32)) * hp, None
         hdp, _ = h.adjoint()._launch(psi, True, False)

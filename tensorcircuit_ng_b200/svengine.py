@@ -462,7 +462,8 @@ def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) 
     probe = [g[0]._lazy.theta if hasattr(g[0], "pending") and g[0].pending() else g[0].tensor for g in gates]
     device = pick_device(probe + ([init_node.tensor] if init_node is not None else []))
     structure = [(g[1], gate_kind(g[0], g[2]), int(math.prod(g[0].shape))) for g in gates]
-    cc = compile_circuit(n, structure, device, absorb_prefix=init_node is None)
+    batched = any(autograd.is_batched(t) for t in probe)
+    cc = compile_circuit(n, structure, device, absorb_prefix=init_node is None and not batched)
     if torch.is_grad_enabled():
         for g in gates:
             if len(g[1]) > 2 and not (hasattr(g[0], "pending") and g[0].pending()) and g[0].tensor.requires_grad:

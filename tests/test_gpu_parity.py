@@ -415,3 +415,69 @@ def test_vvag_tfim_vqe_batch(cuda):
         pm[l, k, q] -= eps
         fd = (ref(pp) - ref(pm)) / (2 * eps)
         assert abs(float(grads[b, l, k, q]) - fd) <= 3e-3, (b, l, k, q, float(grads[b, l, k, q]), fd)
+
+
+def test_vvag_batched_path_equals_loop(cuda):
+    """backend.vvag / vmap: one evaluation under torch.vmap with the kernels launched at batch = B gives the
+    values and per-sample gradients of the per-sample loop; functions outside the batched path fall back."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import backend
+
+    n, depth, B = 12, 2, 5
+    ls, ws = [], []
+    for q in range(n - 1):
+        t = [0] * n
+        t[q] = t[q + 1] = 3
+        ls.append(t)
+        ws.append(-1.0)
+    for q in range(n):
+        t = [0] * n
+        t[q] = 1
+        ls.append(t)
+        ws.append(-0.7)
+    ham = tc.quantum.PauliStringSum2COO(ls, ws)
+
+    def energy(p, shift):
+        c = tc.Circuit(n)
+        for q in range(n):
+            c.h(q)
+        for l in range(depth):
+            for q in range(n - 1):
+                c.rzz(q, q + 1, theta=p[l, 0, q] * 2.0)
+            c.cnot(0, 1)
+            for q in range(n):
+                c.rx(q, theta=p[l, 1, q] + shift)
+        return tc.templates.measurements.operator_expectation(c, ham)
+
+    torch.manual_seed(1)
+    p = 0.4 * torch.randn(B, depth, 2, n)
+    shift = torch.tensor(0.3)
+    old = backend.batched_mode
+    try:
+        backend.batched_mode = "strict"
+        v1, g1 = backend.vvag(energy, argnums=0, vectorized_argnums=0)(p, shift)
+        assert backend.last_vmap_path == "batched"
+        v1s, (g1p, g1s) = backend.vvag(energy, argnums=(0, 1), vectorized_argnums=0)(p, shift)
+        vm = backend.vmap(energy, vectorized_argnums=0)(p, shift)
+        backend.batched_mode = "loop"
+        v2, g2 = backend.vvag(energy, argnums=0, vectorized_argnums=0)(p, shift)
+        v2s, (g2p, g2s) = backend.vvag(energy, argnums=(0, 1), vectorized_argnums=0)(p, shift)
+        assert backend.last_vmap_path.startswith("loop")
+        backend.batched_mode = "auto"
+
+        def uses_item(x):  # data-dependent python: cannot be traced by vmap -> falls back to the loop
+            c = tc.Circuit(3)
+            c.rx(0, theta=float(x[0]))
+            return c.expectation_ps(z=[0]).real
+
+        out = backend.vmap(uses_item)(torch.tensor([[0.1], [0.2]]))
+        assert backend.last_vmap_path.startswith("loop") and tuple(out.shape) == (2,)
+    finally:
+        backend.batched_mode = old
+    assert tuple(v1.shape) == (B,) and tuple(g1.shape) == tuple(p.shape)
+    assert float((v1 - v2).abs().max()) < 2e-5 and float((vm - v2).abs().max()) < 2e-5
+    assert float((g1 - g2).abs().max()) < 5e-5
+    assert float((g1p - g2p).abs().max()) < 5e-5 and abs(float(g1s) - float(g2s)) < 2e-4  # shared arg: summed
+    assert float(g2.abs().max()) > 1e-2
