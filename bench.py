@@ -733,11 +733,12 @@ def run_vqe(args: argparse.Namespace) -> None:
         "dtype": "complex64",
         "data": "synthetic",
         "config": {"workload": f"tfim_vqe_n{n}_depth{depth}_vvag_batch{batch}", "gates_per_sample": n_gates,
-                   "value_definition": "forward gates x batch / s for one value_and_grad step (energy = one "
-                                       "Pauli-sum launch; backward = layered adjoint walk: runs of diagonal gates and "
-                                       "of one-qubit gates are differentiated from a few reads of psi and lambda and "
-                                       "un-applied as fused sub-circuits, other gates one fused launch each; vmap = "
-                                       "loop over the batch, host-bound)",
+                   "value_definition": "forward gates x batch / s for one value_and_grad step: ONE evaluation "
+                                       "under torch.vmap, kernels launched with batch = 64 (8 GiB of states); energy "
+                                       "= one Pauli-sum launch; backward = layered adjoint walk (runs of diagonal / "
+                                       "one-qubit gates differentiated from a few reads of psi and lambda, un-applied "
+                                       "as fused sub-circuits)",
+                   "vmap_path": tc.backend.last_vmap_path,
                    "energy_mean": float(vals.mean()), "grad_norm": float(grads.norm())},
         "roofline": None,
         "cpu_baseline": None,

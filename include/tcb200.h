@@ -127,17 +127,18 @@ int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
  * psi, lam the states after the run, dL/dd_j[c] = d_j[c] * out[j][c]):
  *   out[j][c] (complex128 pairs, +=) = sum over amplitudes i whose gate-j bits read c of lam[i] conj(psi[i]),
  * c = bit_a(i) for a one-qubit gate (gate_bits = {a, -1}), (bit_a(i) << 1) | bit_b(i) for two qubits; out has
- * 4 slots per gate.                                                                                      */
-int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int ngates, const int* gate_bits_host,
-                           double* out, void* stream);
+ * 4 slots per gate.
+ * batch: states [batch][2^nbits]; out_batch_stride in complex128 elements.                          */
+int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int64_t batch, int ngates,
+                           const int* gate_bits_host, double* out, int64_t out_batch_stride, void* stream);
 
 /* Cross reduced density matrices of single qubits between two states, up to 10 qubits per read of both:
  *   out[t][r][c] (complex128 pairs, +=) = sum_rest lam[rest, bit_t = r] conj(psi[rest, bit_t = c])
  * for the tile bits t = 0..min(3,nbits)-1 (the lowest address bits, always in the tile) followed by the nsel
  * (<= 7) selected bits (ascending, >= 3).  With lam, psi the states BEFORE a layer of one-qubit gates on
  * distinct qubits, dL/dU_q = U_q out[q] for every gate of the layer (same convention as tcb_sv_gate_grad). */
-int tcb_sv_cross_rdm(const void* lam, const void* psi, int nbits, int nsel, const int* sel_bits_host, double* out,
-                     void* stream);
+int tcb_sv_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch, int nsel, const int* sel_bits_host,
+                     double* out, int64_t out_batch_stride, void* stream);
 
 /* ---- statevector: sampling ------------------------------
  * Replaces probability() + cumsum + searchsorted of tensorcircuit/basecircuit.py:1490-1512 /

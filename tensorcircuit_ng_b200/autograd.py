@@ -90,16 +90,19 @@ class _DiagRun:
         self.sub_idx = torch.tensor(sub_idx, dtype=torch.long, device=device)
 
     def backward(self, nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor, g_all: torch.Tensor) -> None:
-        bins = torch.zeros(self.ngates * 4, 2, dtype=torch.float64, device=psi.device)
-        _lib.call("tcb_sv_cross_marginals", lam.data_ptr(), psi.data_ptr(), nbits, self.ngates, self.gate_bits,
-                  bins.data_ptr(), _lib.stream_ptr())  # fmt: skip
+        """lam, psi: [2^n] or a contiguous batch [B, 2^n]; dag [.., T], g_all [.., T, 2] likewise."""
+        nb = 1 if lam.dim() == 1 else int(lam.shape[0])
+        dag2, g2 = dag.reshape(nb, -1), g_all.reshape(nb, -1, 2)
+        bins = torch.zeros(nb, self.ngates * 4, 2, dtype=torch.float64, device=psi.device)
+        _lib.call("tcb_sv_cross_marginals", lam.data_ptr(), psi.data_ptr(), nbits, nb, self.ngates, self.gate_bits,
+                  bins.data_ptr(), self.ngates * 4, _lib.stream_ptr())  # fmt: skip
         # dL/dd_j[c] = d_j[c] * bins_j[c];  d_j[c] = conj(U^dagger[c, c])
-        dvals = dag[self.gidx].conj().to(torch.complex128)
+        dvals = dag2[:, self.gidx].conj().to(torch.complex128)
         grad = torch.view_as_real(dvals * torch.view_as_complex(bins))
-        g_all.index_put_((self.gidx[self.ok],), grad[self.ok], accumulate=True)
-        sub_gb = dag[self.sub_idx]
-        self.sub.run(psi, sub_gb)
-        self.sub.run(lam, sub_gb)
+        g2.index_add_(1, self.gidx[self.ok], grad[:, self.ok])
+        sub_gb = dag2[:, self.sub_idx].contiguous()
+        self.sub.run(psi, sub_gb, batch=nb, gate_batch_stride=int(sub_gb.shape[1]))
+        self.sub.run(lam, sub_gb, batch=nb, gate_batch_stride=int(sub_gb.shape[1]))
 
 
 class _OneQubitRun:
@@ -143,17 +146,21 @@ class _OneQubitRun:
         self.sub_idx = torch.tensor(sub_idx, dtype=torch.long, device=device)
 
     def backward(self, nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor, g_all: torch.Tensor) -> None:
-        sub_gb = dag[self.sub_idx]
-        self.sub.run(psi, sub_gb)  # psi_0, lam_0: the states before the run
-        self.sub.run(lam, sub_gb)
-        cr = torch.zeros(len(self.groups) * 40, 2, dtype=torch.float64, device=psi.device)
+        """lam, psi: [2^n] or a contiguous batch [B, 2^n]; dag [.., T], g_all [.., T, 2] likewise."""
+        nb = 1 if lam.dim() == 1 else int(lam.shape[0])
+        dag2, g2 = dag.reshape(nb, -1), g_all.reshape(nb, -1, 2)
+        sub_gb = dag2[:, self.sub_idx].contiguous()
+        self.sub.run(psi, sub_gb, batch=nb, gate_batch_stride=int(sub_gb.shape[1]))  # psi_0, lam_0: before the run
+        self.sub.run(lam, sub_gb, batch=nb, gate_batch_stride=int(sub_gb.shape[1]))
+        ng = len(self.groups)
+        cr = torch.zeros(nb, ng * 40, 2, dtype=torch.float64, device=psi.device)
         for gi, (nsel, sel) in enumerate(self.groups):
-            _lib.call("tcb_sv_cross_rdm", lam.data_ptr(), psi.data_ptr(), nbits, nsel, sel,
-                      cr.data_ptr() + gi * 40 * 16, _lib.stream_ptr())  # fmt: skip
-        c = torch.view_as_complex(cr[self.src]).reshape(self.m, 2, 2)
-        u = dag[self.dst].reshape(self.m, 2, 2).conj().transpose(1, 2).to(torch.complex128)  # U = (U^dagger)^dagger
-        g = torch.bmm(u, c).reshape(-1)
-        g_all.index_put_((self.dst,), torch.view_as_real(g), accumulate=True)
+            _lib.call("tcb_sv_cross_rdm", lam.data_ptr(), psi.data_ptr(), nbits, nb, nsel, sel,
+                      cr.data_ptr() + gi * 40 * 16, ng * 40, _lib.stream_ptr())  # fmt: skip
+        c = torch.view_as_complex(cr[:, self.src]).reshape(nb * self.m, 2, 2)
+        u = dag2[:, self.dst].reshape(nb * self.m, 2, 2).conj().transpose(1, 2).to(torch.complex128)  # (U^dagger)^dagger
+        g = torch.bmm(u, c).reshape(nb, -1)
+        g2.index_add_(1, self.dst, torch.view_as_real(g))
 
 
 class _AdjointTables:
@@ -336,8 +343,7 @@ class _EvolveBatched(torch.autograd.Function):
         src = torch.cat([gb.conj().resolve_conj(), torch.zeros(nb, 1, dtype=gb.dtype, device=gb.device)], dim=1)
         dag = src[:, tabs.dag_idx].contiguous()
         g_all = torch.zeros(nb, max(tabs.total, 1), 2, dtype=torch.float64, device=gb.device)
-        for b in range(nb):  # the walk itself is per sample (two states each); everything around it is batched
-            _walk(cc, tabs, nbits, lam[b], psi[b], dag[b], g_all[b])
+        _walk(cc, tabs, nbits, lam, psi, dag, g_all)
         grad_buf = torch.zeros(nb, nelem, 2, dtype=torch.float32, device=gb.device)
         grad_buf.index_add_(1, tabs.scat_dst, g_all[:, tabs.scat_src].to(torch.float32))
         return torch.view_as_complex(grad_buf), None
@@ -345,16 +351,25 @@ class _EvolveBatched(torch.autograd.Function):
 
 def _walk(cc: Any, tabs: "_AdjointTables", nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor,
           g_all: torch.Tensor) -> None:  # fmt: skip
-    """The adjoint walk over one sample: psi is un-computed in place, lam becomes the cotangent of the initial
-    state, g_all (float64 pairs, one dense block per gate) receives dL/dU."""
+    """The adjoint walk (one sample [2^n], or a contiguous batch [B, 2^n] walked together): psi is un-computed in
+    place, lam becomes the cotangent of the initial state, g_all (float64 pairs, one dense block per gate)
+    receives dL/dU."""
+
+    def plain(first: int, last: int) -> None:
+        if lam.dim() == 1:
+            cc.vjp(lam, psi, dag, g_all, first, last)
+        else:
+            for b in range(lam.shape[0]):
+                cc.vjp(lam[b], psi[b], dag[b], g_all[b], first, last)
+
     if layered_adjoint and len(tabs.segments) > 1:
         for seg in reversed(tabs.segments):
             if isinstance(seg, (_DiagRun, _OneQubitRun)):
                 seg.backward(nbits, lam, psi, dag, g_all)
             else:
-                cc.vjp(lam, psi, dag, g_all, seg[1], seg[2])
+                plain(seg[1], seg[2])
     else:
-        cc.vjp(lam, psi, dag, g_all)
+        plain(0, len(cc.ops))
 
 
 def evolve(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor, init: Optional[torch.Tensor]) -> torch.Tensor:

@@ -46,8 +46,8 @@ int launch_gate_grad(const void*, const void*, int, int64_t, const int*, int, vo
                      cudaStream_t);
 int launch_adjoint_step(void*, void*, int, int64_t, const int*, int, const void*, int64_t, void*, int64_t,
                         cudaStream_t);
-int launch_cross_marginals(const void*, const void*, int, int, const int*, double*, cudaStream_t);
-int launch_cross_rdm(const void*, const void*, int, int, const int*, double*, cudaStream_t);
+int launch_cross_marginals(const void*, const void*, int, int64_t, int, const int*, double*, int64_t, cudaStream_t);
+int launch_cross_rdm(const void*, const void*, int, int64_t, int, const int*, double*, int64_t, cudaStream_t);
 int launch_sample_prepare(const void*, int, int, double*, cudaStream_t);
 int launch_sample(const void*, int, int, const double*, const double*, int64_t, int, long long*, double*,
                   cudaStream_t);
@@ -187,22 +187,22 @@ int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
                              grad_batch_stride, S(stream));
 }
 
-int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int ngates, const int* gate_bits_host,
-                           double* out, void* stream) {
+int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int64_t batch, int ngates,
+                           const int* gate_bits_host, double* out, int64_t out_batch_stride, void* stream) {
   NOTNULL(lam, "tcb_sv_cross_marginals");
   NOTNULL(psi, "tcb_sv_cross_marginals");
   NOTNULL(out, "tcb_sv_cross_marginals");
   if (ngates > 0) NOTNULL(gate_bits_host, "tcb_sv_cross_marginals");
-  return launch_cross_marginals(lam, psi, nbits, ngates, gate_bits_host, out, S(stream));
+  return launch_cross_marginals(lam, psi, nbits, batch, ngates, gate_bits_host, out, out_batch_stride, S(stream));
 }
 
-int tcb_sv_cross_rdm(const void* lam, const void* psi, int nbits, int nsel, const int* sel_bits_host, double* out,
-                     void* stream) {
+int tcb_sv_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch, int nsel, const int* sel_bits_host,
+                     double* out, int64_t out_batch_stride, void* stream) {
   NOTNULL(lam, "tcb_sv_cross_rdm");
   NOTNULL(psi, "tcb_sv_cross_rdm");
   NOTNULL(out, "tcb_sv_cross_rdm");
   if (nsel > 0) NOTNULL(sel_bits_host, "tcb_sv_cross_rdm");
-  return launch_cross_rdm(lam, psi, nbits, nsel, sel_bits_host, out, S(stream));
+  return launch_cross_rdm(lam, psi, nbits, batch, nsel, sel_bits_host, out, out_batch_stride, S(stream));
 }
 
 int tcb_sv_sample_prepare(const void* state, int nbits, int seg_bits, double* cdf, void* stream) {

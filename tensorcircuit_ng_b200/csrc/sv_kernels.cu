@@ -1060,7 +1060,10 @@ struct CmGates {
 
 __global__ void __launch_bounds__(256)
 cross_marginals_kernel(const float4* __restrict__ lam, const float4* __restrict__ psi, uint64_t nvec, CmGates g,
-                       int ngates, double* out) {
+                       int ngates, double* out, long long out_bstride) {
+  lam += (size_t)blockIdx.y * nvec;
+  psi += (size_t)blockIdx.y * nvec;
+  out += (size_t)blockIdx.y * out_bstride;
   float2 acc[CM_G][4], acc2[CM_G][4];
 #pragma unroll
   for (int j = 0; j < CM_G; ++j)
@@ -1109,9 +1112,10 @@ cross_marginals_kernel(const float4* __restrict__ lam, const float4* __restrict_
   }
 }
 
-int launch_cross_marginals(const void* lam, const void* psi, int nbits, int ngates, const int* gate_bits,
-                           double* out, cudaStream_t stream) {
+int launch_cross_marginals(const void* lam, const void* psi, int nbits, int64_t batch, int ngates,
+                           const int* gate_bits, double* out, int64_t out_bstride, cudaStream_t stream) {
   TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_cross_marginals: nbits=%d", nbits);
+  TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_cross_marginals: batch=%lld", (long long)batch);
   TCB_REQUIRE(ngates >= 0, "tcb_sv_cross_marginals: ngates=%d", ngates);
   const uint64_t nvec = 1ull << (nbits - 1);
   for (int first = 0; first < ngates; first += CM_G) {
@@ -1124,8 +1128,10 @@ int launch_cross_marginals(const void* lam, const void* psi, int nbits, int ngat
       TCB_REQUIRE(g.a[j] >= 0 && g.a[j] < nbits && g.b[j] >= -1 && g.b[j] < nbits && g.a[j] != g.b[j],
                   "tcb_sv_cross_marginals: gate %d has bits (%d, %d)", src, g.a[j], g.b[j]);
     }
-    cross_marginals_kernel<<<grid_for(nvec, 256, 4), 256, 0, stream>>>(
-        reinterpret_cast<const float4*>(lam), reinterpret_cast<const float4*>(psi), nvec, g, cnt, out + 8 * first);
+    dim3 grid(grid_for(nvec, 256, 4), (unsigned)batch);
+    cross_marginals_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(lam),
+                                                     reinterpret_cast<const float4*>(psi), nvec, g, cnt,
+                                                     out + 8 * first, 2 * out_bstride);
     TCB_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -1146,7 +1152,11 @@ struct CrBits {
 };
 
 __global__ void __launch_bounds__(256)
-cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi, int nbits, CrBits cb, double* out) {
+cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi, int nbits, CrBits cb, double* out,
+                 long long out_bstride) {
+  lam += (size_t)blockIdx.y << nbits;
+  psi += (size_t)blockIdx.y << nbits;
+  out += (size_t)blockIdx.y * out_bstride;
   __shared__ float2 sl[1 << CR_MAXB], sp[1 << CR_MAXB];
   __shared__ double sacc[CR_MAXB * 4 * 2];
   const int tb = cb.nlow + cb.nsel;          // tile bits
@@ -1214,9 +1224,10 @@ cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi,
   for (int e = tid; e < tb * 8; e += blockDim.x) atomicAdd(out + e, sacc[e]);
 }
 
-int launch_cross_rdm(const void* lam, const void* psi, int nbits, int nsel, const int* sel_bits, double* out,
-                     cudaStream_t stream) {
+int launch_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch, int nsel, const int* sel_bits,
+                     double* out, int64_t out_bstride, cudaStream_t stream) {
   TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_cross_rdm: nbits=%d", nbits);
+  TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_cross_rdm: batch=%lld", (long long)batch);
   CrBits cb;
   cb.nlow = nbits < 3 ? nbits : 3;
   cb.nsel = nsel;
@@ -1230,8 +1241,10 @@ int launch_cross_rdm(const void* lam, const void* psi, int nbits, int nsel, cons
   const uint64_t ntiles = 1ull << (nbits - cb.nlow - nsel);
   uint64_t grid = (uint64_t)sm_count() * 4;
   if (grid > ntiles) grid = ntiles;
-  cross_rdm_kernel<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const float2*>(lam),
-                                                      reinterpret_cast<const float2*>(psi), nbits, cb, out);
+  if (batch > 1 && grid > (uint64_t)sm_count()) grid = sm_count();  // (batch rows share the SMs)
+  dim3 g2((unsigned)grid, (unsigned)batch);
+  cross_rdm_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const float2*>(lam), reinterpret_cast<const float2*>(psi),
+                                           nbits, cb, out, 2 * out_bstride);
   TCB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

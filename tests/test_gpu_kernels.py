@@ -224,8 +224,8 @@ def test_cross_marginals(cuda, n):
             gates.append((int(rng.integers(0, n)), -1))
     out = torch.zeros(len(gates) * 4, 2, dtype=torch.float64, device="cuda")
     lt, pt = torch.from_numpy(lam).cuda(), torch.from_numpy(psi).cuda()
-    _lib.call("tcb_sv_cross_marginals", lt.data_ptr(), pt.data_ptr(), n, len(gates),
-              _lib.int_array([x for g in gates for x in g]), out.data_ptr(), _lib.stream_ptr())  # fmt: skip
+    _lib.call("tcb_sv_cross_marginals", lt.data_ptr(), pt.data_ptr(), n, 1, len(gates),
+              _lib.int_array([x for g in gates for x in g]), out.data_ptr(), 0, _lib.stream_ptr())  # fmt: skip
     got = torch.view_as_complex(out).cpu().numpy().reshape(len(gates), 4)
     q = lam.astype(np.complex128) * np.conj(psi.astype(np.complex128))
     idx = np.arange(2**n)
@@ -248,8 +248,8 @@ def test_cross_rdm(cuda, n, sel):
     bits = list(range(low)) + sel
     out = torch.zeros(40, 2, dtype=torch.float64, device="cuda")
     lt, pt = torch.from_numpy(lam).cuda(), torch.from_numpy(psi).cuda()
-    _lib.call("tcb_sv_cross_rdm", lt.data_ptr(), pt.data_ptr(), n, len(sel), _lib.int_array(sel) if sel else None,
-              out.data_ptr(), _lib.stream_ptr())  # fmt: skip
+    _lib.call("tcb_sv_cross_rdm", lt.data_ptr(), pt.data_ptr(), n, 1, len(sel), _lib.int_array(sel) if sel else None,
+              out.data_ptr(), 0, _lib.stream_ptr())  # fmt: skip
     got = torch.view_as_complex(out).cpu().numpy().reshape(10, 2, 2)
     L = lam.astype(np.complex128).reshape([2] * n)
     P = psi.astype(np.complex128).reshape([2] * n)
