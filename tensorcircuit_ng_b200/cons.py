@@ -206,7 +206,16 @@ def _finalize(nodes: Sequence[Any], tensor: torch.Tensor, tensor_edges: Sequence
 
 
 # ---- [psi, psi*, ops...] networks (tensorcircuit/basecircuit.py:393-447) ---------------------
+def _phys(t: torch.Tensor) -> torch.Tensor:
+    """The physical tensor behind a torch.vmap batched tensor (storage identity / conj bit live there)."""
+    f = torch._C._functorch
+    while isinstance(t, torch.Tensor) and f.is_batchedtensor(t):
+        t = f.get_unwrapped(t)
+    return t
+
+
 def _same_storage_conj(a: torch.Tensor, b: torch.Tensor) -> bool:
+    a, b = _phys(a), _phys(b)
     if a.shape != b.shape or a.is_conj() == b.is_conj():
         return False
     pa, pb = (a.conj() if a.is_conj() else a), (b.conj() if b.is_conj() else b)
@@ -220,7 +229,7 @@ def _recognize_expectation(nodes: Sequence[Any]):
     if any(_is_copynode(x) for x in nodes):
         return None
     # the bra is the lazily conjugated view of the ket's storage (tn.Node.copy(conjugate=True))
-    bra = next((x for x in nodes if x.tensor.is_conj()), None)
+    bra = next((x for x in nodes if _phys(x.tensor).is_conj()), None)
     if bra is None:
         return None
     ket = next((x for x in nodes if x is not bra and _same_storage_conj(x.tensor, bra.tensor)), None)
@@ -275,7 +284,7 @@ def _z_moment(ket: torch.Tensor, n: int, zq: Sequence[int]) -> Optional[torch.Te
     queries are lookups.  Worst case (exactly two queries): ~10 reads instead of 2."""
     from . import expect
 
-    if not speculate_z_moments or n < 2 or n > 40 or not ket.is_cuda:
+    if not speculate_z_moments or n < 2 or n > 40 or not ket.is_cuda or _phys(ket) is not ket:
         return None
     cache = getattr(ket, "_b200_zcache", None)
     if cache is None or cache["version"] != ket._version:

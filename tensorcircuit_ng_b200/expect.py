@@ -28,24 +28,31 @@ def _mask(n: int, axes: Sequence[int]) -> int:
 
 
 def _apply_dense(state: torch.Tensor, n: int, axes: Sequence[int], mat: torch.Tensor) -> None:
+    """In place on one state [2^n] or a contiguous batch [B, 2^n] (the same matrix for every member)."""
     bp = _lib.int_array([n - 1 - a for a in axes])
     m = mat.to(torch.complex64).resolve_conj().contiguous()
-    _lib.call("tcb_sv_apply_dense", state.data_ptr(), n, 1, bp, len(axes), m.data_ptr(), 0, _lib.stream_ptr())
+    nb = 1 if state.dim() == 1 else int(state.shape[0])
+    _lib.call("tcb_sv_apply_dense", state.data_ptr(), n, nb, bp, len(axes), m.data_ptr(), 0, _lib.stream_ptr())
 
 
 def _pauli_raw(psi: torch.Tensor, n: int, xs: Sequence[int], ys: Sequence[int], zs: Sequence[int]) -> torch.Tensor:
+    """psi [2^n] -> complex64 scalar; a contiguous batch [B, 2^n] -> [B]."""
     _lib.require_cuda(psi, "state")
     psi = psi.resolve_conj().contiguous()
-    out = torch.zeros(2, dtype=torch.float64, device=psi.device)
+    nb = 1 if psi.dim() == 1 else int(psi.shape[0])
     xm = _mask(n, list(xs) + list(ys))
     zm = _mask(n, list(zs) + list(ys))
     if xm == 0:
+        out = torch.zeros(nb, dtype=torch.float64, device=psi.device)  # a Z string: real, one slot per member
         zmask = torch.tensor([zm], dtype=torch.int64, device=psi.device)
-        _lib.call("tcb_sv_expect_z", psi.data_ptr(), n, 1, zmask.data_ptr(), 1, 0, out.data_ptr(), _lib.stream_ptr())
+        _lib.call("tcb_sv_expect_z", psi.data_ptr(), n, nb, zmask.data_ptr(), 1, 0, out.data_ptr(), _lib.stream_ptr())
+        res = out.to(torch.complex64)
     else:
-        _lib.call("tcb_sv_expect_pauli", psi.data_ptr(), n, 1, xm, zm, len(ys), 0, out.data_ptr(),
+        out = torch.zeros(nb, 2, dtype=torch.float64, device=psi.device)
+        _lib.call("tcb_sv_expect_pauli", psi.data_ptr(), n, nb, xm, zm, len(ys), 0, out.data_ptr(),
                   _lib.stream_ptr())  # fmt: skip
-    return torch.view_as_complex(out.reshape(1, 2)).reshape(()).to(torch.complex64)
+        res = torch.view_as_complex(out).to(torch.complex64)
+    return res if psi.dim() == 2 else res.reshape(())
 
 
 def _apply_pauli(psi: torch.Tensor, n: int, xs: Sequence[int], ys: Sequence[int], zs: Sequence[int]) -> torch.Tensor:
@@ -69,11 +76,24 @@ class _PauliExpect(torch.autograd.Function):
         n, xs, ys, zs = ctx.meta
         # s = psi^H P psi, P Hermitian:  grad_psi = conj(g) P psi + g P^H psi = 2 Re(g) P psi
         ppsi = _apply_pauli(psi, n, xs, ys, zs)
+        if psi.dim() == 2:
+            g = g.reshape(-1, 1)
         return (2.0 * g.real.to(torch.float32)) * ppsi, None, None, None, None
 
 
 def pauli_expectation(psi: torch.Tensor, n: int, xs: Sequence[int], ys: Sequence[int], zs: Sequence[int]) -> torch.Tensor:
     """<psi| X_xs Y_ys Z_zs |psi> as a complex64 scalar tensor (abstractcircuit.py:1523-1603)."""
+    from . import autograd
+
+    if autograd.is_batched(psi):  # under torch.vmap: one launch for the whole batch
+        phys, lvl = autograd.unwrap_batched(psi)
+        with autograd.outside_vmap():
+            p2 = phys.to(torch.complex64).resolve_conj().reshape(phys.shape[0], -1).contiguous()
+            if p2.requires_grad and torch.is_grad_enabled():
+                out = _PauliExpect.apply(p2, n, tuple(xs), tuple(ys), tuple(zs))
+            else:
+                out = _pauli_raw(p2, n, xs, ys, zs)
+        return autograd.rewrap_batched(out, lvl)
     if psi.requires_grad and torch.is_grad_enabled():
         return _PauliExpect.apply(psi, n, tuple(xs), tuple(ys), tuple(zs))
     return _pauli_raw(psi, n, xs, ys, zs)

@@ -481,3 +481,48 @@ def test_vvag_batched_path_equals_loop(cuda):
     assert float((g1 - g2).abs().max()) < 5e-5
     assert float((g1p - g2p).abs().max()) < 5e-5 and abs(float(g1s) - float(g2s)) < 2e-4  # shared arg: summed
     assert float(g2.abs().max()) > 1e-2
+
+
+def test_vmap_batches_expectation_ps_circuits(cuda):
+    """The QML pattern (tests/test_torchnn.py:21-49 of the reference): per-qubit expectation_ps read-outs of a
+    data-encoding circuit, batched over the data — one torch.vmap evaluation == the per-sample loop, values and
+    weight gradients."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import backend
+
+    n, nlayers, B = 6, 2, 4
+
+    def qpred(x, weights):
+        c = tc.Circuit(n)
+        for i in range(n):
+            c.rx(i, theta=x[i])
+        for j in range(nlayers):
+            for i in range(n - 1):
+                c.cnot(i, i + 1)
+            for i in range(n):
+                c.rx(i, theta=weights[2 * j, i])
+                c.ry(i, theta=weights[2 * j + 1, i])
+        outs = [c.expectation_ps(x=[i]) for i in range(n)] + [c.expectation_ps(z=[0, 1]), c.expectation_ps(y=[2], z=[3])]
+        return tc.backend.real(tc.backend.stack(outs))
+
+    torch.manual_seed(3)
+    xs = torch.rand(B, n)
+    w = torch.randn(2 * nlayers, n)
+    old = backend.batched_mode
+    try:
+        backend.batched_mode = "strict"
+        y1 = backend.vmap(qpred, vectorized_argnums=0)(xs, w)
+        loss = lambda xx, ww: qpred(xx, ww).sum()  # noqa: E731
+        v1, g1 = backend.vvag(loss, argnums=1, vectorized_argnums=0)(xs, w)
+        assert backend.last_vmap_path == "batched"
+        backend.batched_mode = "loop"
+        y2 = backend.vmap(qpred, vectorized_argnums=0)(xs, w)
+        v2, g2 = backend.vvag(loss, argnums=1, vectorized_argnums=0)(xs, w)
+    finally:
+        backend.batched_mode = old
+    assert tuple(y1.shape) == (B, n + 2)
+    assert float((y1 - y2).abs().max()) < 1e-5
+    assert float((v1 - v2).abs().max()) < 1e-5 and float((g1 - g2).abs().max()) < 5e-5
+    assert float(g2.abs().max()) > 1e-2
