@@ -387,13 +387,14 @@ def exponential_gate(unitary: Any, theta: float, name: str = "none") -> Gate:  #
 
 def exponential_gate_unity(unitary: Any, theta: float, half: bool = False, name: str = "none") -> Gate:
     """cos(theta) I - i sin(theta) U for U^2 = I (gates.py:920-953)."""
-    kind = _probe_kind(unitary)
     if _lazy_ok(theta) and isinstance(unitary, np.ndarray) and unitary.size <= 256:
         n = int(round(math.log2(unitary.size)))
         key = ("exp1", unitary.shape, unitary.dtype.str, unitary.tobytes(), bool(half))
-        fam = TrigFamily.get(key, lambda: TrigFamily(_eye_for(n), -1.0j * unitary, 0.5 if half is True else 1.0, kind))
+        fam = TrigFamily.get(key, lambda: TrigFamily(_eye_for(n), -1.0j * unitary, 0.5 if half is True else 1.0,
+                                                     _probe_kind(unitary)))  # fmt: skip  (structure probed once per family)
         g = LazyGate(_LazySpec(fam, theta), name="exp1-" + name)
         return g
+    kind = _probe_kind(unitary)
     th = _scalar(theta)
     u = _const(unitary, _dev(th)) if isinstance(unitary, np.ndarray) else num_to_tensor(unitary)
     n = int(round(math.log2(u.numel())))

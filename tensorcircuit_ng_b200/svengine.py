@@ -59,6 +59,8 @@ def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any],
     if n == 0 or n > max_qubits:
         raise NotCircuitShaped("no dangling outputs" if n == 0 else "too many qubits for a statevector")
     node_ids = {id(x) for x in nodes}
+    # classify every node once (the wire walk below visits a gate once per leg)
+    cls: Dict[int, Tuple[bool, bool, int]] = {id(x): (_is_copynode(x), _is_input_node(x), x.get_rank()) for x in nodes}
     legs: Dict[int, List[Optional[int]]] = {}
     gate_nodes: Dict[int, Any] = {}
     diag_legs: Dict[int, List[Optional[int]]] = {}
@@ -76,10 +78,11 @@ def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any],
                 raise NotCircuitShaped("wire walk did not terminate")
             if id(node) not in node_ids:
                 raise NotCircuitShaped("wire leaves the node set")
-            if _is_copynode(node):
+            is_copy, is_input, r = cls[id(node)]
+            if is_copy:
                 # diagonal gate in hyperedge form (tensorcircuit/basecircuit.py:343-355):
                 # cn[0] <- previous front, cn[1] <-> coefficient leg, cn[2] -> next
-                if node.get_rank() != 3 or axis != 2:
+                if r != 3 or axis != 2:
                     raise NotCircuitShaped("unsupported CopyNode wiring")
                 coef, cax = _other_end(node.edges[1], node, 1)
                 if coef is None or _is_copynode(coef):
@@ -94,8 +97,8 @@ def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any],
                     raise NotCircuitShaped("dangling CopyNode input")
                 node, axis = _other_end(prev, node, 0)
                 continue
-            if _is_input_node(node):
-                if node.get_rank() == 1 and str(getattr(node, "name", "")).startswith("qb-"):
+            if is_input:
+                if r == 1 and str(getattr(node, "name", "")).startswith("qb-"):
                     n_zero_inputs += 1  # |0> leaf of all_zero_nodes (basecircuit.py:52-66)
                 else:
                     if init_node is not None and init_node is not node:
@@ -107,7 +110,6 @@ def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any],
                     raise NotCircuitShaped("input leg reached twice")
                 visited_inputs.add((id(node), axis))
                 break
-            r = node.get_rank()
             if r % 2:
                 raise NotCircuitShaped("odd-rank node on a wire")
             k = r // 2
@@ -130,7 +132,7 @@ def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any],
     seen = set(legs) | set(diag_legs)
     gates: List[Tuple[Any, Tuple[int, ...], bool]] = []
     for x in nodes:
-        if _is_copynode(x) or _is_input_node(x):
+        if cls[id(x)][0] or cls[id(x)][1]:
             continue
         if id(x) not in seen:
             raise NotCircuitShaped("node not on any wire")
