@@ -35,6 +35,21 @@ def _apply_dense(state: torch.Tensor, n: int, axes: Sequence[int], mat: torch.Te
     _lib.call("tcb_sv_apply_dense", state.data_ptr(), n, nb, bp, len(axes), m.data_ptr(), 0, _lib.stream_ptr())
 
 
+_single_masks: dict = {}
+
+
+def _single_mask(zm: int, device: torch.device) -> torch.Tensor:
+    """A one-element device mask table, uploaded once: a host->device copy of a fresh tensor would make every
+    expectation call wait for the circuit's passes (the copy is stream-ordered behind them)."""
+    key = (zm, str(device))
+    t = _single_masks.get(key)
+    if t is None:
+        if len(_single_masks) > 4096:
+            _single_masks.clear()
+        t = _single_masks[key] = torch.tensor([zm], dtype=torch.int64, device=device)
+    return t
+
+
 def _pauli_raw(psi: torch.Tensor, n: int, xs: Sequence[int], ys: Sequence[int], zs: Sequence[int]) -> torch.Tensor:
     """psi [2^n] -> complex64 scalar; a contiguous batch [B, 2^n] -> [B]."""
     _lib.require_cuda(psi, "state")
@@ -44,7 +59,7 @@ def _pauli_raw(psi: torch.Tensor, n: int, xs: Sequence[int], ys: Sequence[int], 
     zm = _mask(n, list(zs) + list(ys))
     if xm == 0:
         out = torch.zeros(nb, dtype=torch.float64, device=psi.device)  # a Z string: real, one slot per member
-        zmask = torch.tensor([zm], dtype=torch.int64, device=psi.device)
+        zmask = _single_mask(zm, psi.device)
         _lib.call("tcb_sv_expect_z", psi.data_ptr(), n, nb, zmask.data_ptr(), 1, 0, out.data_ptr(), _lib.stream_ptr())
         res = out.to(torch.complex64)
     else:

@@ -80,7 +80,7 @@ def test_expectation_kernels(cuda, n):
     p = np.abs(psi.astype(np.complex128)) ** 2
     idx = np.arange(2**n)
     # (n = 17 asks for more terms than one launch of the kernel carries: exercises the chunking)
-    nterms = 150 if n == 17 else min(37, 3 * n)
+    nterms = 400 if n == 17 else min(37, 3 * n)
     terms = [[int(q) for q in rng.permutation(n)[: int(rng.integers(1, min(n, 4) + 1))]] for _ in range(nterms)]
     got = expect.z_expectations(st, n, terms).cpu().numpy()
     for t, g in zip(terms, got):
