@@ -240,6 +240,12 @@ class Circuit:
             if t is None:
                 nodes, d_edges = self._copy()
                 t = contractor(nodes, output_edge_order=d_edges)
+                try:  # which qubit pairs the circuit couples: a hint for the Z-moment table (cons._z_moment)
+                    t.tensor._b200_pair_hint = {  # type: ignore[attr-defined]
+                        (min(d["index"]), max(d["index"])) for d in self._qir if len(d["index"]) == 2
+                    }
+                except Exception:  # pylint: disable=broad-except  (wrapper tensors)
+                    pass
                 setattr(self, "state_tensor", t)
             ndict, edict = tn.copy([t], conjugate=conj)
             return [ndict[t]], [edict[e] for e in t.edges]

@@ -288,19 +288,34 @@ def _z_moment(ket: torch.Tensor, n: int, zq: Sequence[int]) -> Optional[torch.Te
         return None
     cache = getattr(ket, "_b200_zcache", None)
     if cache is None or cache["version"] != ket._version:
-        cache = {"version": ket._version, "count": 0, "table": None, "index": None}
+        cache = {"version": ket._version, "count": 0, "tables": []}
         try:
             ket._b200_zcache = cache  # type: ignore[attr-defined]
         except Exception:  # pylint: disable=broad-except  (wrapper tensors)
             return None
     cache["count"] += 1
-    if cache["table"] is None:
-        if cache["count"] < 2:
-            return None
-        terms = [[i] for i in range(n)] + [[i, j] for i in range(n) for j in range(i + 1, n)]
-        cache["index"] = {tuple(t): k for k, t in enumerate(terms)}
-        cache["table"] = expect.z_expectations(ket.reshape(-1), n, terms).to(torch.complex64)
-    return cache["table"][cache["index"][tuple(zq)]]
+    key = tuple(zq)
+    for index, table in cache["tables"]:
+        if key in index:
+            return table[index[key]]
+    if cache["count"] < 2:
+        return None
+
+    def build(terms: List[List[int]]) -> torch.Tensor:
+        index = {tuple(t): k for k, t in enumerate(terms)}
+        table = expect.z_expectations(ket.reshape(-1), n, terms).to(torch.complex64)
+        cache["tables"].append((index, table))
+        return table[index[key]]
+
+    # first table: every single qubit + the pairs the circuit itself couples (the terms of a VQE / QAOA energy
+    # usually follow the circuit's connectivity; hint left on the state by Circuit._copy_state_tensor) — one or
+    # two reads; a query outside it pays for the full table of all pairs
+    hint = getattr(ket, "_b200_pair_hint", None)
+    if not cache["tables"] and hint:
+        terms = [[i] for i in range(n)] + [list(p) for p in sorted(hint) if 0 <= p[0] < p[1] < n]
+        if key in {tuple(t) for t in terms} and len(terms) < n + n * (n - 1) // 4:
+            return build(terms)
+    return build([[i] for i in range(n)] + [[i, j] for i in range(n) for j in range(i + 1, n)])
 
 
 def _expectation_value(ket: torch.Tensor, n: int, ops: Sequence[Tuple[Any, Tuple[int, ...]]]) -> torch.Tensor:

@@ -526,3 +526,41 @@ def test_vmap_batches_expectation_ps_circuits(cuda):
     assert float((y1 - y2).abs().max()) < 1e-5
     assert float((v1 - v2).abs().max()) < 1e-5 and float((g1 - g2).abs().max()) < 5e-5
     assert float(g2.abs().max()) > 1e-2
+
+
+def test_z_moment_tables_follow_circuit_couplings(cuda):
+    """Repeated <Z_i>, <Z_i Z_j> queries on one state: the first is a direct reduction, the second builds the table
+    of the circuit's own couplings, a pair outside it builds the full table — every answer equals the oracle's."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import cons
+
+    n = 9
+    rng = np.random.default_rng(11)
+    th = rng.uniform(0, 2 * np.pi, size=(3, n))
+
+    def build(mod):
+        c = mod.Circuit(n)
+        for q in range(n):
+            c.h(q)
+        for l in range(3):
+            for q in range(n - 1):
+                c.rzz(q, q + 1, theta=float(th[l, q]))
+            for q in range(n):
+                c.rx(q, theta=float(th[l, (q + 1) % n]))
+        return c
+
+    c, oc = build(tc), build(tc_oracle)
+    queries = [[0, 1], [3, 4], [5], [7, 8], [2, 3], [0, 5], [1, 7], [4], [6, 8]]  # [0,5], [1,7], [6,8]: not coupled
+    with torch.no_grad():
+        for zq in queries:
+            got = float(c.expectation_ps(z=zq).real)
+            want = float(np.real(oc.expectation_ps(z=zq)))
+            assert abs(got - want) < 2e-6, zq
+    state = c._copy_state_tensor()[0][0].tensor
+    src = c.state_tensor.tensor
+    cache = getattr(src, "_b200_zcache", None)
+    assert cache is not None and len(cache["tables"]) == 2
+    assert len(cache["tables"][0][0]) == n + (n - 1) and len(cache["tables"][1][0]) == n + n * (n - 1) // 2
+    assert cons.speculate_z_moments
