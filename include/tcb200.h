@@ -125,7 +125,7 @@ int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
 
 /* Gradients of a run of consecutive DIAGONAL gates from one read of the two states (they commute: with
  * psi, lam the states after the run, dL/dd_j[c] = d_j[c] * out[j][c]):
- *   out[j][c] (complex128 pairs, +=) = sum over amplitudes i whose gate-j bits read c of lam[i] conj(psi[i]),
+ *   out[j][c] (complex128 pairs, =) = sum over amplitudes i whose gate-j bits read c of lam[i] conj(psi[i]),
  * c = bit_a(i) for a one-qubit gate (gate_bits = {a, -1}), (bit_a(i) << 1) | bit_b(i) for two qubits; out has
  * 4 slots per gate.
  * batch: states [batch][2^nbits]; out_batch_stride in complex128 elements.                          */

@@ -1050,65 +1050,126 @@ int launch_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
 // Gradients of a RUN of consecutive diagonal gates in one read of the two states.  Diagonal gates commute,
 // so with psi_L / lam_L the states AFTER the run,  dL/dd_j[c] = d_j[c] * sum_{i in c} lam_L[i] conj(psi_L[i])
 // for every gate j of the run (unit-modulus d): the only state-sized work is the marginal of the
-// elementwise product over the gate's one or two bits.  Up to CM_G gates per launch (register bins,
+// elementwise product over the gate's one or two bits.  Up to CM_G gates per launch (moment sums,
 // predicated adds; two-level float accumulation, double across threads).
 constexpr int CM_G = 8;
 
 struct CmGates {
-  int a[CM_G], b[CM_G];  // bit of matrix-index MSB / LSB; b = -1 for a one-qubit gate
+  int a[CM_G], b[CM_G];  // bit of matrix-index MSB / LSB; a = -1 for a one-qubit gate (its bit is the LSB)
 };
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float2 cm_flip(float2 v, unsigned sign_bit) {  // sign_bit: 0 or 0x80000000
+  return make_float2(__uint_as_float(__float_as_uint(v.x) ^ sign_bit), __uint_as_float(__float_as_uint(v.y) ^ sign_bit));
+}
+
+// Accumulates the +-1 MOMENTS of q = lam * conj(psi) per gate (M_a, M_b, M_ab; M_0 = sum q is shared) instead of
+// the four bins: a sign flip and three complex adds per gate per PAIR of amplitudes (the two amplitudes of a
+// 16-byte load share every sign except bit 0's), and the launcher's epilogue kernel turns moments into bins.
+__global__ void __launch_bounds__(256, 2)
 cross_marginals_kernel(const float4* __restrict__ lam, const float4* __restrict__ psi, uint64_t nvec, CmGates g,
-                       int ngates, double* out, long long out_bstride) {
+                       int ngates, double* mom, long long mom_bstride) {
   lam += (size_t)blockIdx.y * nvec;
   psi += (size_t)blockIdx.y * nvec;
-  out += (size_t)blockIdx.y * out_bstride;
-  float2 acc[CM_G][4], acc2[CM_G][4];
+  mom += (size_t)blockIdx.y * mom_bstride;
+  // first-level sums in registers, second level per thread in shared memory ([slot][thread], conflict-free)
+  extern __shared__ float cm_acc2[];
+  float2 acc[CM_G][3], m0 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < CM_G; ++j)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[j][c] = acc2[j][c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < 3; ++c) acc[j][c] = make_float2(0.f, 0.f);
+  for (int e = 0; e < CM_G * 6 + 2; ++e) cm_acc2[e * 256 + threadIdx.x] = 0.f;
   int cnt = 0;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nvec; p += stride) {
-    const float4 l = ldg_stream(lam + p), s = ldg_stream(psi + p);
-    // q = lam * conj(psi) for the two amplitudes 2p, 2p + 1
-    const float2 q0 = make_float2(l.x * s.x + l.y * s.y, l.y * s.x - l.x * s.y);
-    const float2 q1 = make_float2(l.z * s.z + l.w * s.w, l.w * s.z - l.z * s.w);
-    const uint64_t i0 = p << 1;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 2;
+  for (uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; p0 < nvec; p0 += stride) {
+    float4 l[2], s[2];
 #pragma unroll
-    for (int j = 0; j < CM_G; ++j) {
-      const int hi0 = (int)((i0 >> g.a[j]) & 1ull), hi1 = g.a[j] == 0 ? 1 : hi0;
-      const int lo0 = g.b[j] < 0 ? 0 : (int)((i0 >> g.b[j]) & 1ull), lo1 = g.b[j] == 0 ? 1 : lo0;
-      const int c0 = g.b[j] < 0 ? hi0 : (hi0 << 1) | lo0, c1 = g.b[j] < 0 ? hi1 : (hi1 << 1) | lo1;
+    for (int k = 0; k < 2; ++k) {  // four independent 16-byte loads in flight
+      const bool ok = p0 + k < nvec;
+      l[k] = ok ? ldg_stream(lam + p0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s[k] = ok ? ldg_stream(psi + p0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        acc[j][c].x += (c == c0 ? q0.x : 0.f) + (c == c1 ? q1.x : 0.f);
-        acc[j][c].y += (c == c0 ? q0.y : 0.f) + (c == c1 ? q1.y : 0.f);
+    for (int k = 0; k < 2; ++k) {
+      // q = lam * conj(psi) for the two amplitudes 2p, 2p + 1; their sum and difference
+      const float2 q0 = make_float2(l[k].x * s[k].x + l[k].y * s[k].y, l[k].y * s[k].x - l[k].x * s[k].y);
+      const float2 q1 = make_float2(l[k].z * s[k].z + l[k].w * s[k].w, l[k].w * s[k].z - l[k].z * s[k].w);
+      const float2 qs = make_float2(q0.x + q1.x, q0.y + q1.y), qd = make_float2(q0.x - q1.x, q0.y - q1.y);
+      m0.x += qs.x;
+      m0.y += qs.y;
+      const uint64_t i0 = (p0 + k) << 1;
+#pragma unroll
+      for (int j = 0; j < CM_G; ++j) {
+        const int a = g.a[j], b = g.b[j];
+        const unsigned sa = a > 0 ? (unsigned)((i0 >> a) & 1ull) << 31 : 0u;
+        const unsigned sb = b > 0 ? (unsigned)((i0 >> b) & 1ull) << 31 : 0u;
+        const float2 ua = a == 0 ? qd : cm_flip(qs, sa);
+        const float2 ub = b == 0 ? qd : cm_flip(qs, sb);
+        const float2 uab = (a == 0 || b == 0) ? cm_flip(qd, sa ^ sb) : cm_flip(qs, sa ^ sb);
+        acc[j][0].x += ua.x;  acc[j][0].y += ua.y;
+        acc[j][1].x += ub.x;  acc[j][1].y += ub.y;
+        acc[j][2].x += uab.x; acc[j][2].y += uab.y;
       }
     }
-    if ((++cnt & 31) == 0) {
+    if ((++cnt & 15) == 0) {
+      cm_acc2[(CM_G * 6) * 256 + threadIdx.x] += m0.x;
+      cm_acc2[(CM_G * 6 + 1) * 256 + threadIdx.x] += m0.y;
+      m0 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < CM_G; ++j)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          acc2[j][c].x += acc[j][c].x;
-          acc2[j][c].y += acc[j][c].y;
+        for (int c = 0; c < 3; ++c) {
+          cm_acc2[((j * 3 + c) * 2) * 256 + threadIdx.x] += acc[j][c].x;
+          cm_acc2[((j * 3 + c) * 2 + 1) * 256 + threadIdx.x] += acc[j][c].y;
           acc[j][c] = make_float2(0.f, 0.f);
         }
     }
   }
+  const float2 m02 = make_float2(cm_acc2[(CM_G * 6) * 256 + threadIdx.x], cm_acc2[(CM_G * 6 + 1) * 256 + threadIdx.x]);
+  // moments of gate j at mom[4 j + {0: M_0, 1: M_b, 2: M_a, 3: M_ab}] (index = (sa << 1) | sb)
+  __shared__ double s0[2];
+  if (threadIdx.x == 0) s0[0] = s0[1] = 0.0;
+  __syncthreads();
+  block_reduce_add2((double)m02.x + (double)m0.x, (double)m02.y + (double)m0.y, s0);
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < CM_G; ++j) {
     if (j < ngates) {  // (uniform)
+      if (threadIdx.x == 0) {
+        atomicAdd(mom + 2 * (4 * j), s0[0]);
+        atomicAdd(mom + 2 * (4 * j) + 1, s0[1]);
+      }
+      const int slot[3] = {2, 1, 3};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        block_reduce_add2((double)acc2[j][c].x + (double)acc[j][c].x, (double)acc2[j][c].y + (double)acc[j][c].y,
-                          out + 2 * (4 * j + c));
+      for (int c = 0; c < 3; ++c) {
+        block_reduce_add2((double)cm_acc2[((j * 3 + c) * 2) * 256 + threadIdx.x] + (double)acc[j][c].x,
+                          (double)cm_acc2[((j * 3 + c) * 2 + 1) * 256 + threadIdx.x] + (double)acc[j][c].y,
+                          mom + 2 * (4 * j + slot[c]));
         __syncthreads();
       }
     }
+  }
+}
+
+// moments -> bins, in place: bins[(ca << 1) | cb] = 1/4 sum_{sa, sb} (-1)^(ca sa + cb sb) M[(sa << 1) | sb]
+__global__ void cm_moments_to_bins_kernel(double* mom, int ngates_total) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ngates_total) return;
+  double* m = mom + 8 * (size_t)j;
+  double re[4], im[4];
+  for (int s = 0; s < 4; ++s) {
+    re[s] = m[2 * s];
+    im[s] = m[2 * s + 1];
+  }
+  for (int c = 0; c < 4; ++c) {
+    double r = 0.0, i = 0.0;
+    for (int s = 0; s < 4; ++s) {
+      const double sg = (__popc(c & s) & 1) ? -0.25 : 0.25;
+      r += sg * re[s];
+      i += sg * im[s];
+    }
+    m[2 * c] = r;
+    m[2 * c + 1] = i;
   }
 }
 
@@ -1117,23 +1178,44 @@ int launch_cross_marginals(const void* lam, const void* psi, int nbits, int64_t 
   TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_cross_marginals: nbits=%d", nbits);
   TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_cross_marginals: batch=%lld", (long long)batch);
   TCB_REQUIRE(ngates >= 0, "tcb_sv_cross_marginals: ngates=%d", ngates);
+  TCB_REQUIRE(batch == 1 || out_bstride == (int64_t)4 * ngates,
+              "tcb_sv_cross_marginals: batched output must be dense (out_batch_stride = 4 * ngates)");
+  if (ngates == 0) return 0;
+  // The kernels accumulate moments and convert them to bins IN PLACE, so `out` must start from zero for this
+  // call: a scratch-free contract that the += of the header would break; enforce by clearing here.
+  TCB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 8 * (size_t)ngates * (size_t)batch, stream));
   const uint64_t nvec = 1ull << (nbits - 1);
   for (int first = 0; first < ngates; first += CM_G) {
     const int cnt = ngates - first < CM_G ? ngates - first : CM_G;
     CmGates g;
     for (int j = 0; j < CM_G; ++j) {
-      const int src = first + (j < cnt ? j : 0);  // padding repeats a real gate; its bins are not written
-      g.a[j] = gate_bits[2 * src];
-      g.b[j] = gate_bits[2 * src + 1];
-      TCB_REQUIRE(g.a[j] >= 0 && g.a[j] < nbits && g.b[j] >= -1 && g.b[j] < nbits && g.a[j] != g.b[j],
-                  "tcb_sv_cross_marginals: gate %d has bits (%d, %d)", src, g.a[j], g.b[j]);
+      const int src = first + (j < cnt ? j : 0);  // padding repeats a real gate; its moments are not written
+      int a = gate_bits[2 * src], b = gate_bits[2 * src + 1];
+      TCB_REQUIRE(a >= 0 && a < nbits && b >= -1 && b < nbits && a != b,
+                  "tcb_sv_cross_marginals: gate %d has bits (%d, %d)", src, a, b);
+      if (b < 0) {  // one-qubit gate: its bit plays the LSB, the MSB is a constant 0
+        b = a;
+        a = -1;
+      }
+      g.a[j] = a;
+      g.b[j] = b;
     }
-    dim3 grid(grid_for(nvec, 256, 4), (unsigned)batch);
-    cross_marginals_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(lam),
+    dim3 grid(grid_for((nvec + 1) / 2, 256, 2), (unsigned)batch);
+    constexpr size_t cm_smem = sizeof(float) * 256 * (CM_G * 6 + 2);
+    static bool attr_set = false;
+    if (!attr_set) {
+      TCB_CHECK_CUDA(cudaFuncSetAttribute(cross_marginals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)cm_smem));
+      attr_set = true;
+    }
+    cross_marginals_kernel<<<grid, 256, cm_smem, stream>>>(reinterpret_cast<const float4*>(lam),
                                                      reinterpret_cast<const float4*>(psi), nvec, g, cnt,
                                                      out + 8 * first, 2 * out_bstride);
     TCB_CHECK_CUDA(cudaGetLastError());
   }
+  const int total = ngates * (int)batch;
+  cm_moments_to_bins_kernel<<<(total + 127) / 128, 128, 0, stream>>>(out, total);
+  TCB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -1157,7 +1239,7 @@ cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi,
   lam += (size_t)blockIdx.y << nbits;
   psi += (size_t)blockIdx.y << nbits;
   out += (size_t)blockIdx.y * out_bstride;
-  __shared__ float2 sl[1 << CR_MAXB], sp[1 << CR_MAXB];
+  __shared__ __align__(16) float2 sl[1 << CR_MAXB], sp[1 << CR_MAXB];
   __shared__ double sacc[CR_MAXB * 4 * 2];
   const int tb = cb.nlow + cb.nsel;          // tile bits
   const int tsize = 1 << tb;
@@ -1193,11 +1275,32 @@ cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi,
     // tile base: spread the tile counter over the bits that are NOT in the tile
     uint64_t base = tile << cb.nlow;
     for (int j = 0; j < cb.nsel; ++j) base = insert_zero(base, cb.sel[j]);  // sel ascending
-    for (int e = tid; e < tsize; e += blockDim.x) {
-      uint64_t a = base | (uint64_t)(e & ((1 << cb.nlow) - 1));
-      for (int j = 0; j < cb.nsel; ++j) a |= (uint64_t)((e >> (cb.nlow + j)) & 1) << cb.sel[j];
-      sl[e] = lam[a];
-      sp[e] = psi[a];
+    if (tb == CR_MAXB) {
+      // full tile: 2 x 2 independent 16-byte loads per thread in flight before anything is stored (the simple
+      // loop below keeps one 8-byte load per state in flight and is latency-bound at a tenth of HBM speed)
+      float4 rl[2], rp[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int e = (tid + k * 256) << 1;  // even amplitude index inside the tile; low three bits = address bits
+        uint64_t a = base | (uint64_t)(e & 7);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) a |= (uint64_t)((e >> (3 + j)) & 1) << cb.sel[j];
+        rl[k] = ldg_stream(reinterpret_cast<const float4*>(lam + a));
+        rp[k] = ldg_stream(reinterpret_cast<const float4*>(psi + a));
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int e = (tid + k * 256) << 1;
+        *reinterpret_cast<float4*>(&sl[e]) = rl[k];
+        *reinterpret_cast<float4*>(&sp[e]) = rp[k];
+      }
+    } else {
+      for (int e = tid; e < tsize; e += blockDim.x) {
+        uint64_t a = base | (uint64_t)(e & ((1 << cb.nlow) - 1));
+        for (int j = 0; j < cb.nsel; ++j) a |= (uint64_t)((e >> (cb.nlow + j)) & 1) << cb.sel[j];
+        sl[e] = lam[a];
+        sp[e] = psi[a];
+      }
     }
     __syncthreads();
 #pragma unroll
