@@ -16,7 +16,7 @@ start for each gate (O(G^2) passes, exact for arbitrary matrices).
 
 from __future__ import annotations
 
-from typing import Any, List, Optional
+from typing import Any, Dict, List, Optional
 
 import torch
 
@@ -91,6 +91,11 @@ class _DiagRun:
 
     def backward(self, nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor, g_all: torch.Tensor) -> None:
         """lam, psi: [2^n] or a contiguous batch [B, 2^n]; dag [.., T], g_all [.., T, 2] likewise."""
+        self.grads(nbits, lam, psi, dag, g_all)
+        self.unapply(lam, psi, dag)
+
+    def grads(self, nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor, g_all: torch.Tensor) -> None:
+        """From the states AFTER the run."""
         nb = 1 if lam.dim() == 1 else int(lam.shape[0])
         dag2, g2 = dag.reshape(nb, -1), g_all.reshape(nb, -1, 2)
         bins = torch.zeros(nb, self.ngates * 4, 2, dtype=torch.float64, device=psi.device)
@@ -100,7 +105,10 @@ class _DiagRun:
         dvals = dag2[:, self.gidx].conj().to(torch.complex128)
         grad = torch.view_as_real(dvals * torch.view_as_complex(bins))
         g2.index_add_(1, self.gidx[self.ok], grad[:, self.ok])
-        sub_gb = dag2[:, self.sub_idx].contiguous()
+
+    def unapply(self, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor) -> None:
+        nb = 1 if lam.dim() == 1 else int(lam.shape[0])
+        sub_gb = dag.reshape(nb, -1)[:, self.sub_idx].contiguous()
         self.sub.run(psi, sub_gb, batch=nb, gate_batch_stride=int(sub_gb.shape[1]))
         self.sub.run(lam, sub_gb, batch=nb, gate_batch_stride=int(sub_gb.shape[1]))
 
@@ -147,11 +155,19 @@ class _OneQubitRun:
 
     def backward(self, nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor, g_all: torch.Tensor) -> None:
         """lam, psi: [2^n] or a contiguous batch [B, 2^n]; dag [.., T], g_all [.., T, 2] likewise."""
+        self.unapply(lam, psi, dag)
+        self.grads(nbits, lam, psi, dag, g_all)
+
+    def unapply(self, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor) -> None:
         nb = 1 if lam.dim() == 1 else int(lam.shape[0])
-        dag2, g2 = dag.reshape(nb, -1), g_all.reshape(nb, -1, 2)
-        sub_gb = dag2[:, self.sub_idx].contiguous()
+        sub_gb = dag.reshape(nb, -1)[:, self.sub_idx].contiguous()
         self.sub.run(psi, sub_gb, batch=nb, gate_batch_stride=int(sub_gb.shape[1]))  # psi_0, lam_0: before the run
         self.sub.run(lam, sub_gb, batch=nb, gate_batch_stride=int(sub_gb.shape[1]))
+
+    def grads(self, nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor, g_all: torch.Tensor) -> None:
+        """From the states BEFORE the run."""
+        nb = 1 if lam.dim() == 1 else int(lam.shape[0])
+        dag2, g2 = dag.reshape(nb, -1), g_all.reshape(nb, -1, 2)
         ng = len(self.groups)
         cr = torch.zeros(nb, ng * 40, 2, dtype=torch.float64, device=psi.device)
         for gi, (nsel, sel) in enumerate(self.groups):
@@ -161,6 +177,26 @@ class _OneQubitRun:
         u = dag2[:, self.dst].reshape(nb * self.m, 2, 2).conj().transpose(1, 2).to(torch.complex128)  # (U^dagger)^dagger
         g = torch.bmm(u, c).reshape(nb, -1)
         g2.index_add_(1, self.dst, torch.view_as_real(g))
+
+
+class _FusedUnapply:
+    """A one-qubit run immediately followed (program order) by a diagonal run, un-applied as ONE sub-circuit: the
+    diagonal run's gradients need the states after it, the one-qubit run's the states before it, so nothing in
+    between is needed and the two share their passes."""
+
+    def __init__(self, cc: "svengine.CompiledCircuit", first: int, last: int, dense_offs: List[int],
+                 device: torch.device) -> None:  # fmt: skip
+        nq = cc.plan.nbits
+        ops = cc.ops[first:last]
+        structure = [(op.qubits, ("diag",) if op.kind[0] in ("diag", "diagvec") else ("dense",), (1 << op.k) ** 2)
+                     for op in reversed(ops)]  # fmt: skip
+        self.sub = svengine.compile_circuit(nq, structure, device, absorb_prefix=False)
+        sub_idx: List[int] = []
+        for op, off in zip(reversed(ops), reversed(dense_offs)):
+            sub_idx += list(range(off, off + (1 << op.k) ** 2))
+        self.sub_idx = torch.tensor(sub_idx, dtype=torch.long, device=device)
+
+    unapply = _OneQubitRun.unapply
 
 
 class _AdjointTables:
@@ -234,6 +270,11 @@ class _AdjointTables:
             else:
                 i = max(j, i + 1)
         add_general(start, len(ops))
+        self.fused: Dict[int, _FusedUnapply] = {}  # index of a _OneQubitRun segment directly followed by a _DiagRun
+        for k in range(len(self.segments) - 1):
+            a, b = self.segments[k], self.segments[k + 1]
+            if isinstance(a, _OneQubitRun) and isinstance(b, _DiagRun) and a.last == b.first:
+                self.fused[k] = _FusedUnapply(cc, a.first, b.last, offs[a.first : b.last], device)
         self.dag_idx = torch.tensor(dag_idx, dtype=torch.long, device=device)
         self.scat_src = torch.tensor(scat_src, dtype=torch.long, device=device)
         self.scat_dst = torch.tensor(scat_dst, dtype=torch.long, device=device)
@@ -363,11 +404,20 @@ def _walk(cc: Any, tabs: "_AdjointTables", nbits: int, lam: torch.Tensor, psi: t
                 cc.vjp(lam[b], psi[b], dag[b], g_all[b], first, last)
 
     if layered_adjoint and len(tabs.segments) > 1:
-        for seg in reversed(tabs.segments):
+        k = len(tabs.segments) - 1
+        while k >= 0:
+            seg = tabs.segments[k]
+            if isinstance(seg, _DiagRun) and (k - 1) in tabs.fused:
+                seg.grads(nbits, lam, psi, dag, g_all)             # states after the diagonal run
+                tabs.fused[k - 1].unapply(lam, psi, dag)           # both runs in one fused sub-circuit
+                tabs.segments[k - 1].grads(nbits, lam, psi, dag, g_all)  # states before the one-qubit run
+                k -= 2
+                continue
             if isinstance(seg, (_DiagRun, _OneQubitRun)):
                 seg.backward(nbits, lam, psi, dag, g_all)
             else:
                 plain(seg[1], seg[2])
+            k -= 1
     else:
         plain(0, len(cc.ops))
 
