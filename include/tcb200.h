@@ -136,9 +136,10 @@ int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int64_t 
  *   out[t][r][c] (complex128 pairs, +=) = sum_rest lam[rest, bit_t = r] conj(psi[rest, bit_t = c])
  * for the tile bits t = 0..min(3,nbits)-1 (the lowest address bits, always in the tile) followed by the nsel
  * (<= 7) selected bits (ascending, >= 3).  With lam, psi the states BEFORE a layer of one-qubit gates on
- * distinct qubits, dL/dU_q = U_q out[q] for every gate of the layer (same convention as tcb_sv_gate_grad). */
+ * distinct qubits, dL/dU_q = U_q out[q] for every gate of the layer (same convention as tcb_sv_gate_grad).
+ * skip_low != 0: leave the low-bit entries untouched (a later call of a series only adds its selected bits). */
 int tcb_sv_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch, int nsel, const int* sel_bits_host,
-                     double* out, int64_t out_batch_stride, void* stream);
+                     int skip_low, double* out, int64_t out_batch_stride, void* stream);
 
 /* ---- statevector: sampling ------------------------------
  * Replaces probability() + cumsum + searchsorted of tensorcircuit/basecircuit.py:1490-1512 /

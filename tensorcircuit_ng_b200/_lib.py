@@ -106,7 +106,7 @@ SYMBOLS = {
     ),
     "tcb_sv_cross_rdm": (
         c_int,
-        [c_void_p, c_void_p, c_int, c_int64, c_int, POINTER(c_int), c_void_p, c_int64, c_void_p],
+        [c_void_p, c_void_p, c_int, c_int64, c_int, POINTER(c_int), c_int, c_void_p, c_int64, c_void_p],
     ),
     "tcb_sv_sample_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "tcb_sv_sample": (

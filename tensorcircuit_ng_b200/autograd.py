@@ -171,7 +171,7 @@ class _OneQubitRun:
         ng = len(self.groups)
         cr = torch.zeros(nb, ng * 40, 2, dtype=torch.float64, device=psi.device)
         for gi, (nsel, sel) in enumerate(self.groups):
-            _lib.call("tcb_sv_cross_rdm", lam.data_ptr(), psi.data_ptr(), nbits, nb, nsel, sel,
+            _lib.call("tcb_sv_cross_rdm", lam.data_ptr(), psi.data_ptr(), nbits, nb, nsel, sel, int(gi > 0),
                       cr.data_ptr() + gi * 40 * 16, ng * 40, _lib.stream_ptr())  # fmt: skip
         c = torch.view_as_complex(cr[:, self.src]).reshape(nb * self.m, 2, 2)
         u = dag2[:, self.dst].reshape(nb * self.m, 2, 2).conj().transpose(1, 2).to(torch.complex128)  # (U^dagger)^dagger

@@ -47,7 +47,7 @@ int launch_gate_grad(const void*, const void*, int, int64_t, const int*, int, vo
 int launch_adjoint_step(void*, void*, int, int64_t, const int*, int, const void*, int64_t, void*, int64_t,
                         cudaStream_t);
 int launch_cross_marginals(const void*, const void*, int, int64_t, int, const int*, double*, int64_t, cudaStream_t);
-int launch_cross_rdm(const void*, const void*, int, int64_t, int, const int*, double*, int64_t, cudaStream_t);
+int launch_cross_rdm(const void*, const void*, int, int64_t, int, const int*, int, double*, int64_t, cudaStream_t);
 int launch_sample_prepare(const void*, int, int, double*, cudaStream_t);
 int launch_sample(const void*, int, int, const double*, const double*, int64_t, int, long long*, double*,
                   cudaStream_t);
@@ -197,12 +197,12 @@ int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int64_t 
 }
 
 int tcb_sv_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch, int nsel, const int* sel_bits_host,
-                     double* out, int64_t out_batch_stride, void* stream) {
+                     int skip_low, double* out, int64_t out_batch_stride, void* stream) {
   NOTNULL(lam, "tcb_sv_cross_rdm");
   NOTNULL(psi, "tcb_sv_cross_rdm");
   NOTNULL(out, "tcb_sv_cross_rdm");
   if (nsel > 0) NOTNULL(sel_bits_host, "tcb_sv_cross_rdm");
-  return launch_cross_rdm(lam, psi, nbits, batch, nsel, sel_bits_host, out, out_batch_stride, S(stream));
+  return launch_cross_rdm(lam, psi, nbits, batch, nsel, sel_bits_host, skip_low, out, out_batch_stride, S(stream));
 }
 
 int tcb_sv_sample_prepare(const void* state, int nbits, int seg_bits, double* cdf, void* stream) {

@@ -1234,39 +1234,44 @@ struct CrBits {
 };
 
 __global__ void __launch_bounds__(256)
-cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi, int nbits, CrBits cb, double* out,
-                 long long out_bstride) {
+cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi, int nbits, CrBits cb, int t_begin,
+                 double* out, long long out_bstride) {
   lam += (size_t)blockIdx.y << nbits;
   psi += (size_t)blockIdx.y << nbits;
   out += (size_t)blockIdx.y * out_bstride;
   __shared__ __align__(16) float2 sl[1 << CR_MAXB], sp[1 << CR_MAXB];
-  __shared__ double sacc[CR_MAXB * 4 * 2];
+  __shared__ double sacc[CR_MAXB * 3 * 2 + 2];  // per bit [0][0], [0][1], [1][0]; then the total sum lam conj(psi)
   const int tb = cb.nlow + cb.nsel;          // tile bits
   const int tsize = 1 << tb;
   const int tid = threadIdx.x;
-  for (int e = tid; e < CR_MAXB * 8; e += blockDim.x) sacc[e] = 0.0;
-  float2 acc[CR_MAXB][4];
+  for (int e = tid; e < CR_MAXB * 6 + 2; e += blockDim.x) sacc[e] = 0.0;
+  // C[1][1] = (sum over ALL amplitudes of lam conj(psi)) - C[0][0] for every bit: three products per pair, not four
+  float2 acc[CR_MAXB][3], tot = make_float2(0.f, 0.f);
 #pragma unroll
   for (int t = 0; t < CR_MAXB; ++t)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[t][c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < 3; ++c) acc[t][c] = make_float2(0.f, 0.f);
+  auto warp_add = [&](float re, float im, int slot) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      re += __shfl_xor_sync(0xffffffffu, re, o);
+      im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&sacc[2 * slot], (double)re);
+      atomicAdd(&sacc[2 * slot + 1], (double)im);
+    }
+  };
   auto flush = [&]() {
 #pragma unroll
     for (int t = 0; t < CR_MAXB; ++t)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float re = acc[t][c].x, im = acc[t][c].y;
+      for (int c = 0; c < 3; ++c) {
+        if (t >= t_begin && t < tb) warp_add(acc[t][c].x, acc[t][c].y, t * 3 + c);  // (uniform)
         acc[t][c] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          re += __shfl_xor_sync(0xffffffffu, re, o);
-          im += __shfl_xor_sync(0xffffffffu, im, o);
-        }
-        if ((tid & 31) == 0 && t < tb) {
-          atomicAdd(&sacc[(t * 4 + c) * 2], (double)re);
-          atomicAdd(&sacc[(t * 4 + c) * 2 + 1], (double)im);
-        }
       }
+    warp_add(tot.x, tot.y, CR_MAXB * 3);
+    tot = make_float2(0.f, 0.f);
   };
   const uint64_t ntiles = 1ull << (nbits - tb);
   int it = 0;
@@ -1276,8 +1281,8 @@ cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi,
     uint64_t base = tile << cb.nlow;
     for (int j = 0; j < cb.nsel; ++j) base = insert_zero(base, cb.sel[j]);  // sel ascending
     if (tb == CR_MAXB) {
-      // full tile: 2 x 2 independent 16-byte loads per thread in flight before anything is stored (the simple
-      // loop below keeps one 8-byte load per state in flight and is latency-bound at a tenth of HBM speed)
+      // full tile: 2 x 2 independent 16-byte loads per thread in flight before anything is stored (a simple
+      // element loop keeps one 8-byte load per state in flight and is latency-bound at a tenth of HBM speed)
       float4 rl[2], rp[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -1293,26 +1298,30 @@ cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi,
         const int e = (tid + k * 256) << 1;
         *reinterpret_cast<float4*>(&sl[e]) = rl[k];
         *reinterpret_cast<float4*>(&sp[e]) = rp[k];
+        tot.x += rl[k].x * rp[k].x + rl[k].y * rp[k].y + rl[k].z * rp[k].z + rl[k].w * rp[k].w;
+        tot.y += rl[k].y * rp[k].x - rl[k].x * rp[k].y + rl[k].w * rp[k].z - rl[k].z * rp[k].w;
       }
     } else {
       for (int e = tid; e < tsize; e += blockDim.x) {
         uint64_t a = base | (uint64_t)(e & ((1 << cb.nlow) - 1));
         for (int j = 0; j < cb.nsel; ++j) a |= (uint64_t)((e >> (cb.nlow + j)) & 1) << cb.sel[j];
-        sl[e] = lam[a];
-        sp[e] = psi[a];
+        const float2 l = lam[a], q = psi[a];
+        sl[e] = l;
+        sp[e] = q;
+        tot.x += l.x * q.x + l.y * q.y;
+        tot.y += l.y * q.x - l.x * q.y;
       }
     }
     __syncthreads();
 #pragma unroll
     for (int t = 0; t < CR_MAXB; ++t) {
-      if (t < tb) {
+      if (t >= t_begin && t < tb) {
         for (int j = tid; j < (tsize >> 1); j += blockDim.x) {
           const int i0 = (int)insert_zero((uint64_t)j, t), i1 = i0 | (1 << t);
           const float2 l0 = sl[i0], l1 = sl[i1], p0 = sp[i0], p1 = sp[i1];
           acc[t][0].x += l0.x * p0.x + l0.y * p0.y;  acc[t][0].y += l0.y * p0.x - l0.x * p0.y;  // [0][0]
           acc[t][1].x += l0.x * p1.x + l0.y * p1.y;  acc[t][1].y += l0.y * p1.x - l0.x * p1.y;  // [0][1]
           acc[t][2].x += l1.x * p0.x + l1.y * p0.y;  acc[t][2].y += l1.y * p0.x - l1.x * p0.y;  // [1][0]
-          acc[t][3].x += l1.x * p1.x + l1.y * p1.y;  acc[t][3].y += l1.y * p1.x - l1.x * p1.y;  // [1][1]
         }
       }
     }
@@ -1324,11 +1333,17 @@ cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi,
   }
   flush();
   __syncthreads();
-  for (int e = tid; e < tb * 8; e += blockDim.x) atomicAdd(out + e, sacc[e]);
+  // out[t][r][c]: [0][0], [0][1], [1][0] as accumulated, [1][1] = total - [0][0]
+  for (int e = tid; e < tb * 8; e += blockDim.x) {
+    const int t = e >> 3, c = (e >> 1) & 3, ri = e & 1;
+    if (t < t_begin) continue;
+    const double v = c < 3 ? sacc[(t * 3 + c) * 2 + ri] : sacc[CR_MAXB * 6 + ri] - sacc[(t * 3) * 2 + ri];
+    atomicAdd(out + e, v);
+  }
 }
 
 int launch_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch, int nsel, const int* sel_bits,
-                     double* out, int64_t out_bstride, cudaStream_t stream) {
+                     int skip_low, double* out, int64_t out_bstride, cudaStream_t stream) {
   TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_cross_rdm: nbits=%d", nbits);
   TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_cross_rdm: batch=%lld", (long long)batch);
   CrBits cb;
@@ -1347,7 +1362,7 @@ int launch_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch,
   if (batch > 1 && grid > (uint64_t)sm_count()) grid = sm_count();  // (batch rows share the SMs)
   dim3 g2((unsigned)grid, (unsigned)batch);
   cross_rdm_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const float2*>(lam), reinterpret_cast<const float2*>(psi),
-                                           nbits, cb, out, 2 * out_bstride);
+                                           nbits, cb, skip_low ? cb.nlow : 0, out, 2 * out_bstride);
   TCB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -249,7 +249,13 @@ def test_cross_rdm(cuda, n, sel):
     out = torch.zeros(40, 2, dtype=torch.float64, device="cuda")
     lt, pt = torch.from_numpy(lam).cuda(), torch.from_numpy(psi).cuda()
     _lib.call("tcb_sv_cross_rdm", lt.data_ptr(), pt.data_ptr(), n, 1, len(sel), _lib.int_array(sel) if sel else None,
-              out.data_ptr(), 0, _lib.stream_ptr())  # fmt: skip
+              0, out.data_ptr(), 0, _lib.stream_ptr())  # fmt: skip
+    if sel:  # skip_low: only the selected bits are written
+        out2 = torch.zeros(40, 2, dtype=torch.float64, device="cuda")
+        _lib.call("tcb_sv_cross_rdm", lt.data_ptr(), pt.data_ptr(), n, 1, len(sel), _lib.int_array(sel), 1,
+                  out2.data_ptr(), 0, _lib.stream_ptr())  # fmt: skip
+        assert float(out2[: min(3, n) * 4].abs().max()) == 0.0
+        assert float((out2[min(3, n) * 4 :] - out[min(3, n) * 4 :]).abs().max()) <= 1e-9 * float(out.abs().max())
     got = torch.view_as_complex(out).cpu().numpy().reshape(10, 2, 2)
     L = lam.astype(np.complex128).reshape([2] * n)
     P = psi.astype(np.complex128).reshape([2] * n)
