@@ -151,6 +151,15 @@ class CudaExecutor:
         cc = cache.get(key)
         if cc is None:
             plan = passplan.compile_plan(list(ops), nq, nbits_local=nl, pos_of=pos_of, **svengine.plan_options)
+            if svengine.auto_low_bits and svengine.plan_options.get("low_bits") == 3 and nl >= 28:
+                # same rule as svengine.compile_circuit: 16-byte segments when they save a pass of this segment
+                n3 = sum(isinstance(st, passplan.PassStep) for st in plan.steps)
+                if n3 >= 4:
+                    alt = passplan.compile_plan(list(ops), nq, nbits_local=nl, pos_of=pos_of,
+                                                **{**svengine.plan_options, "low_bits": 2})  # fmt: skip
+                    n2 = sum(isinstance(st, passplan.PassStep) for st in alt.steps)
+                    if len(alt.steps) - n2 <= len(plan.steps) - n3 and n2 * 1.04 < n3:
+                        plan = alt
             cc = svengine.CompiledCircuit(plan, list(ops), self.device)
             cache[key] = cc
         cc.run(state, gatebuf, index_base=index_base)
