@@ -56,6 +56,7 @@ def _dense_matrix(gatebuf: torch.Tensor, op: GateOp) -> torch.Tensor:
 
 diag_run_min = 3  # shorter runs of diagonal gates are walked gate by gate
 one_qubit_run_min = 4  # likewise for runs of one-qubit gates on distinct qubits
+const_run_min = 2  # ... and for runs of constant gates (un-applied together, no gradients)
 layered_adjoint = True
 
 
@@ -199,13 +200,27 @@ class _FusedUnapply:
     unapply = _OneQubitRun.unapply
 
 
+class _ConstRun(_FusedUnapply):
+    """A run of consecutive gates that take no gradient (H, CNOT, CZ, SWAP ... between the trainable layers): the
+    adjoint walk only has to un-apply them, which the fused pass kernel does for the whole run at once."""
+
+    def __init__(self, cc: "svengine.CompiledCircuit", first: int, last: int, dense_offs: List[int],
+                 device: torch.device) -> None:  # fmt: skip
+        super().__init__(cc, first, last, dense_offs, device)
+        self.first, self.last = first, last
+
+    def backward(self, nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor, g_all: torch.Tensor) -> None:
+        self.unapply(lam, psi, dag)
+
+
 class _AdjointTables:
     """Per-circuit index tables for the backward walk, built once and cached on the compiled circuit:
     a dense row-major U^dagger for every gate comes from ONE gather of conj(gate buffer), and the
     float64 per-gate reductions land in one buffer that is scattered back with ONE index_add."""
 
-    def __init__(self, cc: "svengine.CompiledCircuit", nelem: int, device: torch.device) -> None:
+    def __init__(self, cc: "svengine.CompiledCircuit", nelem: int, device: torch.device, const_mask: Any = None) -> None:
         nq = cc.plan.nbits
+        const = tuple(const_mask) if const_mask is not None else (False,) * len(cc.ops)
         dag_idx: List[int] = []
         scat_src: List[int] = []
         scat_dst: List[int] = []
@@ -244,7 +259,8 @@ class _AdjointTables:
                 self.segments.append(("G", a, b))
 
         def add_general(a: int, b: int) -> None:
-            """[a, b) holds no long diagonal run: carve out runs of one-qubit gates on distinct qubits."""
+            """[a, b) holds no long diagonal run: carve out runs of one-qubit gates on distinct qubits and runs of
+            constant gates (no gradient wanted: un-applied as one fused sub-circuit, e.g. a CNOT ladder)."""
             i = a
             while i < b:
                 j, seen = i, set()
@@ -253,6 +269,13 @@ class _AdjointTables:
                     j += 1
                 if j - i >= one_qubit_run_min:
                     self.segments.append(_OneQubitRun(cc, i, j, offs[i:j], device))
+                    i = j
+                    continue
+                j = i
+                while j < b and const[j] and ops[j].k <= 4:
+                    j += 1
+                if j - i >= const_run_min:
+                    self.segments.append(_ConstRun(cc, i, j, offs[i:j], device))
                     i = j
                 else:
                     add_plain(i, i + 1)
@@ -280,19 +303,26 @@ class _AdjointTables:
         self.scat_dst = torch.tensor(scat_dst, dtype=torch.long, device=device)
 
 
-def _adjoint_tables(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor) -> _AdjointTables:
-    t = getattr(cc, "_adjoint_tables", None)
-    if t is None or t.dag_idx.device != gatebuf.device:
-        t = _AdjointTables(cc, gatebuf.numel(), gatebuf.device)
-        cc._adjoint_tables = t
+def _adjoint_tables(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor, const_mask: Any = None) -> _AdjointTables:
+    """Cached per circuit, device and set of constant gates (`const_mask[g]`: gate g takes no gradient)."""
+    cache = getattr(cc, "_adjoint_tables", None)
+    if cache is None:
+        cache = cc._adjoint_tables = {}
+    key = (str(gatebuf.device), const_mask)
+    t = cache.get(key)
+    if t is None:
+        if len(cache) > 8:
+            cache.clear()
+        t = cache[key] = _AdjointTables(cc, gatebuf.numel(), gatebuf.device, const_mask)
     return t
 
 
 class _Evolve(torch.autograd.Function):
     @staticmethod
-    def forward(ctx: Any, gatebuf: torch.Tensor, init: Optional[torch.Tensor], cc: Any) -> torch.Tensor:
+    def forward(ctx: Any, gatebuf: torch.Tensor, init: Optional[torch.Tensor], cc: Any, const_mask: Any = None) -> torch.Tensor:
         state = _forward(cc, gatebuf.detach(), init)
         ctx.cc = cc
+        ctx.const_mask = const_mask
         ctx.has_init = init is not None
         ctx.save_for_backward(gatebuf.detach(), state)
         return state
@@ -304,7 +334,7 @@ class _Evolve(torch.autograd.Function):
         nbits = cc.plan.nbits
         if not assume_unitary:
             raise _lib.EngineError("autograd.assume_unitary=False (recompute mode) is not implemented in this round")
-        tabs = _adjoint_tables(cc, gatebuf)
+        tabs = _adjoint_tables(cc, gatebuf, ctx.const_mask)
         lam = grad_out.to(torch.complex64).resolve_conj().reshape(-1).clone()
         psi = psi_out.clone()
         src = torch.cat([gatebuf.conj().resolve_conj(), torch.zeros(1, dtype=gatebuf.dtype, device=gatebuf.device)])
@@ -316,7 +346,7 @@ class _Evolve(torch.autograd.Function):
         grad_buf = torch.zeros_like(gatebuf)
         torch.view_as_real(grad_buf).index_add_(0, tabs.scat_dst, g_all[tabs.scat_src].to(torch.float32))
         grad_init = lam if ctx.has_init and ctx.needs_input_grad[1] else None
-        return grad_buf, grad_init, None
+        return grad_buf, grad_init, None, None
 
 
 # ---- batched evolution under torch.vmap ------------------------------------------------------------
@@ -329,6 +359,13 @@ _ft = torch._C._functorch
 
 def is_batched(t: Any) -> bool:
     return isinstance(t, torch.Tensor) and _ft.is_batchedtensor(t)
+
+
+def wants_grad(t: torch.Tensor) -> bool:
+    """requires_grad of the physical tensor (the flag is not mirrored on torch.vmap's batched wrappers)."""
+    while is_batched(t):
+        t = _ft.get_unwrapped(t)
+    return bool(t.requires_grad)
 
 
 def unwrap_batched(t: torch.Tensor) -> Any:
@@ -354,7 +391,8 @@ class _EvolveBatched(torch.autograd.Function):
     """B independent parameter sets of one circuit: states [B, 2^n], gate buffers [B, elems]."""
 
     @staticmethod
-    def forward(ctx: Any, gatebuf: torch.Tensor, cc: Any) -> torch.Tensor:
+    def forward(ctx: Any, gatebuf: torch.Tensor, cc: Any, const_mask: Any = None) -> torch.Tensor:
+        ctx.const_mask = const_mask
         gb = gatebuf.detach().to(torch.complex64).contiguous()
         nb, nelem = gb.shape
         nbits = cc.plan.nbits
@@ -378,7 +416,7 @@ class _EvolveBatched(torch.autograd.Function):
         cc = ctx.cc
         nbits = cc.plan.nbits
         nb, nelem = gb.shape
-        tabs = _adjoint_tables(cc, gb[0])
+        tabs = _adjoint_tables(cc, gb[0], ctx.const_mask)
         lam = grad_out.to(torch.complex64).resolve_conj().contiguous().clone()
         psi = psi_out.clone()
         src = torch.cat([gb.conj().resolve_conj(), torch.zeros(nb, 1, dtype=gb.dtype, device=gb.device)], dim=1)
@@ -387,7 +425,7 @@ class _EvolveBatched(torch.autograd.Function):
         _walk(cc, tabs, nbits, lam, psi, dag, g_all)
         grad_buf = torch.zeros(nb, nelem, 2, dtype=torch.float32, device=gb.device)
         grad_buf.index_add_(1, tabs.scat_dst, g_all[:, tabs.scat_src].to(torch.float32))
-        return torch.view_as_complex(grad_buf), None
+        return torch.view_as_complex(grad_buf), None, None
 
 
 def _walk(cc: Any, tabs: "_AdjointTables", nbits: int, lam: torch.Tensor, psi: torch.Tensor, dag: torch.Tensor,
@@ -413,7 +451,7 @@ def _walk(cc: Any, tabs: "_AdjointTables", nbits: int, lam: torch.Tensor, psi: t
                 tabs.segments[k - 1].grads(nbits, lam, psi, dag, g_all)  # states before the one-qubit run
                 k -= 2
                 continue
-            if isinstance(seg, (_DiagRun, _OneQubitRun)):
+            if isinstance(seg, (_DiagRun, _OneQubitRun, _ConstRun)):
                 seg.backward(nbits, lam, psi, dag, g_all)
             else:
                 plain(seg[1], seg[2])
@@ -422,15 +460,18 @@ def _walk(cc: Any, tabs: "_AdjointTables", nbits: int, lam: torch.Tensor, psi: t
         plain(0, len(cc.ops))
 
 
-def evolve(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor, init: Optional[torch.Tensor]) -> torch.Tensor:
+def evolve(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor, init: Optional[torch.Tensor],
+           const_mask: Any = None) -> torch.Tensor:  # fmt: skip
+    """`const_mask[g]` (optional, one bool per gate of cc.ops): gate g is a constant — the backward walk skips its
+    gradient and un-applies runs of such gates as fused sub-circuits."""
     if is_batched(gatebuf) or is_batched(init):
         if init is not None or cc.prefix_levels:
             raise _lib.EngineError("the batched engine path starts from |0...0> (no `inputs`, no absorbed prefix)")
         phys, lvl = unwrap_batched(gatebuf)
         with outside_vmap():
-            out = _EvolveBatched.apply(phys, cc)
+            out = _EvolveBatched.apply(phys, cc, const_mask)
         return rewrap_batched(out, lvl)
     needs = torch.is_grad_enabled() and (gatebuf.requires_grad or (init is not None and init.requires_grad))
     if not needs:
         return _forward(cc, gatebuf, init)
-    return _Evolve.apply(gatebuf, init, cc)
+    return _Evolve.apply(gatebuf, init, cc, const_mask)

@@ -487,5 +487,12 @@ def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) 
     init = None
     if init_node is not None:
         init = init_node.tensor.to(torch.complex64).to(device).reshape(-1)
-    state = autograd.evolve(cc, gatebuf, init)
+    const_mask = None
+    if torch.is_grad_enabled() and len(gates) == len(cc.ops):
+        # which gates are constants (no gradient wanted): the backward walk un-applies runs of them in fused passes
+        const_mask = tuple(
+            not autograd.wants_grad(g[0]._lazy.theta if hasattr(g[0], "pending") and g[0].pending() else g[0].tensor)
+            for g in gates
+        )
+    state = autograd.evolve(cc, gatebuf, init, const_mask)
     return state.reshape([2] * n)

@@ -237,3 +237,60 @@ def test_gpu_layered_adjoint_equals_gate_by_gate_walk(cuda, n):
     assert abs(float(v1) - float(v2)) < 1e-6
     assert float((g1 - g2).abs().max()) < 2e-5
     assert float(g2.abs().max()) > 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [6, 14])
+def test_gpu_constant_runs_are_unapplied_fused(cuda, n):
+    """A hardware-efficient ansatz (ry / rz layers between CNOT ladders, a toffoli and a swap): the constant gates
+    form runs that the backward walk un-applies as fused sub-circuits; gradients equal the gate-by-gate walk and
+    central differences of the oracle."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import autograd
+
+    def energy(mod, p, real):
+        c = mod.Circuit(n)
+        k = 0
+        for l in range(2):
+            for q in range(n):
+                c.ry(q, theta=p[k])
+                c.rz(q, theta=p[k + 1])
+                k += 2
+            for q in range(n - 1):
+                c.cnot(q, q + 1)
+            c.toffoli(0, 2, 4)
+            c.swap(1, 3)
+            c.h(5)
+        return real(c.expectation_ps(z=[0, n - 1])) + real(c.expectation_ps(x=[2])) + real(c.expectation_ps(y=[1], z=[3]))
+
+    p0 = np.linspace(0.15, 2.6, 4 * n)
+    pt = torch.tensor(p0, dtype=torch.float32)
+    seen = []
+    orig = autograd._adjoint_tables
+
+    def spy(cc, gb, mask=None):
+        t = orig(cc, gb, mask)
+        seen.append(t)
+        return t
+
+    autograd._adjoint_tables = spy
+    try:
+        v1, g1 = tc.backend.value_and_grad(lambda x: energy(tc, x, torch.real))(pt)
+    finally:
+        autograd._adjoint_tables = orig
+    assert any(isinstance(sg, autograd._ConstRun) for t in seen for sg in t.segments)
+    autograd.layered_adjoint = False
+    try:
+        v2, g2 = tc.backend.value_and_grad(lambda x: energy(tc, x, torch.real))(pt)
+    finally:
+        autograd.layered_adjoint = True
+    assert abs(float(v1) - float(v2)) < 1e-6 and float((g1 - g2).abs().max()) < 2e-5
+    f = lambda x: float(energy(otc, x, np.real))
+    assert abs(float(v1) - f(p0)) < 1e-5
+    for k in (0, 3, 2 * n + 1, 4 * n - 1):
+        xp, xm = p0.copy(), p0.copy()
+        xp[k] += 1e-2
+        xm[k] -= 1e-2
+        assert abs(float(g1[k]) - (f(xp) - f(xm)) / 2e-2) < 5e-3
