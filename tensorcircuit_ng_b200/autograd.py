@@ -122,10 +122,12 @@ class _OneQubitRun:
     two states (`tcb_sv_cross_rdm`) instead of one adjoint step per gate."""
 
     def __init__(self, cc: "svengine.CompiledCircuit", first: int, last: int, dense_offs: List[int],
-                 device: torch.device) -> None:  # fmt: skip
+                 device: torch.device, indices: Optional[List[int]] = None) -> None:  # fmt: skip
+        """Gates cc.ops[first:last], or the explicit `indices` (one round of a block of one-qubit gates in which
+        qubits repeat: gates on different qubits commute, so the block is its rounds one after the other)."""
         nq = cc.plan.nbits
-        ops = cc.ops[first:last]
-        self.first, self.last = first, last
+        ops = cc.ops[first:last] if indices is None else [cc.ops[i] for i in indices]
+        self.first, self.last = (first, last) if indices is None else (-1, -2)
         low = min(3, nq)
         bitpos = [nq - 1 - op.qubits[0] for op in ops]
         high = sorted(b for b in bitpos if b >= low)
@@ -271,6 +273,29 @@ class _AdjointTables:
                     self.segments.append(_OneQubitRun(cc, i, j, offs[i:j], device))
                     i = j
                     continue
+                # a block of one-qubit gates in which qubits repeat (ry(q) rz(q) per qubit ...): its rounds
+                j = i
+                while j < b and ops[j].k == 1:
+                    j += 1
+                if j - i >= 2 * one_qubit_run_min:
+                    depth: Dict[int, int] = {}
+                    rounds: List[List[int]] = []
+                    for g in range(i, j):
+                        q = ops[g].qubits[0]
+                        r = depth.get(q, 0)
+                        depth[q] = r + 1
+                        if r == len(rounds):
+                            rounds.append([])
+                        rounds[r].append(g)
+                    if max(len(r) for r in rounds) >= one_qubit_run_min:
+                        for r in rounds:
+                            if len(r) >= one_qubit_run_min:
+                                self.segments.append(_OneQubitRun(cc, 0, 0, [offs[g] for g in r], device, indices=r))
+                            else:
+                                for g in r:
+                                    self.segments.append(("G", g, g + 1))
+                        i = j
+                        continue
                 j = i
                 while j < b and const[j] and ops[j].k <= 4:
                     j += 1

@@ -281,6 +281,8 @@ def test_gpu_constant_runs_are_unapplied_fused(cuda, n):
     finally:
         autograd._adjoint_tables = orig
     assert any(isinstance(sg, autograd._ConstRun) for t in seen for sg in t.segments)
+    # the ry(q) rz(q) blocks repeat qubits: split into rounds of one-qubit gates on distinct qubits
+    assert any(isinstance(sg, autograd._OneQubitRun) and sg.first == -1 for t in seen for sg in t.segments)
     autograd.layered_adjoint = False
     try:
         v2, g2 = tc.backend.value_and_grad(lambda x: energy(tc, x, torch.real))(pt)
