@@ -89,3 +89,27 @@ def test_degenerate_batches_and_constant_circuits(cuda):
 
     v, g = tc.backend.value_and_grad(const)(torch.ones(3))
     assert abs(float(v) - 1.0) < 1e-6 and float(g.abs().max()) == 0.0
+
+
+def test_reference_closed_forms(cuda):
+    """tests/test_circuit.py:1501-1504 (<Y> = -1 on (-1, i)/sqrt 2), :57-62 (measure after a Toffoli reads a bit),
+    :65-77 (Bell measurements are perfectly correlated)."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+
+    c = tc.Circuit(1, inputs=torch.tensor(1 / np.sqrt(2) * np.array([-1, 1.0j]), dtype=torch.complex64).cuda())
+    assert abs(complex(c.expectation_ps(y=[0]).cpu()) + 1.0) < 1e-5
+    c = tc.Circuit(3)
+    c.H(0)
+    c.h(1)
+    c.toffoli(0, 1, 2)
+    assert float(c.measure(2)[0][0]) in (0.0, 1.0)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    c = tc.Circuit(2)
+    c.H(0)
+    c.cnot(0, 1)
+    counts = c.sample(batch=300, allow_state=False, format="count_dict_bin", random_generator=g)
+    assert set(counts) <= {"00", "11"} and sum(counts.values()) == 300 and min(counts.get("00", 0), counts.get("11", 0)) > 90
+    bits, p = c.measure(0, 1, with_prob=True, status=torch.tensor([0.9, 0.1]))
+    assert bits.cpu().tolist() == [1.0, 1.0] and abs(float(p) - 0.5) < 1e-6
