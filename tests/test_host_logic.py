@@ -413,3 +413,31 @@ def test_diagonal_only_subcircuit_plans(built):
             assert rc == 0
         assert n < 12 or 1 <= npass <= 3
         assert np.abs(state - want.reshape(-1)).max() < 2e-5 * np.abs(want).max()
+
+
+def test_second_plan_with_16_byte_segments_is_kept_only_when_it_saves_a_pass(built):
+    """svengine.compile_circuit plans states of >= 28 qubits a second time with low_bits = 2 and keeps that plan
+    only when it has fewer passes (30-qubit QAOA p=8: 18 instead of 19); smaller states keep low_bits = 3."""
+    import bench
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import passplan, svengine
+
+    if not svengine.auto_low_bits or svengine.plan_options.get("low_bits") != 3:
+        pytest.skip("TCB_LOW_BITS is set")
+    zz = np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0]))
+    for n, p, want_low in [(30, 8, 2), (24, 4, 3)]:
+        edges, gam, bet = bench.qaoa_problem(n, p)
+        c = bench.build_qaoa(tc, n, edges, torch.from_numpy(gam), torch.from_numpy(bet), zz)
+        nodes, e = c._copy()
+        nn, init, gates = svengine.extract_gate_stream(nodes, e)
+        structure = [(g[1], svengine.gate_kind(g[0], g[2]), int(np.prod(g[0].shape))) for g in gates]
+        cc = svengine.compile_circuit(nn, structure, torch.device("cpu"), absorb_prefix=True)
+        passes = [s for s in cc.plan.steps if isinstance(s, passplan.PassStep)]
+        assert {s.low_bits for s in passes} == {want_low}
+        if n == 30:
+            _, rest = svengine.split_prefix(cc.ops, nn)
+            base = passplan.compile_plan(rest, nn, **svengine.plan_options)
+            n3 = sum(isinstance(s, passplan.PassStep) for s in base.steps)
+            assert len(passes) < n3
