@@ -441,3 +441,70 @@ def test_second_plan_with_16_byte_segments_is_kept_only_when_it_saves_a_pass(bui
             base = passplan.compile_plan(rest, nn, **svengine.plan_options)
             n3 = sum(isinstance(s, passplan.PassStep) for s in base.steps)
             assert len(passes) < n3
+
+
+def test_adjoint_segments_partition_the_circuit(built):
+    """autograd._AdjointTables: every gate lands in exactly one segment; diagonal runs hold only diagonal gates,
+    one-qubit runs distinct qubits, constant runs only constants; a one-qubit run directly followed by a diagonal
+    run gets a fused un-apply plan."""
+    import torch
+
+    from tensorcircuit_ng_b200 import autograd, svengine
+
+    n = 14
+    structure, const = [], []
+
+    def add(qubits, kind, is_const):
+        structure.append((tuple(qubits), (kind,), 4 ** len(qubits)))
+        const.append(is_const)
+
+    for q in range(n):
+        add([q], "dense", True)  # H layer
+    for l in range(2):
+        for q in range(n - 1):
+            add([q, q + 1], "diag", False)  # rzz layer
+        for q in range(n):
+            add([q], "dense", False)  # rx layer
+        for q in range(n - 1):
+            add([q, q + 1], "dense", True)  # CNOT ladder
+        add([0, 1, 2], "dense", True)  # toffoli
+        for q in range(n):  # ry(q) rz(q): qubits repeat
+            add([q], "dense", False)
+            add([q], "diag", False)
+        add([3, 4], "dense", False)  # a trainable two-qubit gate: gate-by-gate
+    cc = svengine.compile_circuit(n, structure, torch.device("cpu"), absorb_prefix=False)
+    tabs = autograd._AdjointTables(cc, sum(s[2] for s in structure), torch.device("cpu"), tuple(const))
+    seen = []
+    kinds = set()
+    for seg in tabs.segments:
+        if isinstance(seg, tuple):
+            idx = list(range(seg[1], seg[2]))
+            kinds.add("G")
+        elif isinstance(seg, autograd._OneQubitRun) and seg.first == -1:
+            idx = None  # rounds: indices live in seg.dst (4 entries per gate); recover them from the offsets
+            offs = {it[2]: k for k, it in enumerate(tabs.items)}
+            idx = [offs[int(o)] for o in seg.dst[::4].tolist()]
+            qs = [cc.ops[i].qubits[0] for i in idx]
+            assert len(set(qs)) == len(qs) and all(cc.ops[i].k == 1 for i in idx)
+            kinds.add("rounds")
+        else:
+            idx = list(range(seg.first, seg.last))
+            if isinstance(seg, autograd._DiagRun):
+                assert all(cc.ops[i].kind[0] == "diag" for i in idx) and len(idx) >= autograd.diag_run_min
+                kinds.add("D")
+            elif isinstance(seg, autograd._OneQubitRun):
+                qs = [cc.ops[i].qubits[0] for i in idx]
+                assert len(set(qs)) == len(qs) and all(cc.ops[i].k == 1 for i in idx)
+                kinds.add("S")
+            else:
+                assert isinstance(seg, autograd._ConstRun) and all(const[i] for i in idx)
+                kinds.add("C")
+        seen += idx
+    assert sorted(seen) == list(range(len(structure)))
+    assert kinds == {"G", "rounds", "D", "S", "C"}
+    # program order is respected between segments that do not commute trivially: contiguous segments are ascending
+    firsts = [s[1] if isinstance(s, tuple) else s.first for s in tabs.segments if not (not isinstance(s, tuple) and s.first == -1)]
+    assert firsts == sorted(firsts)
+    assert len(tabs.fused) >= 1  # the first rx layer follows an rzz layer? no: H layer (one-qubit run) + rzz run
+    for k, fu in tabs.fused.items():
+        assert isinstance(tabs.segments[k], autograd._OneQubitRun) and isinstance(tabs.segments[k + 1], autograd._DiagRun)
