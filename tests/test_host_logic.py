@@ -508,3 +508,40 @@ def test_adjoint_segments_partition_the_circuit(built):
     assert len(tabs.fused) >= 1  # the first rx layer follows an rzz layer? no: H layer (one-qubit run) + rzz run
     for k, fu in tabs.fused.items():
         assert isinstance(tabs.segments[k], autograd._OneQubitRun) and isinstance(tabs.segments[k + 1], autograd._DiagRun)
+
+
+def test_backend_vmap_and_vvag_paths_on_plain_torch_functions():
+    """backend.vmap / vvag semantics (pytorch_backend.py:816-878) independent of the engine: one torch.vmap
+    evaluation when the function can be traced, the per-sample loop otherwise, identical results either way."""
+    import torch
+
+    from tensorcircuit_ng_b200 import backend
+
+    x = torch.arange(6.0).reshape(3, 2)
+    w = torch.tensor([1.0, 2.0])
+    f = lambda a, b: (a * b).sum() ** 2  # noqa: E731
+    old = backend.batched_mode
+    try:
+        backend.batched_mode = "strict"
+        out = backend.vmap(f, vectorized_argnums=0)(x, w)
+        assert backend.last_vmap_path == "batched" and out.tolist() == [4.0, 64.0, 196.0]
+        v, (gx, gw) = backend.vvag(f, argnums=(0, 1), vectorized_argnums=0)(x, w)
+        backend.batched_mode = "loop"
+        v2, (gx2, gw2) = backend.vvag(f, argnums=(0, 1), vectorized_argnums=0)(x, w)
+        assert backend.last_vmap_path.startswith("loop")
+        assert torch.allclose(v, v2) and torch.allclose(gx, gx2) and torch.allclose(gw, gw2)
+        assert tuple(gx.shape) == (3, 2) and tuple(gw.shape) == (2,)  # vectorised arg: stacked; shared arg: summed
+        backend.batched_mode = "auto"
+        h = lambda a: torch.tensor(float(a.sum()) * 2.0)  # noqa: E731  (data-dependent python: not traceable)
+        out = backend.vmap(h)(x)
+        assert backend.last_vmap_path.startswith("loop") and out.tolist() == [2.0, 10.0, 18.0]
+        with pytest.raises(Exception):
+            backend.batched_mode = "strict"
+            backend.vmap(h)(x)
+        backend.batched_mode = "auto"
+        pair = backend.vmap(lambda a: (a.sum(), a.prod()))(x)  # tuple outputs
+        assert pair[0].tolist() == [1.0, 5.0, 9.0] and pair[1].tolist() == [0.0, 6.0, 20.0]
+        va, ga = backend.vvag(lambda a: (a.sum() ** 2, a.mean()), has_aux=True)(x)  # aux outputs take the loop
+        assert backend.last_vmap_path.startswith("loop") and tuple(ga.shape) == (3, 2)
+    finally:
+        backend.batched_mode = old
