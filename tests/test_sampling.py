@@ -138,3 +138,26 @@ def test_gpu_sample_formats_and_statistics(cuda):  # tests/test_circuit.py:1462-
         cv = c3.sample(batch=20000, allow_state=allow_state, format="count_vector", random_generator=g).cpu().numpy()
         assert cv.sum() == 20000
         assert 0.5 * np.abs(cv / 20000.0 - p / p.sum()).sum() < 0.12
+
+
+def test_sample_format_helpers_on_host_tensors():
+    """quantum.sample2all and friends (tensorcircuit/quantum.py:3587-3902) on explicit samples."""
+    import torch
+
+    from tensorcircuit_ng_b200 import quantum as q
+
+    s = torch.tensor([0, 3, 3, 2])
+    assert q.sample_int2bin(s, 2).tolist() == [[0, 0], [1, 1], [1, 1], [1, 0]]
+    assert q.sample_int2bin(s, 2).tolist() == oq.sample_int2bin(s.numpy(), 2).tolist()
+    assert q.sample_bin2int(q.sample_int2bin(s, 2), 2).tolist() == s.tolist()
+    assert q.sample2all(s, 2, format="sample_int").tolist() == s.tolist()
+    assert q.sample2all(q.sample_int2bin(s, 2), 2, format="sample_int").tolist() == s.tolist()
+    assert q.sample2all(s, 2, format="count_vector").tolist() == [1, 0, 1, 2]
+    idx, cnt = q.sample2all(s, 2, format="count_tuple")
+    assert idx.tolist() == [0, 2, 3] and cnt.tolist() == [1, 1, 2]
+    assert q.sample2all(s, 2, format="count_dict_bin") == {"00": 1, "10": 1, "11": 2}
+    assert q.sample2all(s, 2, format="count_dict_int") == {0: 1, 2: 1, 3: 2}
+    with pytest.raises(ValueError):
+        q.sample2all(s, 2, format="nonsense")
+    with pytest.raises(ValueError):
+        q.sample2all(torch.zeros(2, 2, 2), 2)
