@@ -1,17 +1,21 @@
 """
 Differentiable statevector evolution (north-star kernel (3)).
 
-`evolve(cc, gatebuf, init)` is a `torch.autograd.Function` whose forward runs the fused
-pass programs and whose backward is the *adjoint method*: instead of saving every
-intermediate 2^n state (what autograd over `torch.tensordot` does in the reference,
-tensorcircuit/backends/pytorch_backend.py:775-786), it keeps only the final state and
-walks the gates in reverse, un-computing |psi> with U^dagger while propagating the
-cotangent |lam>, and reducing  dL/dU = sum lam (x) conj(psi_in)  per gate — all three in one
-pass over the two states per gate (`tcb_sv_adjoint_step`).  Memory: 2 states + 1 scratch, independent of depth.
+`evolve(cc, gatebuf, init)` is a `torch.autograd.Function` whose forward runs the fused pass programs and whose
+backward is the *adjoint method*: instead of saving every intermediate 2^n state (what autograd over
+`torch.tensordot` does in the reference, tensorcircuit/backends/pytorch_backend.py:775-786), it keeps only the
+final state and walks the circuit in reverse, un-computing |psi> with U^dagger while propagating the cotangent
+|lam> and reducing  dL/dU = sum lam (x) conj(psi_in).  Memory: 2 states + 1 scratch, independent of depth.
 
-Valid for unitary gates (every factory in gates.py except user matrices passed to
-`any` / `diagonal`); `assume_unitary = False` switches to recomputing psi_in from the
-start for each gate (O(G^2) passes, exact for arbitrary matrices).
+The walk is layered (`_AdjointTables.segments`): runs of diagonal gates, runs of one-qubit gates on distinct
+qubits and runs of constant gates are differentiated / un-applied as a whole (`_DiagRun`, `_OneQubitRun`,
+`_ConstRun`, `_FusedUnapply`: a few reads of psi and lam + fused sub-circuits), everything else takes one fused
+launch per gate (`tcb_sv_adjoint_step`).  Under `torch.vmap` (`backend.vmap / vvag`) the same walk runs over a
+batch of states at once (`_EvolveBatched`).
+
+Valid for unitary gates (every factory in gates.py except user matrices passed to `any` / `diagonal`);
+`assume_unitary = False` (recompute psi_in from the start for each gate, exact for arbitrary matrices) is not
+implemented.
 """
 
 from __future__ import annotations
@@ -21,7 +25,6 @@ from typing import Any, Dict, List, Optional
 import torch
 
 from . import _lib, svengine
-from .passplan import GateOp
 
 assume_unitary = True
 
@@ -39,19 +42,6 @@ def _forward(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor, init: Option
         _lib.require_cuda(state, "inputs")
     cc.run(state, gatebuf)
     return state
-
-
-def _apply_single(state: torch.Tensor, nbits: int, nq: int, op: GateOp, mat: torch.Tensor) -> None:
-    """Apply one k-qubit dense matrix (device tensor, row-major) in place (unfused launch)."""
-    bp = _lib.int_array([nq - 1 - q for q in op.qubits])
-    _lib.call("tcb_sv_apply_dense", state.data_ptr(), nbits, 1, bp, op.k, mat.data_ptr(), 0, _lib.stream_ptr())
-
-
-def _dense_matrix(gatebuf: torch.Tensor, op: GateOp) -> torch.Tensor:
-    d = 1 << op.k
-    if op.kind[0] == "diagvec":
-        return torch.diag(gatebuf[op.mat_off : op.mat_off + d])
-    return gatebuf[op.mat_off : op.mat_off + d * d].reshape(d, d)
 
 
 diag_run_min = 3  # shorter runs of diagonal gates are walked gate by gate
