@@ -545,3 +545,28 @@ def test_backend_vmap_and_vvag_paths_on_plain_torch_functions():
         assert backend.last_vmap_path.startswith("loop") and tuple(ga.shape) == (3, 2)
     finally:
         backend.batched_mode = old
+
+
+def test_public_entry_points_fail_loudly_without_a_gpu(built):
+    """No CPU fallback anywhere on the product path: without a CUDA device the statevector route, the torch
+    interface, the Pauli-sum operators and the sampler raise EngineError instead of computing on the host."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    c = tc.Circuit(2)
+    c.h(0)
+    c.cnot(0, 1)
+    with pytest.raises(tc._lib.EngineError):
+        c.wavefunction()
+    with pytest.raises(tc._lib.EngineError):
+        tc.interfaces.torch_interface(lambda p: p.sum())(torch.ones(2))
+    h = tc.quantum.PauliStringSum([[3, 3]], [1.0])
+    with pytest.raises(tc._lib.EngineError):
+        h.expectation(torch.ones(4, dtype=torch.complex64))
+    with pytest.raises(tc._lib.EngineError):
+        tc.sampling.StateSampler(torch.ones(4, dtype=torch.complex64), 2)
+    with pytest.raises(tc._lib.EngineError):
+        c.sample(batch=2, allow_state=True)
