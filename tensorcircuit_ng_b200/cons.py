@@ -118,12 +118,14 @@ class _UnionFind:
             self.parent[rb] = ra
 
 
-def get_tn_info(nodes: Sequence[Any]):
+def get_tn_info(nodes: Sequence[Any], use_primitives: Optional[bool] = None):
     """(input_sets, output_set, size_dict), sorted nodes — cons.py:773-804 for plain networks and
     cons.py:492-547 (`_extract_topology`) when CopyNode hyperedges are present: same node order
-    (`_stable_id_`), same edge order (`sorted_edges`), same symbol assignment."""
+    (`_stable_id_`), same edge order (`sorted_edges`), same symbol assignment.
+    `use_primitives` follows cons.py:898-908: True, or None with CopyNodes present, takes the hyperedge
+    description; False keeps CopyNodes as ordinary (dense delta) nodes."""
     nodes_new = sorted(nodes, key=lambda node: getattr(node, "_stable_id_", -1))
-    has_hyper = any(_is_copynode(n) for n in nodes_new)
+    has_hyper = any(_is_copynode(n) for n in nodes_new) if use_primitives is None else bool(use_primitives)
     if not has_hyper:
         all_edges_sorted = sorted_edges(_all_edges(nodes_new))
         mapping: Dict[int, str] = {}
@@ -318,11 +320,15 @@ def _z_moment(ket: torch.Tensor, n: int, zq: Sequence[int]) -> Optional[torch.Te
     return build([[i] for i in range(n)] + [[i, j] for i in range(n) for j in range(i + 1, n)])
 
 
-def _expectation_value(ket: torch.Tensor, n: int, ops: Sequence[Tuple[Any, Tuple[int, ...]]]) -> torch.Tensor:
-    from . import expect
+def _expectation_value(ket: torch.Tensor, n: int, ops: Sequence[Tuple[Any, Tuple[int, ...]]]) -> Optional[torch.Tensor]:
+    from . import autograd, expect
 
     psi = ket.reshape(-1)
     paulis = [_pauli_of(op) for op, _ in ops]
+    if torch.is_grad_enabled() and any(p is None and autograd.wants_grad(op.tensor) for (op, _), p in zip(ops, paulis)):
+        # a trainable operator tensor: the reduction kernels treat operators as constants, so this sandwich
+        # goes to the tensor-network route, whose pairwise contractions differentiate every operand
+        return None
     if all(p in ("z", "i") for p in paulis) and not (ket.requires_grad and torch.is_grad_enabled()):
         zq = sorted(ax[0] for (op, ax), p in zip(ops, paulis) if p == "z")
         if 1 <= len(zq) <= 2:
@@ -357,7 +363,8 @@ def b200_contractor(nodes: List[Any], output_edge_order: Optional[List[Any]] = N
         rec = _recognize_expectation(nodes)
         if rec is not None:
             val = _expectation_value(*rec)
-            return _finalize(nodes, val, [], order, ignore_edge_order)
+            if val is not None:
+                return _finalize(nodes, val, [], order, ignore_edge_order)
     # 3. general tensor network
     return _tn_route(nodes, order, ignore_edge_order, optimizer, **kws)
 
@@ -437,11 +444,79 @@ def wire_groups(input_sets: Sequence[Sequence[str]], sorted_nodes: Sequence[Any]
     return {x: find(x) for t in input_sets for x in t}
 
 
+def _merge_single_gates(nodes: Sequence[Any]) -> List[Any]:
+    """The reference's `preprocessing=True` step (tensorcircuit/cons.py:298-374): every node of rank <= 2 is
+    absorbed into the neighbour on its first connected leg, newly created small nodes first.  The merged node
+    takes the LATER of the two list positions and a fresh `_stable_id_`, so the node order, the edge axes and
+    hence the symbols an optimizer sees afterwards are the reference's."""
+    slots: List[Any] = list(nodes)
+    where: Dict[int, int] = {id(n): i for i, n in enumerate(slots)}
+    todo = deque(n for n in slots if len(n.shape) <= 2)
+    waiting: Set[int] = {id(n) for n in todo}
+    while todo:
+        small = todo.popleft()
+        if id(small) not in waiting:
+            continue  # already absorbed as somebody's neighbour
+        waiting.discard(id(small))
+        bond = next((e for e in small.edges[:2] if not e.is_dangling()), None)
+        if bond is None:
+            continue
+        a, b = bond.node1, bond.node2
+        ia, ib = where.pop(id(a)), where.pop(id(b), None)
+        merged = tn.contract_parallel(bond)
+        waiting.discard(id(a))
+        waiting.discard(id(b))
+        if ib is None or ib == ia:  # a trace leg: the node is replaced in its own slot
+            slots[ia] = merged
+            where[id(merged)] = ia
+        else:
+            slots[min(ia, ib)] = None
+            slots[max(ia, ib)] = merged
+            where[id(merged)] = max(ia, ib)
+        if len(merged.shape) <= 2:
+            todo.appendleft(merged)
+            waiting.add(id(merged))
+    return [n for n in slots if n is not None]
+
+
+def contraction_info_decorator(algorithm: Callable[..., Any]) -> Callable[..., Any]:
+    """cons.py:1084-1120: print the cost summary of the path an optimizer returns (same line format; the
+    numbers come from `planner.path_stats`, the cotengra accounting of SURVEY §8d)."""
+    import math
+    import time
+
+    def new_algorithm(input_sets: Any, output_set: Any, size_dict: Any, **kws: Any) -> Any:
+        t0 = time.time()
+        path = algorithm(input_sets, output_set, size_dict, **kws)
+        dt = time.time() - t0
+        st = planner.path_stats(input_sets, output_set, size_dict, [p for p in path if len(p) == 2])
+        print("------ contraction cost summary ------")
+        print(
+            "log10[FLOPs]: ", "%.3f" % math.log10(max(st["flops"], 1.0)),
+            " log2[SIZE]: ", "%.0f" % math.log2(max(st["size"], 1.0)),
+            " log2[WRITE]: ", "%.3f" % math.log2(max(st["write"], 1.0)),
+            " PathFindingTime: ", "%.3f" % dt,
+        )  # fmt: skip
+        return path
+
+    return new_algorithm
+
+
+def _strip_exponent(t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(mantissa, exponent) with t = mantissa * 10 ** exponent and max |mantissa| = 1: the return convention of
+    cotengra's `tree.contract(..., strip_exponent=True)` that cons.py:736-740,763-764 passes on
+    [UPSTREAM-UNVERIFIED base-10 convention]."""
+    scale = t.detach().abs().max()
+    safe = torch.where(scale > 0, scale, torch.ones_like(scale))
+    return t / safe, torch.log10(safe)
+
+
 def _tn_route(nodes: List[Any], order: Optional[List[Any]], ignore_edge_order: bool, optimizer: Any,
               **kws: Any) -> Any:  # fmt: skip
-    (input_sets, output_set, size_dict), sorted_nodes = get_tn_info(nodes)
+    (input_sets, output_set, size_dict), sorted_nodes = get_tn_info(nodes, kws.get("use_primitives"))
     tensors = [n.tensor for n in sorted_nodes]
-    if kws.get("hyper_diagonal", True):
+    if kws.get("hyper_diagonal", optimizer is None):
+        # (a caller-supplied path / optimizer is computed for the reference's network: leave it alone)
         input_sets, output_set, size_dict, tensors = diagonal_to_hyperedges(
             input_sets, output_set, size_dict, sorted_nodes, tensors)  # fmt: skip
     device = svengine.pick_device(tensors)
@@ -454,7 +529,7 @@ def _tn_route(nodes: List[Any], order: Optional[List[Any]], ignore_edge_order: b
     elif optimizer is not None:
         path = optimizer(input_sets, output_set, size_dict)
     else:
-        path = planner.greedy(input_sets, output_set, size_dict)
+        path = planner.greedy_alpha(input_sets, output_set, size_dict)
     # the tree writes the caller's edge order directly (no final transpose, K2)
     if order is not None and not ignore_edge_order and len(set(output_set)) == len(output_set):
         sym_of = {id(e): s for e, s in zip(dangling, output_set)}
@@ -464,6 +539,9 @@ def _tn_route(nodes: List[Any], order: Optional[List[Any]], ignore_edge_order: b
         want = list(output_set)
         result_edges = list(dangling)
     out = tnengine.contract_tree(tensors, input_sets, want, path)
+    if kws.get("strip_exponent", False):
+        out, exponent = _strip_exponent(out)
+        return _finalize(nodes, out, result_edges, order, ignore_edge_order), exponent
     return _finalize(nodes, out, result_edges, order, ignore_edge_order)
 
 
@@ -480,18 +558,50 @@ def plain_contractor(nodes: List[Any], output_edge_order: Optional[List[Any]] = 
     return final_node
 
 
+_CUSTOM_KWS = ("preprocessing", "strip_exponent", "hyper_diagonal", "contraction_info")
+
+
 def custom(nodes: List[Any], optimizer: Any, memory_limit: Optional[int] = None,
            output_edge_order: Optional[List[Any]] = None, ignore_edge_order: bool = False,
-           debug_level: int = 0, **kws: Any) -> Any:  # fmt: skip
-    """cons.py:1007-1050 Level-1 plug: the caller's planner, our executor."""
+           debug_level: int = 0, use_primitives: Optional[bool] = None, **kws: Any) -> Any:  # fmt: skip
+    """cons.py:1007-1050 Level-1 plug: the caller's planner, our executor.  Same behaviour as the reference:
+    fewer than five nodes use the exhaustive `optimal` search (:1019-1030), `preprocessing` merges rank <= 2
+    nodes first unless the network has hyperedges (:1034), the optimizer may be a literal path (:1037-1040) and
+    `strip_exponent` returns `(node, exponent)` (:763-764)."""
+    unknown = sorted(k for k in kws if k not in _CUSTOM_KWS)
+    if unknown:
+        raise TypeError(f"custom contractor: unsupported option(s) {unknown}; honoured: {list(_CUSTOM_KWS)}")
     nodes = list(nodes)
     order = _validate_edge_order(nodes, output_edge_order, ignore_edge_order)
     if debug_level == 2:
         shape = [e.dimension for e in order] if order else []
         return tn.Node(torch.zeros(shape, dtype=torch.complex64))
-    if not isinstance(optimizer, list) and optimizer is not None:
-        optimizer = partial(optimizer, memory_limit=memory_limit)
-    return _tn_route(nodes, order, ignore_edge_order, optimizer)
+    has_hyper = any(_is_copynode(n) for n in nodes)
+    if len(nodes) < 5:
+        alg: Any = planner.optimal
+    else:
+        if kws.get("preprocessing") and not has_hyper:
+            nodes = _merge_single_gates(nodes)
+        alg = optimizer if isinstance(optimizer, list) or optimizer is None else partial(optimizer, memory_limit=memory_limit)
+    if alg is None:
+        alg = planner.greedy
+    return _tn_route(nodes, order, ignore_edge_order, alg, use_primitives=use_primitives,
+                     strip_exponent=kws.get("strip_exponent", False),
+                     hyper_diagonal=kws.get("hyper_diagonal", False))  # fmt: skip
+
+
+def custom_stateful(nodes: List[Any], optimizer: Any, memory_limit: Optional[int] = None,
+                    opt_conf: Optional[Dict[str, Any]] = None, output_edge_order: Optional[List[Any]] = None,
+                    ignore_edge_order: bool = False, use_primitives: Optional[bool] = None, **kws: Any) -> Any:  # fmt: skip
+    """cons.py:1053-1081: the optimizer class is instantiated afresh for every contraction."""
+    opt = optimizer(**(opt_conf or {}))
+    local = dict(kws)
+    debug_level = local.pop("debug_level", 0)
+    if local.pop("contraction_info", None):
+        opt = contraction_info_decorator(opt)
+    return custom(nodes, opt, memory_limit=memory_limit, output_edge_order=output_edge_order,
+                  ignore_edge_order=ignore_edge_order, debug_level=debug_level, use_primitives=use_primitives,
+                  **local)  # fmt: skip
 
 
 class NodesReturn(Exception):  # cons.py:964-973
@@ -504,35 +614,90 @@ def _get_sorted_nodes(nodes: List[Any], *args: Any, **kws: Any) -> Any:
     raise NodesReturn(sorted(nodes, key=lambda node: getattr(node, "_stable_id_", -1)))
 
 
+def _auto_path(input_sets: Any, output_set: Any, size_dict: Any, memory_limit: Optional[int] = None) -> Any:
+    """opt_einsum's "auto": exhaustive below five tensors, greedy from there on (its branch-* middle tiers are
+    not restated, so between 5 and 14 tensors this is greedy where opt_einsum would still search)."""
+    f = planner.optimal if len(input_sets) < 5 else planner.greedy
+    return f(input_sets, output_set, size_dict, memory_limit=memory_limit)
+
+
+# method names the reference forwards to `getattr(opt_einsum.paths, method)` (cons.py:1245-1246)
+_OPT_EINSUM_METHODS: Dict[str, Any] = {
+    "greedy": planner.greedy, "eager": planner.greedy, "opportunistic": planner.greedy,
+    "optimal": planner.optimal, "auto": _auto_path, "auto-hq": _auto_path,
+}  # fmt: skip
+_OPT_EINSUM_UNSUPPORTED = ("branch", "branch-all", "branch-2", "branch-1", "dp", "dynamic-programming",
+                           "random-greedy", "random-greedy-128")  # fmt: skip
+
+
 def set_contractor(method: Optional[str] = None, optimizer: Optional[Any] = None,
                    memory_limit: Optional[int] = None, opt_conf: Optional[Dict[str, Any]] = None,
                    set_global: bool = True, contraction_info: bool = False, debug_level: int = 0,
                    use_primitives: Optional[bool] = None, **kws: Any) -> Callable[..., Any]:  # fmt: skip
     """Same signature as the reference's `set_contractor` (cons.py:1123-1261).
 
-    method: "b200" (default: statevector passes + GPU tensor-network fallback), "tn" / "greedy"
-    (always the planned tensor-network executor, our greedy planner), "plain", "custom"
-    (caller's `optimizer`: callable `f(inputs, output, size_dict, memory_limit=None) -> path` or a
-    literal path), "before" (node capture).  "cotengra*" / "omeco*" need those packages and raise
-    ImportError like the reference when they are absent (cons.py:678-683)."""
+    method:
+      "b200" (default)   statevector passes / reduction kernels, planned tensor-network executor otherwise;
+      "greedy", "eager", "opportunistic", "optimal", "auto", "auto-hq"
+                         the opt_einsum path finders the reference resolves these names to (cons.py:1245-1246),
+                         restated in `planner` (same paths as the reference's default contractor), executed by
+                         the tensor-network engine through `custom`;
+      "tn"               always the tensor-network engine, with this package's own planner;
+      "plain"            literal node order (cons.py:429-463);
+      "custom" / "custom_stateful"   the caller's `optimizer` (callable
+                         `f(inputs, output, size_dict, memory_limit=None) -> path`, a literal path, or a class
+                         instantiated per call with `opt_conf`);
+      "before"           node capture (cons.py:976-1004).
+    Options honoured like the reference: `preprocessing` (merge rank <= 2 nodes first), `contraction_info`,
+    `debug_level`, `use_primitives`, `strip_exponent` (implies `use_primitives`, cons.py:1161-1163).  Anything
+    else raises `TypeError` instead of being dropped.  "cotengra*" / "omeco*" need those packages and raise
+    ImportError like the reference when they are absent (cons.py:678-683); opt_einsum's branch-and-bound /
+    dynamic-programming / random-greedy finders are not restated and raise ValueError."""
     if not method:
         method = "b200"
+    if kws.get("strip_exponent", False) and use_primitives is None:
+        use_primitives = True
     if method.startswith("cotengra") or method.startswith("omeco"):
         raise ImportError(
             f"contractor {method!r} needs the optional third-party planner, which is not installed; "
             "load a plan with experimental.DistributedContractor.from_path or pass "
             "method='custom', optimizer=<callable>"
         )
+    if method in _OPT_EINSUM_UNSUPPORTED:
+        raise ValueError(
+            f"contractor {method!r} is an opt_einsum path finder that this package does not restate (opt_einsum is "
+            f"not installed); available: {sorted(_OPT_EINSUM_METHODS)} or method='custom', optimizer=<callable>"
+        )
+    allowed = {"b200": ("hyper_diagonal", "force_tn"), "tn": ("hyper_diagonal",), "plain": (), "before": ()}
+    if method in allowed:
+        bad = sorted(k for k in kws if k not in allowed[method])
+        if opt_conf is not None or optimizer is not None or memory_limit is not None:
+            bad.append("optimizer / opt_conf / memory_limit")
+        if method in ("plain", "before") and (contraction_info or use_primitives is not None):
+            bad.append("contraction_info / use_primitives")
+        if bad:
+            raise TypeError(f"set_contractor({method!r}): unsupported option(s) {bad}")
     if method == "plain":
         cf: Callable[..., Any] = plain_contractor
     elif method == "before":
         cf = _get_sorted_nodes
     elif method == "b200":
-        cf = partial(b200_contractor, debug_level=debug_level, **kws)
-    elif method in ("tn", "greedy"):
-        cf = partial(b200_contractor, force_tn=True, debug_level=debug_level)
-    elif method == "custom":
-        cf = partial(custom, optimizer=optimizer, memory_limit=memory_limit, debug_level=debug_level)
+        cf = partial(b200_contractor, debug_level=debug_level, use_primitives=use_primitives, **kws)
+    elif method == "tn":
+        opt = contraction_info_decorator(planner.greedy_alpha) if contraction_info else None
+        cf = partial(b200_contractor, force_tn=True, optimizer=opt, debug_level=debug_level,
+                     use_primitives=use_primitives, **kws)  # fmt: skip
+    elif method == "custom_stateful":
+        cf = partial(custom_stateful, optimizer=optimizer, opt_conf=opt_conf, memory_limit=memory_limit,
+                     contraction_info=contraction_info, debug_level=debug_level, use_primitives=use_primitives,
+                     **kws)  # fmt: skip
+    elif method == "custom" or method in _OPT_EINSUM_METHODS:
+        if method != "custom":
+            optimizer = _OPT_EINSUM_METHODS[method]
+        if contraction_info is True and not isinstance(optimizer, list) and optimizer is not None:
+            optimizer = contraction_info_decorator(optimizer)
+        cf = partial(custom, optimizer=optimizer, memory_limit=memory_limit, debug_level=debug_level,
+                     use_primitives=use_primitives, **kws)  # fmt: skip
     else:
         raise ValueError(f"Unknown contractor type: {method}")
     if set_global:

@@ -155,7 +155,13 @@ class _OperatorExpect(torch.autograd.Function):
     def backward(ctx: Any, g: torch.Tensor):  # type: ignore[override]
         psi, *mats = ctx.saved_tensors
         n, axes_list = ctx.meta
-        # s = psi^H O psi:  grad_psi = conj(g) O psi + g O^H psi   (operators are treated as constants)
+        if any(ctx.needs_input_grad[3:]):
+            raise _lib.EngineError(
+                "gradient with respect to an operator tensor was requested from the expectation reduction kernel, "
+                "which treats operators as constants; contract the sandwich with set_contractor('tn') instead "
+                "(cons.b200_contractor does this on its own when an operator requires grad)"
+            )
+        # s = psi^H O psi:  grad_psi = conj(g) O psi + g O^H psi   (operators are constants here)
         o_psi = psi.clone()
         oh_psi = psi.clone()
         for axes, m in zip(axes_list, mats):

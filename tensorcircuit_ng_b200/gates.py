@@ -55,6 +55,11 @@ class TrigFamily:
     def __init__(self, c0: np.ndarray, c1: np.ndarray, scale: float, kind: Tuple[Any, ...]) -> None:
         self.k = np.stack([np.asarray(c0).reshape(-1), np.asarray(c1).reshape(-1)]).astype(np.complex64)
         self.scale, self.kind = float(scale), kind
+        # cos(a) C0 + sin(a) C1 is unitary for every real a iff C0 = 1 and C1 = -i U with U Hermitian, U^2 = 1
+        d = int(round(math.sqrt(self.k.shape[1])))
+        c0m, um = self.k[0].reshape(d, d), 1j * self.k[1].reshape(d, d)
+        self.unitary = bool(np.allclose(c0m, np.eye(d), atol=1e-6) and np.allclose(um, um.conj().T, atol=1e-6)
+                            and np.allclose(um @ um, np.eye(d), atol=1e-6))  # fmt: skip
         self.numel = int(self.k.shape[1])
         nleg = int(round(math.log2(self.numel)))
         self.shape = (2,) * nleg
@@ -74,10 +79,45 @@ class TrigFamily:
 
 
 class _LazySpec:
-    __slots__ = ("family", "theta", "value")
+    """(family, theta) of a deferred gate.  The reference builds the matrix eagerly
+    (tensorcircuit/gates.py:692-743), so the VALUE theta has at gate creation is what counts: a
+    parameter that does not require grad is snapshotted here (host scalars as python floats, device
+    scalars as a detached copy); a differentiated one is kept by reference with its version counter and
+    `current_theta` refuses to build the gate once the tensor was modified in place."""
+
+    __slots__ = ("family", "theta", "value", "version")
 
     def __init__(self, family: TrigFamily, theta: torch.Tensor) -> None:
-        self.family, self.theta, self.value = family, theta, None
+        self.family, self.value, self.version = family, None, None
+        if _is_functorch(theta) or (theta.requires_grad and torch.is_grad_enabled()) or theta.grad_fn is not None:
+            self.theta = theta
+            self.version = _version_of(theta)
+        elif theta.is_cuda:
+            self.theta = theta.detach().clone()
+        else:
+            self.theta = torch.tensor(float(theta.detach().reshape(())), dtype=theta.dtype)
+
+    def current_theta(self) -> torch.Tensor:
+        if self.version is not None and _version_of(self.theta) != self.version:
+            raise RuntimeError(
+                "a gate parameter was modified in place after the gate was created; the reference builds gate "
+                "matrices eagerly, so rebuild the circuit (or pass a copy of the parameter)"
+            )
+        return self.theta
+
+
+def _is_functorch(t: torch.Tensor) -> bool:
+    try:
+        return bool(torch._C._functorch.is_functorch_wrapped_tensor(t))
+    except Exception:  # pylint: disable=broad-except
+        return type(t) is not torch.Tensor
+
+
+def _version_of(t: torch.Tensor) -> Optional[int]:
+    try:
+        return int(t._version)
+    except Exception:  # pylint: disable=broad-except  (functorch wrappers)
+        return None
 
 
 class LazyGate(Gate):
@@ -91,6 +131,7 @@ class LazyGate(Gate):
         self.backend = None
         self._stable_id_ = tn._next_id()
         self._b200_kind = spec.family.kind
+        self._b200_unitary = spec.family.unitary
 
     def pending(self) -> bool:
         return self._own is None and self._lazy.value is None
@@ -101,7 +142,7 @@ class LazyGate(Gate):
             return self._own
         sp = self._lazy
         if sp.value is None:
-            sp.value = sp.family.batched(sp.theta.reshape(1))[0].reshape(sp.family.shape)
+            sp.value = sp.family.batched(sp.current_theta().reshape(1))[0].reshape(sp.family.shape)
         return sp.value
 
     @tensor.setter
@@ -120,6 +161,7 @@ class LazyGate(Gate):
             t = self.tensor
             g = Gate(t.conj() if conjugate else t, name=self.name)
             g._b200_kind = self._b200_kind  # type: ignore[attr-defined]
+            g._b200_unitary = self._b200_unitary  # type: ignore[attr-defined]
             return g
         return LazyGate(self._lazy, name=self.name)  # shares the spec: materialised at most once
 
@@ -212,9 +254,13 @@ def _is_diag_host(m: np.ndarray) -> bool:
     return bool(np.count_nonzero(mm - np.diag(np.diagonal(mm))) == 0)
 
 
-def _mk(t: torch.Tensor, kind: Tuple[Any, ...], name: Optional[str] = None) -> Gate:
+def _mk(t: torch.Tensor, kind: Tuple[Any, ...], name: Optional[str] = None, unitary: bool = True) -> Gate:
+    """`unitary`: the factory guarantees U^dagger U = 1 (every reference gate except user matrices and
+    complex-time exponentials); the adjoint-method backward un-computes the state with U^dagger and checks the
+    others on the device before relying on it (svengine.run_circuit_network)."""
     g = Gate(t, name=name)
     g._b200_kind = kind  # type: ignore[attr-defined]
+    g._b200_unitary = unitary  # type: ignore[attr-defined]
     return g
 
 
@@ -374,7 +420,7 @@ def any_gate(unitary: Any, name: str = "any") -> Gate:  # gates.py:866-890
             unitary._b200_kind = ("dense",)  # type: ignore[attr-defined]
         return unitary  # type: ignore[return-value]
     kind = _probe_kind(unitary)
-    return _mk(_reshape2(num_to_tensor(unitary)), kind, name=name)
+    return _mk(_reshape2(num_to_tensor(unitary)), kind, name=name, unitary=False)
 
 
 def exponential_gate(unitary: Any, theta: float, name: str = "none") -> Gate:  # gates.py:893-914
@@ -382,7 +428,7 @@ def exponential_gate(unitary: Any, theta: float, name: str = "none") -> Gate:  #
     th, u = _scalar(theta), num_to_tensor(unitary)
     d = int(round(math.sqrt(u.numel())))
     mat = torch.linalg.matrix_exp(-1.0j * th * u.reshape(d, d))
-    return _mk(_reshape2(mat), kind, name="exp-" + name)
+    return _mk(_reshape2(mat), kind, name="exp-" + name, unitary=False)
 
 
 def exponential_gate_unity(unitary: Any, theta: float, half: bool = False, name: str = "none") -> Gate:
@@ -403,7 +449,7 @@ def exponential_gate_unity(unitary: Any, theta: float, half: bool = False, name:
     if half is True:
         th = th / 2.0
     mat = torch.cos(th) * it - 1.0j * torch.sin(th) * u
-    return _mk(mat, kind, name="exp1-" + name)
+    return _mk(mat, kind, name="exp1-" + name, unitary=False)
 
 
 _eyes: Dict[int, np.ndarray] = {}
@@ -452,7 +498,7 @@ def _controlled(f: Callable[..., Gate], name: str, on: int) -> Callable[..., Gat
             kind = ("ctrl", 1, on)
         else:
             kind = ("dense",)
-        return _mk(_reshape2(cu), kind, name=name)
+        return _mk(_reshape2(cu), kind, name=name, unitary=bool(getattr(base, "_b200_unitary", False)))
 
     return g
 
@@ -470,7 +516,7 @@ orz_gate = _controlled(rz_gate, "orz", 0)
 def diagonal_gate(diag: Any, dim: int = 2, name: str = "diagonal") -> Gate:  # gates.py:1059-1078
     d = num_to_tensor(diag)
     noe = int(round(math.log(d.numel()) / math.log(dim)))
-    return _mk(d.reshape([dim] * noe), ("diagvec",), name=name)
+    return _mk(d.reshape([dim] * noe), ("diagvec",), name=name, unitary=False)
 
 
 # ---- memoised construction -----------------------------------------------------------------
@@ -487,8 +533,10 @@ def _memo_key(v: Any) -> Any:
         return ("v", type(v).__name__, v)
     if isinstance(v, np.generic):
         return ("v", "np", v.item())
-    if type(v) is torch.Tensor and v.numel() == 1:
-        return ("t", v.data_ptr(), str(v.dtype), str(v.device), v._version, bool(v.requires_grad))
+    if type(v) is torch.Tensor and v.numel() == 1 and not v.is_cuda and not _is_functorch(v):
+        # keyed on the VALUE: `.data` writes and numpy-shared buffers do not bump `_version`, so tensor
+        # identity can alias a stale matrix.  Device scalars are not memoised (reading them would sync).
+        return ("t", str(v.dtype), v.detach().reshape(()).item())
     if isinstance(v, np.ndarray) and v.size <= 64:
         return ("a", v.shape, v.dtype.str, v.tobytes())
     return None
@@ -502,8 +550,9 @@ def memoised_gate(gatef: Callable[..., Gate], kws: Dict[str, Any]) -> Gate:
         return gatef(**kws)  # deferred: built with its whole family in one batched expression
     for k in sorted(kws):
         v = kws[k]
-        if isinstance(v, torch.Tensor) and v.requires_grad and torch.is_grad_enabled():
-            return gatef(**kws)  # differentiated parameters: every call owns its autograd graph
+        if isinstance(v, torch.Tensor) and (_is_functorch(v) or v.grad_fn is not None
+                                            or (v.requires_grad and torch.is_grad_enabled())):  # fmt: skip
+            return gatef(**kws)  # differentiated / batched parameters: every call owns its autograd graph
         pk = _memo_key(v)
         if pk is None:
             return gatef(**kws)
@@ -514,11 +563,10 @@ def memoised_gate(gatef: Callable[..., Gate], kws: Dict[str, Any]) -> Gate:
         g = gatef(**kws)
         if len(_gate_memo) >= _GATE_MEMO_MAX:
             _gate_memo.clear()
-        # the parameters are kept alive with the entry so that a recycled data_ptr can never alias it
-        _gate_memo[key] = (dict(kws), g.tensor, getattr(g, "_b200_kind", ("dense",)))
+        _gate_memo[key] = (g.tensor, getattr(g, "_b200_kind", ("dense",)), bool(getattr(g, "_b200_unitary", False)))
         return g
-    _, tensor, kind = hit
-    return _mk(tensor, kind)
+    tensor, kind, uni = hit
+    return _mk(tensor, kind, unitary=uni)
 
 
 def matrix_for_gate(g: Gate) -> np.ndarray:

@@ -217,13 +217,181 @@ def path_stats(inputs: Sequence[Sequence[str]], output: Sequence[str], size_dict
     return {"flops": flops, "write": write, "size": size, "nslices": nslices, "steps": per_step}  # type: ignore[dict-item]
 
 
-def greedy(inputs: Sequence[Sequence[str]], output: Sequence[str], size_dict: Dict[str, int],
-           memory_limit: Optional[int] = None) -> List[Tuple[int, int]]:  # fmt: skip
-    """Optimizer callable with the reference's Level-1 plug signature."""
+def greedy_alpha(inputs: Sequence[Sequence[str]], output: Sequence[str], size_dict: Dict[str, int],
+                 memory_limit: Optional[int] = None, alpha: float = 1.0) -> List[Tuple[int, int]]:  # fmt: skip
+    """This module's own pairwise greedy (cost = out - alpha (a + b) on log sizes), Level-1 plug signature."""
     if len(inputs) == 1:
         return []
     net = _Net(inputs, output, size_dict)
-    return ssa_to_linear(_ssa_greedy(net), len(inputs))
+    return ssa_to_linear(_ssa_greedy(net, alpha), len(inputs))
+
+
+# ---- the reference's default planners -----------------------------------------------------------
+# `tc.set_contractor("greedy")` resolves to `opt_einsum.paths.greedy` (tensorcircuit/cons.py:1245-1246,
+# default at :1264) and `custom` uses `opt_einsum.paths.optimal` below five nodes (:1019-1030).  opt_einsum
+# (pinned 3.4.0, requirements/requirements-2411.txt) is absent from this image: the two functions below restate
+# its published algorithms on Python-int bitsets so that the product picks the SAME path as the reference's
+# default contractor (tests/test_host_logic.py pins them to the oracle's independent set-based restatement).
+def _prod_sizes(mask: int, sizes: Sequence[int]) -> int:
+    r = 1
+    for i in _bits(mask):
+        r *= sizes[i]
+    return r
+
+
+def _ssa_opt_einsum_greedy(inputs: Sequence[int], output: int, sizes: Sequence[int]) -> List[Tuple[int, ...]]:
+    """SSA path of opt_einsum's `ssa_greedy_optimize` with the default 'memory-removed' cost: repeatedly contract
+    the pair of tensors sharing an index whose result is smallest relative to its operands
+    (size(out) - size(a) - size(b)), ties by the larger, then the smaller, SSA id; identical index sets are
+    merged at once; what is left at the end is combined by outer products, smallest first."""
+    if len(inputs) == 1:
+        return [(0,)]
+    common = inputs[0]
+    for m in inputs[1:]:
+        common &= m
+    output = output | common
+    live: Dict[int, int] = {}  # index set -> SSA id
+    nxt = len(inputs)
+    ssa: List[Tuple[int, ...]] = []
+    for i, key in enumerate(inputs):
+        if key in live:  # Hadamard product of equal index sets
+            ssa.append((live[key], i))
+            live[key] = nxt
+            nxt += 1
+        else:
+            live[key] = i
+    holders: Dict[int, set] = {}  # contracted index -> index sets that carry it
+    for key in live:
+        for d in _bits(key & ~output):
+            holders.setdefault(d, set()).add(key)
+    ge2 = ge3 = 0  # indices carried by >= 2 / >= 3 live tensors
+    for d, ks in holders.items():
+        if len(ks) >= 2:
+            ge2 |= 1 << d
+        if len(ks) >= 3:
+            ge3 |= 1 << d
+    foot = {key: _prod_sizes(key, sizes) for key in live}
+    heap: List[Tuple[int, int, int, int, int, int]] = []
+
+    def push_best(k1: int, partners: Sequence[int]) -> None:
+        best = None
+        for k2 in partners:
+            either, two = k1 | k2, k1 & k2
+            one = either & ~two
+            k12 = (either & output) | (two & ge3) | (one & ge2)
+            cost = _prod_sizes(k12, sizes) - foot[k1] - foot[k2]
+            a, b = k1, k2
+            ia, ib = live[a], live[b]
+            if ia > ib:
+                a, ia, b, ib = b, ib, a, ia
+            cand = (cost, ib, ia, a, b, k12)
+            if best is None or cand[:3] < best[:3]:
+                best = cand
+        if best is not None:
+            heapq.heappush(heap, best)
+
+    for d, ks in holders.items():
+        order = sorted(ks, key=live.__getitem__)
+        for i, k1 in enumerate(order[:-1]):
+            push_best(k1, order[i + 1:])
+    while heap:
+        _, _, _, k1, k2, k12 = heapq.heappop(heap)
+        if k1 not in live or k2 not in live:
+            continue
+        id1, id2 = live.pop(k1), live.pop(k2)
+        for d in _bits(k1 & ~output):
+            holders[d].discard(k1)
+        for d in _bits(k2 & ~output):
+            holders[d].discard(k2)
+        ssa.append((id1, id2))
+        if k12 in live:
+            ssa.append((live[k12], nxt))
+            nxt += 1
+        else:
+            for d in _bits(k12 & ~output):
+                holders.setdefault(d, set()).add(k12)
+        live[k12] = nxt
+        nxt += 1
+        for d in _bits(k1 | (k2 & ~output)):
+            c = len(holders.get(d, ()))
+            bit = 1 << d
+            ge2 = (ge2 | bit) if c >= 2 else (ge2 & ~bit)
+            ge3 = (ge3 | bit) if c >= 3 else (ge3 & ~bit)
+        foot[k12] = _prod_sizes(k12, sizes)
+        near = set()
+        for d in _bits(k12 & ~output):
+            near |= holders[d]
+        near.discard(k12)
+        if near:
+            push_best(k12, sorted(near, key=live.__getitem__))
+    rest = [(_prod_sizes(key & output, sizes), i, key) for key, i in live.items()]
+    heapq.heapify(rest)
+    _, id1, k1 = heapq.heappop(rest)
+    while rest:
+        _, id2, k2 = heapq.heappop(rest)
+        ssa.append((min(id1, id2), max(id1, id2)))
+        k12 = (k1 | k2) & output
+        _, id1, k1 = heapq.heappushpop(rest, (_prod_sizes(k12, sizes), nxt, k12))
+        nxt += 1
+    return ssa
+
+
+def _ssa_to_linear_general(ssa: Sequence[Tuple[int, ...]]) -> List[Tuple[int, ...]]:
+    n = 1 + max(max(t) for t in ssa)
+    pos = list(range(n))
+    out: List[Tuple[int, ...]] = []
+    for ids in ssa:
+        out.append(tuple(int(pos[i]) for i in ids))
+        for i in ids:
+            for k in range(i, n):
+                pos[k] -= 1
+    return out
+
+
+def greedy(inputs: Sequence[Sequence[str]], output: Sequence[str], size_dict: Dict[str, int],
+           memory_limit: Optional[int] = None) -> List[Tuple[int, ...]]:  # fmt: skip
+    """The path `opt_einsum.paths.greedy` returns (the reference's default contractor,
+    tensorcircuit/cons.py:1245-1246,1264), in opt_einsum's linear convention."""
+    net = _Net(inputs, output, size_dict)
+    sizes = [size_dict[s] for s in net.names]
+    return _ssa_to_linear_general(_ssa_opt_einsum_greedy(net.inputs, net.output, sizes))
+
+
+def optimal(inputs: Sequence[Sequence[str]], output: Sequence[str], size_dict: Dict[str, int],
+            memory_limit: Optional[int] = None) -> List[Tuple[int, ...]]:  # fmt: skip
+    """`opt_einsum.paths.optimal`: depth-first search over all pair orders, minimising the flop count
+    (tensorcircuit/cons.py:1019-1030 uses it below five nodes)."""
+    net = _Net(inputs, output, size_dict)
+    sizes = [size_dict[s] for s in net.names]
+    n = len(net.inputs)
+    if n == 1:
+        return [(0,)]
+    if n > 10:
+        raise ValueError(f"'optimal' enumerates all pair orders; {n} tensors is too many (use 'greedy')")
+    best_flops = [float("inf")]
+    best_path: List[Tuple[Tuple[int, int], ...]] = [tuple()]
+
+    def walk(path: Tuple[Tuple[int, int], ...], alive: Tuple[int, ...], terms: Tuple[int, ...], flops: int) -> None:
+        if len(alive) == 1:
+            best_flops[0], best_path[0] = flops, path
+            return
+        for x in range(len(alive)):
+            for y in range(x + 1, len(alive)):
+                i, j = alive[x], alive[y]
+                keep = net.output
+                for r in alive:
+                    if r != i and r != j:
+                        keep |= terms[r]
+                either = terms[i] | terms[j]
+                k12 = either & keep
+                f = _prod_sizes(either, sizes) * (2 if either & ~k12 else 1)
+                if flops + f >= best_flops[0]:
+                    continue
+                rest = tuple(r for r in alive if r != i and r != j) + (len(terms),)
+                walk(path + ((i, j),), rest, terms + (k12,), flops + f)
+
+    walk(tuple(), tuple(range(n)), tuple(net.inputs), 0)
+    return _ssa_to_linear_general(best_path[0])
 
 
 def search(inputs: Sequence[Sequence[str]], output: Sequence[str], size_dict: Dict[str, int],

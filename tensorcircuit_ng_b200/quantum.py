@@ -43,6 +43,12 @@ class PauliStringSum:
     def __init__(self, structures: Sequence[Sequence[int]], weights: Optional[Sequence[complex]] = None,
                  nqubits: Optional[int] = None) -> None:  # fmt: skip
         ls = _to_host(structures).astype(np.int64).reshape(len(structures), -1) if len(structures) else None
+        # trainable weights (a torch tensor in an autograd graph): the device tables below hold detached values, so
+        # `expectation` goes term by term (dE/dw_t = <P_t>) and `mvp` refuses instead of dropping the gradient
+        self._live_weights: Optional[torch.Tensor] = None
+        if isinstance(weights, torch.Tensor) and (weights.requires_grad or weights.grad_fn is not None):
+            self._live_weights = weights
+            self._structures = ls
         if ls is None and nqubits is None:
             raise ValueError("an empty Pauli sum needs `nqubits`")
         self.n = int(ls.shape[1]) if ls is not None else int(nqubits)  # type: ignore[union-attr]
@@ -130,14 +136,28 @@ class PauliStringSum:
     def mvp(self, psi: torch.Tensor) -> torch.Tensor:
         """H psi, same shape as `psi` (flat [2^n] or [2]*n)."""
         shape = psi.shape
+        if self._live_weights is not None and torch.is_grad_enabled():
+            raise _lib.EngineError("PauliStringSum.mvp does not differentiate its weights; use `expectation`, or "
+                                   "build the sum from detached weights")
         return _MVP.apply(self._check(psi), self).reshape(shape)
 
     __call__ = mvp
 
     def expectation(self, psi: torch.Tensor) -> torch.Tensor:
         """<psi|H|psi> as a complex64 scalar (real up to rounding for a Hermitian sum)."""
-        from . import autograd
+        from . import autograd, expect
 
+        if self._live_weights is not None and torch.is_grad_enabled():
+            if autograd.is_batched(psi):
+                raise _lib.EngineError("trainable Pauli-sum weights are not supported under vmap")
+            flat = self._check(psi)
+            w = self._live_weights.to(flat.device).reshape(-1)
+            total = torch.zeros((), dtype=torch.complex64, device=flat.device)
+            for t in range(self._structures.shape[0]):  # type: ignore[union-attr]
+                row = self._structures[t]  # type: ignore[index]
+                xs, ys, zs = ([int(k) for k in np.nonzero(row == c)[0]] for c in (1, 2, 3))
+                total = total + w[t].to(torch.complex64) * expect.pauli_expectation(flat, self.n, xs, ys, zs)
+            return total
         if autograd.is_batched(psi):  # under torch.vmap: one launch for the whole batch
             phys, lvl = autograd.unwrap_batched(psi)
             with autograd.outside_vmap():

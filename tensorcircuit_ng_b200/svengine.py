@@ -28,6 +28,38 @@ class NotCircuitShaped(Exception):
     """The network is not `inputs -> gates -> dangling outputs`; use the TN path."""
 
 
+class NonUnitaryGradient(NotCircuitShaped):
+    """A gradient is wanted through a gate that is not unitary: the adjoint-method backward (which un-computes
+    the state with U^dagger) does not apply, the tensor-network route with ordinary autograd does."""
+
+
+unitarity_tol = 1e-4
+
+
+def _require_unitary_for_adjoint(gates: Sequence[Tuple[Any, Tuple[int, ...], bool]]) -> None:
+    """One batched device check  max |U^dagger U - 1|  over the gates whose factory does not guarantee unitarity
+    (`any`, `diagonal`, `exp` / `exp1` with a tensor generator or complex time, foreign nodes)."""
+    from . import autograd
+
+    worst = None
+    for node, qubits, packed in gates:
+        if getattr(node, "_b200_unitary", False):
+            continue
+        t = node.tensor
+        while autograd.is_batched(t):
+            t = torch._C._functorch.get_unwrapped(t)
+        t = t.detach().to(torch.complex64)
+        d = 1 << len(qubits)
+        if packed:
+            dev = (t.reshape(-1, d).abs() ** 2 - 1.0).abs().max()
+        else:
+            m = t.reshape(-1, d, d)
+            dev = (m.conj().transpose(1, 2) @ m - torch.eye(d, dtype=m.dtype, device=m.device)).abs().max()
+        worst = dev if worst is None else torch.maximum(worst, dev.to(worst.device))
+    if worst is not None and float(worst) > unitarity_tol:
+        raise NonUnitaryGradient(f"non-unitary gate (max |U^dagger U - 1| = {float(worst):.2e}) under autograd")
+
+
 # ---------------------------------------------------------------------------------------
 def _is_copynode(node: Any) -> bool:
     return type(node).__name__ == "CopyNode"
@@ -428,6 +460,12 @@ def build_gatebuf(tensors: Sequence[torch.Tensor], device: torch.device) -> torc
 _perm_cache: Dict[Any, torch.Tensor] = {}
 
 
+def autograd_is_batched(t: torch.Tensor) -> bool:
+    from . import autograd  # local import (autograd imports this module)
+
+    return autograd.is_batched(t)
+
+
 def assemble_gatebuf(gate_nodes: Sequence[Any], device: torch.device) -> torch.Tensor:
     """The gate buffer (every gate matrix, flat, in program order).  Deferred parametrised gates
     (`gates.LazyGate`) are built per family in one batched expression — a handful of torch ops and
@@ -446,7 +484,12 @@ def assemble_gatebuf(gate_nodes: Sequence[Any], device: torch.device) -> torch.T
     pieces = [build_gatebuf([gate_nodes[i].tensor for i in eager], device)] if eager else []
     order: List[Tuple[int, int]] = [(i, int(gate_nodes[i].tensor.numel())) for i in eager]  # (gate, numel) in cat order
     for fam, idx in fams.values():
-        thetas = torch.stack([gate_nodes[i]._lazy.theta.reshape(()).to(device=device, dtype=torch.float32) for i in idx])
+        ths = [gate_nodes[i]._lazy.current_theta() for i in idx]
+        if all(not t.is_cuda and not t.requires_grad and t.grad_fn is None and not autograd_is_batched(t) for t in ths):
+            # host snapshots (gates._LazySpec): one upload for the whole family
+            thetas = torch.tensor([float(t) for t in ths], dtype=torch.float32).to(device)
+        else:
+            thetas = torch.stack([t.reshape(()).to(device=device, dtype=torch.float32) for t in ths])
         pieces.append(fam.batched(thetas).reshape(-1))
         order.extend((i, fam.numel) for i in idx)
     cat = torch.cat(pieces) if len(pieces) > 1 else pieces[0]
@@ -483,10 +526,13 @@ def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) 
                     f"gradient with respect to a {len(g[1])}-qubit gate matrix is not supported (the adjoint walk "
                     "differentiates 1- and 2-qubit gates; wider gates must be constants)"
                 )
-    gatebuf = assemble_gatebuf([g[0] for g in gates], device)
     init = None
     if init_node is not None:
         init = init_node.tensor.to(torch.complex64).to(device).reshape(-1)
+    if torch.is_grad_enabled() and (any(autograd.wants_grad(t) for t in probe)
+                                    or (init is not None and autograd.wants_grad(init))):  # fmt: skip
+        _require_unitary_for_adjoint(gates)
+    gatebuf = assemble_gatebuf([g[0] for g in gates], device)
     const_mask = None
     if torch.is_grad_enabled() and len(gates) == len(cc.ops):
         # which gates are constants (no gradient wanted): the backward walk un-applies runs of them in fused passes

@@ -1,0 +1,194 @@
+"""CPU tier, round 2: plan parity with the oracle's restatement of the reference's default planners, the
+`preprocessing` network rewrite, `set_contractor` option handling, and the gate-construction regressions
+(stale memo, deferred theta snapshots)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import tc_oracle
+from helpers import brickwork, build, qaoa, random_layers
+
+
+def _rand_net(rng, n, nidx, maxdeg=4, sizes=(2,)):
+    syms = [chr(97 + i) if i < 26 else chr(200 + i) for i in range(nidx)]
+    inputs = [rng.sample(syms, rng.randint(1, min(maxdeg, nidx))) for _ in range(n)]
+    cnt = {}
+    for t in inputs:
+        for s in t:
+            cnt[s] = cnt.get(s, 0) + 1
+    out = [s for s in syms if cnt.get(s, 0) == 1 and rng.random() < 0.7]
+    return inputs, out, {s: rng.choice(sizes) for s in syms}
+
+
+def test_greedy_and_optimal_paths_equal_the_oracle_on_random_networks():
+    """`planner.greedy / optimal` (bitset restatement of opt_einsum 3.4.0, the planners behind the reference's
+    `set_contractor("greedy")`, cons.py:1245-1264, and `custom` below five nodes, :1019-1030) return the SAME
+    linear path as the oracle's independent set-based restatement."""
+    from tc_oracle import paths
+    from tensorcircuit_ng_b200 import planner
+
+    rng = random.Random(7)
+    for trial in range(300):
+        n, ni = rng.randint(2, 16), rng.randint(2, 18)
+        inp, out, sd = _rand_net(rng, n, ni, sizes=(2,) if trial % 2 else (2, 3, 4))
+        assert [tuple(p) for p in planner.greedy(inp, out, sd)] == [tuple(p) for p in paths.greedy(inp, out, sd)]
+        if n <= 5:
+            assert [tuple(p) for p in planner.optimal(inp, out, sd)] == [tuple(p) for p in paths.optimal(inp, out, sd)]
+
+
+def _networks(mod):
+    """Circuit, amplitude, expectation and CopyNode (diagonal API) networks, as node lists."""
+    nets = []
+    c = build(mod, 6, brickwork(6, 3, seed=1))
+    nets.append(("circuit", c._copy()[0]))
+    c = build(mod, 5, random_layers(5, 2, seed=3))
+    nets.append(("random", c._copy()[0]))
+    c = build(mod, 6, qaoa(6, 2, seed=0)[0])
+    nets.append(("amplitude", c.amplitude_before("010011")))
+    c = build(mod, 6, brickwork(6, 2, seed=5))
+    nets.append(("expectation", c.expectation_before((mod.gates.z(), [0]), (mod.gates.z(), [3]), reuse=False)))
+    c = mod.Circuit(4)
+    for q in range(4):
+        c.h(q)
+    c.diagonal(0, 1, diag=np.exp(1j * np.arange(4)).astype(np.complex64))
+    c.rx(1, theta=0.3)
+    c.diagonal(2, diag=np.array([1.0, 1j], dtype=np.complex64))
+    c.cnot(2, 3)
+    nets.append(("copynode", c._copy()[0]))
+    return nets
+
+
+def test_get_tn_info_and_default_paths_equal_the_oracle():
+    """Product vs oracle on the same networks: identical symbols (`_get_path_cache_friendly`, cons.py:773-800;
+    `_extract_topology` for CopyNodes, :492-547), identical greedy path, also after `preprocessing`
+    (`_merge_single_gates`, :298-374)."""
+    import tensorcircuit_ng_b200 as tc
+    from tc_oracle import cons as ocons, paths
+    from tensorcircuit_ng_b200 import cons, planner
+
+    for (name, pn), (_, on) in zip(_networks(tc), _networks(tc_oracle)):
+        (pi, po, ps), _ = cons.get_tn_info(pn)
+        if name == "copynode":  # hyperedge description (cons.py:492-547)
+            _, oi, oo, os_ = ocons._extract_topology(on)
+            oi, oo = [list(t) for t in oi], list(oo)
+        else:
+            (oi, oo, os_), _ = ocons.get_tn_info(on)
+        assert pi == oi and po == oo and ps == os_, name
+        assert [tuple(p) for p in planner.greedy(pi, po, ps)] == [tuple(p) for p in paths.greedy(oi, oo, os_)], name
+
+
+def test_merge_single_gates_equals_the_oracle():
+    import tensorcircuit_ng_b200 as tc
+    from tc_oracle import cons as ocons
+    from tensorcircuit_ng_b200 import cons
+
+    if not torch.cuda.is_available():
+        pytest.skip("the merge contracts tensors: needs the GPU engine (covered in the gpu tier)")
+    for (name, pn), (_, on) in zip(_networks(tc)[:2], _networks(tc_oracle)[:2]):
+        pm = cons._merge_single_gates(pn)
+        om, _ = ocons._merge_single_gates(on)
+        assert len(pm) == len(om), name
+        assert cons.get_tn_info(pm)[0] == ocons.get_tn_info(om)[0], name
+
+
+def test_set_contractor_options_are_honoured_or_refused():
+    from tensorcircuit_ng_b200 import cons
+
+    old = cons.contractor
+    try:
+        with pytest.raises(TypeError, match="unsupported option"):
+            cons.set_contractor("b200", preprocessing=True)
+        with pytest.raises(TypeError, match="unsupported option"):
+            cons.set_contractor("custom", optimizer=[(0, 1)], no_such_option=1)(
+                [cons.tn.Node(torch.zeros(2)) for _ in range(6)], ignore_edge_order=True)
+        with pytest.raises(ValueError, match="opt_einsum path finder"):
+            cons.set_contractor("dp")
+        with pytest.raises(ImportError):
+            cons.set_contractor("cotengra")
+        with pytest.raises(ValueError, match="Unknown contractor"):
+            cons.set_contractor("nope")
+        for m in ("greedy", "optimal", "auto", "eager"):
+            cf = cons.set_contractor(m, preprocessing=True, set_global=False)
+            assert cf.func is cons.custom and cf.keywords["preprocessing"] is True
+        cf = cons.set_contractor("custom", optimizer=lambda *a, **k: [], strip_exponent=True, set_global=False)
+        assert cf.keywords["use_primitives"] is True  # cons.py:1161-1163
+    finally:
+        cons._set_global_contractor(old)
+
+
+def test_contraction_info_prints_the_reference_summary(capsys):
+    from tensorcircuit_ng_b200 import cons, planner
+
+    inp, out, sd = [["a", "b"], ["b", "c"], ["c", "d"]], ["a", "d"], {k: 2 for k in "abcd"}
+    path = cons.contraction_info_decorator(planner.greedy)(inp, out, sd)
+    assert len(path) == 2
+    text = capsys.readouterr().out
+    assert "contraction cost summary" in text and "log10[FLOPs]" in text and "log2[WRITE]" in text
+
+
+# ---- gate construction regressions ---------------------------------------------------
+def test_memoised_gates_are_keyed_on_values_not_tensor_identity():
+    from tensorcircuit_ng_b200 import gates
+
+    p = torch.tensor([0.3], requires_grad=True)
+    with torch.no_grad():
+        g1 = gates.memoised_gate(gates.crx_gate, {"theta": p[0]}).tensor.reshape(4, 4).clone()
+        p.data += 1.0
+        g2 = gates.memoised_gate(gates.crx_gate, {"theta": p[0]}).tensor.reshape(4, 4)
+    assert abs(float(g1[2, 2].real) - np.cos(0.15)) < 1e-6
+    assert abs(float(g2[2, 2].real) - np.cos(0.65)) < 1e-6, "stale memoised matrix"
+    th = torch.tensor(0.4)
+    with torch.no_grad():
+        a = gates.memoised_gate(gates.phase_gate, {"theta": th}).tensor.clone()
+        th.fill_(1.1)
+        b = gates.memoised_gate(gates.phase_gate, {"theta": th}).tensor
+    assert abs(complex(a[1, 1]) - np.exp(0.4j)) < 1e-6 and abs(complex(b[1, 1]) - np.exp(1.1j)) < 1e-6
+
+
+def test_memoised_gate_survives_plain_vmap():
+    from tensorcircuit_ng_b200 import gates
+
+    def f(t):
+        return gates.memoised_gate(gates.phase_gate, {"theta": t}).tensor[1, 1]
+
+    out = torch.vmap(f)(torch.tensor([0.1, 0.2, 0.3]))
+    assert np.allclose(out.numpy(), np.exp(1j * np.array([0.1, 0.2, 0.3])), atol=1e-6)
+
+
+def test_deferred_gates_snapshot_theta_at_creation():
+    """The reference builds gate matrices eagerly (gates.py:692-743): reusing a scratch buffer for the
+    parameters of consecutive gates must not rewrite the earlier ones."""
+    import tensorcircuit_ng_b200 as tc
+
+    buf = torch.zeros(1)
+    c = tc.Circuit(2)
+    for q, a in enumerate([0.3, 1.2]):
+        buf[0] = a
+        c.rx(q, theta=buf[0])
+    nodes, _ = c._copy()
+    gs = [n for n in nodes if getattr(n, "_b200_kind", None) is not None and len(n.shape) == 2]
+    vals = sorted(float(g.tensor[0, 0].real) for g in gs)
+    assert np.allclose(vals, sorted([np.cos(0.15), np.cos(0.6)]), atol=1e-6)
+    # a differentiated parameter is kept by reference; an in-place change is refused, not silently used
+    p = torch.tensor([0.3], requires_grad=True)
+    c = tc.Circuit(1)
+    c.rx(0, theta=p[0])
+    with torch.no_grad():
+        p.add_(1.0)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        [n.tensor for n in c._copy()[0]]
+
+
+def test_untrusted_gates_are_flagged_for_the_adjoint_check():
+    from tensorcircuit_ng_b200 import gates
+
+    assert gates.rx_gate(theta=torch.tensor(0.3))._b200_unitary
+    assert gates.h()._b200_unitary and gates.cnot()._b200_unitary
+    assert gates.crx_gate(theta=0.2)._b200_unitary
+    assert gates.exp1_gate(gates._zz_matrix, torch.tensor(0.2))._b200_unitary
+    assert not gates.any_gate(np.eye(2))._b200_unitary
+    assert not gates.diagonal_gate(np.ones(2))._b200_unitary
+    assert not gates.exp_gate(gates._x_matrix, -0.3j)._b200_unitary
+    assert not gates.exp1_gate(np.array([[1.0, 0.0], [0.0, 2.0]]), torch.tensor(0.2))._b200_unitary
