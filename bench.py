@@ -42,6 +42,13 @@ from typing import Any, Dict, List, Tuple
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The CPU legs (`cpu_baseline`, `--impl reference`) are the reference's numpy path on ALL host cores
+# (SURVEY §8d "CPU baseline plan"): torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which
+# halved the round-1 reference arm at N > 1, so the BLAS / OpenMP pools are sized here, before numpy loads.
+HOST_CORES = os.cpu_count() or 1
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str(HOST_CORES)
+
 import numpy as np  # noqa: E402
 
 N_QUBITS_1GPU = 30
@@ -158,28 +165,109 @@ def cpu_reference_sample(n_s: int, repeats: int = 1) -> Tuple[float, int, float]
     return best, ng, ng / best
 
 
+def host_memory_gib() -> float:
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available / 2**30
+    except Exception:  # pylint: disable=broad-except
+        return 0.0
+
+
+class DirectCpuSample:
+    """The reference CPU path at the FULL width of the GPU workload: a resident 2^n complex64 state (`inputs=`)
+    and, per call, `pairs` (exp1(ZZ), rx) gate pairs of the QAOA circuit applied through the oracle's `plain`
+    contractor — one numpy tensordot per gate plus the final edge reorder, exactly what
+    `Circuit(n, inputs=psi).exp1(..).rx(..).wavefunction()` costs in the reference.  No extrapolation."""
+
+    def __init__(self, n: int) -> None:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import tc_oracle
+
+        self.tc = tc_oracle
+        self.n = n
+        self.edges, self.gam, self.bet = qaoa_problem(n, 1)
+        self.zz = np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0])).astype(np.complex64)
+        self.psi = np.full(2**n, 2.0 ** (-n / 2), dtype=np.complex64)  # H^n |0..0>
+        self.k = 0
+        tc_oracle.set_contractor("plain")
+
+    def step(self, pairs: int = 1) -> Tuple[float, int]:
+        t0 = time.perf_counter()
+        c = self.tc.Circuit(self.n, inputs=self.psi)
+        for _ in range(pairs):
+            a, b = self.edges[self.k % len(self.edges)]
+            c.exp1(a, b, unitary=self.zz, theta=float(self.gam[0]))
+            c.rx(self.k % self.n, theta=float(self.bet[0]))
+            self.k += 1
+        self.psi = np.ascontiguousarray(c.wavefunction()).reshape(-1)
+        return time.perf_counter() - t0, 2 * pairs
+
+
+def cpu_baseline_record(n: int, ref_qubits: int) -> Dict[str, Any]:
+    """CPU baseline for the statevector line: the layer-1 sample at `ref_qubits` and at ref_qubits + 2 (checks the
+    2x-per-qubit law the extrapolation rests on) and, when the host has the memory, a direct sample at n."""
+    t24, ng, gps24 = cpu_reference_sample(ref_qubits)
+    t26, ng26, gps26 = cpu_reference_sample(ref_qubits + 2)
+    ratio = (t26 / ng26) / (t24 / ng)  # per-gate time ratio for +2 qubits (ideal 4.0)
+    value = gps26 / (2.0 ** (n - ref_qubits - 2))
+    sample = (f"oracle (numpy restatement of the reference CPU path, plain contractor) on the same QAOA family, "
+              f"layer 1: n={ref_qubits} {ng} gates in {t24:.1f} s, n={ref_qubits + 2} {ng26} gates in {t26:.1f} s "
+              f"(per-gate time x{ratio:.2f} for +2 qubits; ideal 4); value = the n={ref_qubits + 2} rate scaled by "
+              f"2^-({n}-{ref_qubits + 2})")  # fmt: skip
+    rec: Dict[str, Any] = {"value": value, "unit": "gates/s", "cores": HOST_CORES, "kind": "port", "sample": sample,
+                           "per_gate_time_ratio_plus2_qubits": ratio}
+    if host_memory_gib() >= 6.0 * 8 * 2**n / 2**30:
+        d = DirectCpuSample(n)
+        d.step(1)
+        sec, g = d.step(2)
+        rec["direct"] = {"value": g / sec, "unit": "gates/s", "qubits": n, "gates": g, "seconds": sec}
+        rec["value"] = g / sec
+        rec["sample"] = (f"DIRECT at n={n}: {g} gates (2 x [exp1(ZZ), rx]) on a resident 2^{n} state through the "
+                         f"oracle's plain contractor in {sec:.1f} s (tensordot per gate + final reorder); "
+                         f"cross-check: " + sample)  # fmt: skip
+    return rec
+
+
 def run_reference(args: argparse.Namespace) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_target = N_QUBITS_1GPU + max(0, int(np.log2(max(1, args.gpus))))
-    n_s = args.ref_qubits
-    cores = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_sample(n_s)
-    times = []
-    ng = 0
-    for _ in range(args.steps):
-        t, ng, _ = cpu_reference_sample(n_s)
-        times.append(t)
-    per_step = sum(times) / len(times)
-    # time per gate of the statevector path is proportional to 2^n (every gate is one pass over the state);
-    # the line is quoted in 30-qubit-equivalent gates/s like the GPU arm (identical to gates/s at N = 1)
-    gps = ng / per_step / (2.0 ** (N_QUBITS_1GPU - n_s))
-    sample = (f"oracle (numpy restatement, plain contractor) on the QAOA family at n={n_s}, layer 1 only "
-              f"({ng} gates, {per_step:.2f} s/step); gates/s scaled by 2^-({N_QUBITS_1GPU}-{n_s}) to 30-qubit-equivalent "
-              "gates/s (per-gate time is one pass over 2^n amplitudes; the CPU has one memory system however "
-              "many GPUs the other arm uses)")  # fmt: skip
+    g = max(0, int(np.log2(max(1, args.gpus))))
+    n_target = N_QUBITS_1GPU + g
+    cores = HOST_CORES
+    direct = host_memory_gib() >= 6.0 * 8 * 2**N_QUBITS_1GPU / 2**30 and not args.ref_extrapolate
+    times: List[float] = []
+    if direct:
+        # every step: 2 gates on a resident 30-qubit state (the reference's own API path, nothing extrapolated)
+        d = DirectCpuSample(N_QUBITS_1GPU)
+        for _ in range(min(args.warmup, 1)):
+            d.step(1)
+        ng = 0
+        for _ in range(args.steps):
+            t, ng = d.step(1)
+            times.append(t)
+        per_step = sum(times) / len(times)
+        gps = ng / per_step
+        measured_on = f"n={N_QUBITS_1GPU} direct: {ng} gates (exp1(ZZ) + rx) per step on a resident state"
+        sample = (f"oracle (numpy restatement, plain contractor) at the FULL width n={N_QUBITS_1GPU}: every step applies "
+                  f"{ng} gates of the QAOA circuit to a resident 2^{N_QUBITS_1GPU} complex64 state through "
+                  f"Circuit(n, inputs=psi)...wavefunction() ({per_step:.2f} s/step); at N > 1 the value stays in "
+                  "30-qubit-equivalent gates/s (the CPU has one memory system however many GPUs the other arm uses)")
+    else:
+        n_s = args.ref_qubits
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_sample(n_s)
+        ng = 0
+        for _ in range(args.steps):
+            t, ng, _ = cpu_reference_sample(n_s)
+            times.append(t)
+        per_step = sum(times) / len(times)
+        gps = ng / per_step / (2.0 ** (N_QUBITS_1GPU - n_s))
+        measured_on = f"n={n_s}, p=1 sample, extrapolated by 2^-({N_QUBITS_1GPU}-{n_s})"
+        sample = (f"oracle (numpy restatement, plain contractor) on the QAOA family at n={n_s}, layer 1 only "
+                  f"({ng} gates, {per_step:.2f} s/step); gates/s scaled by 2^-({N_QUBITS_1GPU}-{n_s}) to 30-qubit-equivalent "
+                  "gates/s (host memory too small for a direct 30-qubit sample)")  # fmt: skip
     line = {
         "impl": "reference",
         "metric": "gates/s",
@@ -194,7 +282,8 @@ def run_reference(args: argparse.Namespace) -> None:
         "vs_baseline": None,
         "dtype": "complex64",
         "data": "synthetic",
-        "config": {"workload": f"qaoa_maxcut_3regular_n{n_target}_p{P_LAYERS}", "measured_on": f"n={n_s}, p=1 sample, extrapolated"},
+        "config": {"workload": f"qaoa_maxcut_3regular_n{n_target}_p{P_LAYERS}", "measured_on": measured_on,
+                   "blas_threads": cores},
         "cpu_baseline": {"value": gps, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": gps, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -333,17 +422,7 @@ def run_b200(args: argparse.Namespace) -> None:
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_s = args.ref_qubits
-        tsec, ng, gps_s = cpu_reference_sample(n_s)
-        cpu_baseline = {
-            "value": gps_s / (2.0 ** (n - n_s)),
-            "unit": "gates/s",
-            "cores": os.cpu_count() or 1,
-            "kind": "port",
-            "sample": (f"oracle (numpy restatement of the reference CPU path, plain contractor) on the same QAOA "
-                       f"family at n={n_s}, layer 1 ({ng} gates in {tsec:.1f} s = {gps_s:.1f} gates/s), scaled by "
-                       f"2^-({n}-{n_s}) to n={n}"),  # fmt: skip
-        }
+        cpu_baseline = cpu_baseline_record(n, args.ref_qubits)
 
     if rank == 0:
         line = {
@@ -397,6 +476,20 @@ def run_b200(args: argparse.Namespace) -> None:
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if not args.no_sub_records:
+            # the rest of BASELINE.json's metric, measured in the same driver run (outside the timed region above):
+            # sliced-contraction TFLOP/s (configs[4]) and the configs[1] VQE step, each a full record of its own
+            del state
+            torch.cuda.empty_cache()
+            subs: Dict[str, Any] = {}
+            for name, fn in (("contraction", lambda: contraction_record(args, 2, 1)),
+                             ("vqe", lambda: vqe_record(args, 3, 1))):  # fmt: skip
+                try:
+                    subs[name] = fn()
+                except Exception as exc:  # pylint: disable=broad-except  (a sub-record must not lose the main line)
+                    subs[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                torch.cuda.empty_cache()
+            line["sub_records"] = subs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -491,9 +584,51 @@ def cpu_contraction_sample(tc: Any, DistributedContractor: Any, planner: Any) ->
 
 
 def run_contraction(args: argparse.Namespace) -> None:
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = contraction_record(args, args.steps, args.warmup)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def tf32_peak_tflops(dev: Any) -> float:
+    """Measured cuBLAS TF32 real GEMM rate (8192^3, best of 5): the tensor-pipe denominator of the 3xTF32 complex
+    contraction kernel is this / 3 (each complex MAC = 4 real MACs x 3 TF32 products = 24 issued flops for 8)."""
+    import torch
+
+    a = torch.randn(8192, 8192, device=dev, dtype=torch.float32)
+    b = torch.randn(8192, 8192, device=dev, dtype=torch.float32)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    best = float("inf")
+    try:
+        (a @ b)
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            (a @ b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return 2.0 * 8192.0**3 / (best * 1e-3) / 1e12
+
+
+def contraction_record(args: argparse.Namespace, steps: int, warmup: int) -> Any:
     """BASELINE.json configs[4]: one amplitude of the 7x7 depth-20 random circuit as a sliced tensor
     network.  A step contracts `--slices` slices per GPU of the full plan (the full job has
-    2^(#sliced indices) slices; TFLOP/s is a per-slice rate, so the sample is representative)."""
+    2^(#sliced indices) slices; TFLOP/s is a per-slice rate, so the sample is representative).
+    Returns the JSON record on rank 0 (None elsewhere); the process group, if any, is the caller's."""
     import pickle
 
     import torch
@@ -502,10 +637,7 @@ def run_contraction(args: argparse.Namespace) -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
     import tensorcircuit_ng_b200 as tc
     from tensorcircuit_ng_b200 import _lib, planner
@@ -562,7 +694,7 @@ def run_contraction(args: argparse.Namespace) -> None:
         torch.cuda.synchronize()
 
     with torch.no_grad():
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             step()
         barrier()
         sampler = ClockSampler(local_rank)
@@ -570,7 +702,7 @@ def run_contraction(args: argparse.Namespace) -> None:
         l0 = _lib.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             amp = step()
         e1.record(stream)
         barrier()
@@ -592,7 +724,7 @@ def run_contraction(args: argparse.Namespace) -> None:
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_s = float(t[0]), float(t[1])
-    ms_per_step = ms_total / args.steps
+    ms_per_step = ms_total / steps
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_contraction_sample(tc, DistributedContractor, planner)
@@ -600,14 +732,18 @@ def run_contraction(args: argparse.Namespace) -> None:
     gbs = bytes_slice * nsl / (ms_per_step * 1e-3) / 1e9  # per GPU
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    tf32 = tf32_peak_tflops(dev) if rank == 0 else 0.0
+    # share of the slice's complex MACs that the plan's steps hand to the tcgen05 kernel (GEMM-shaped steps)
+    gemm_flops = sum(8.0 * 2.0 ** u for a_, b_, c_, u in st["steps"] if min(a_, b_) >= 7 and u - c_ >= 3)
+    line = None
     if rank == 0:
         line = {
             "metric": "sliced-contraction TFLOP/s",
             "value": tflops,
             "unit": "TFLOP/s",
             "n_gpus": world,
-            "steps": args.steps,
-            "warmup": args.warmup,
+            "steps": steps,
+            "warmup": warmup,
             "ms_per_step": ms_per_step,
             "higher_is_better": True,
             "scaling": "weak",
@@ -641,6 +777,11 @@ def run_contraction(args: argparse.Namespace) -> None:
                 "traffic": None,
                 "alg_bytes_per_slice": bytes_slice,
                 "plan_bytes_per_slice_unfused": plan_bytes_slice,
+                "tensor": {"bound": "tensor", "achieved": tflops / world, "peak": tf32 / 3.0, "unit": "TFLOP/s",
+                           "frac": (tflops / world) / (tf32 / 3.0) if tf32 else None,
+                           "peak_source": f"cuBLAS TF32 8192^3 measured in this run ({tf32:.0f} TFLOP/s) / 3 (3xTF32 "
+                                          "complex: 24 issued flops per 8 algorithmic)",
+                           "gemm_shaped_flops_share": gemm_flops / flops_slice if flops_slice else None},
             },
             "cpu_baseline": cpu_baseline,
             "e2e": {
@@ -653,12 +794,46 @@ def run_contraction(args: argparse.Namespace) -> None:
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def run_vqe(args: argparse.Namespace) -> None:
+    print(json.dumps(vqe_record(args, args.steps, args.warmup)), flush=True)
+
+
+def cpu_vqe_sample(n_s: int, depth: int) -> Dict[str, Any]:
+    """CPU leg of the VQE workload: the oracle (numpy restatement of the reference path, plain contractor) evaluates
+    the SAME ansatz and energy for one parameter set at n_s qubits — forward value only (the reference's reverse
+    mode costs about two more sweeps per forward one, pytorch_backend.py:775-786; not restated on numpy)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tc_oracle
+
+    tc_oracle.set_contractor("plain")
+    rng = np.random.default_rng(0)
+    p = 0.1 * rng.standard_normal((depth, 2, n_s)).astype(np.float32)
+    t0 = time.perf_counter()
+    c = tc_oracle.Circuit(n_s)
+    for q in range(n_s):
+        c.h(q)
+    for l in range(depth):
+        for q in range(n_s - 1):
+            c.rzz(q, q + 1, theta=float(p[l, 0, q]))
+        for q in range(n_s):
+            c.rx(q, theta=float(p[l, 1, q]))
+    psi = np.asarray(c.wavefunction()).reshape([2] * n_s)
+    prob = np.abs(psi) ** 2
+    e = 0.0
+    for q in range(n_s - 1):
+        zq = prob.sum(axis=tuple(k for k in range(n_s) if k not in (q, q + 1)))
+        e -= float(zq[0, 0] - zq[0, 1] - zq[1, 0] + zq[1, 1])
+    for q in range(n_s):
+        e -= float(np.real(np.vdot(psi, np.flip(psi, axis=q))))
+    sec = time.perf_counter() - t0
+    ng = n_s + depth * (2 * n_s - 1)
+    return {"seconds": sec, "gates": ng, "qubits": n_s, "energy": e}
+
+
+def vqe_record(args: argparse.Namespace, steps: int, warmup: int) -> Dict[str, Any]:
     """BASELINE.json configs[1]: 24-qubit 1D TFIM hardware-efficient ansatz
     (examples/benchmark_jax_vs_torch_vqe.py:160-200: H on all, depth 6 x [rzz(i,i+1), rx(i)]), energy
     = -sum <Z_i Z_i+1> - sum <X_i> via `operator_expectation` on the `PauliStringSum2COO` Hamiltonian
@@ -707,26 +882,52 @@ def run_vqe(args: argparse.Namespace) -> None:
         vals, grads = vvag(p)
         return vals.cpu(), grads
 
-    for _ in range(min(1, args.warmup)):
+    for _ in range(max(1, min(1, warmup))):
         step()
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
     l0 = _lib.launch_count
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         vals, grads = step()
     torch.cuda.synchronize()
-    sec = (time.perf_counter() - t0) / args.steps
+    sec = (time.perf_counter() - t0) / steps
     clocks = sampler.stop()
+    launches = _lib.launch_count - l0
+    # device-resident value: the same step with the parameters already on the GPU and nothing read back
+    p_dev = params_host.to(dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        vvag(p_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    sec_res = e0.elapsed_time(e1) * 1e-3 / steps
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    # every state-sized launch of the step (fused passes, reductions over psi and lambda, the Pauli sum) reads and
+    # writes or reads twice: 16 B per amplitude of the batch — the aggregate roofline of the whole step
+    state_launches = launches / steps
+    alg_bytes = state_launches * 16.0 * batch * 2.0**n
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        n_s = min(n, 20)
+        smp = cpu_vqe_sample(n_s, depth)
+        gps = smp["gates"] / smp["seconds"] / 2.0 ** (n - n_s)
+        cpu_baseline = {"value": gps, "unit": "gates/s", "cores": HOST_CORES, "kind": "port",
+                        "sample": f"oracle forward energy of the same ansatz, one parameter set at n={n_s} "
+                                  f"({smp['gates']} gates in {smp['seconds']:.2f} s), scaled by 2^-({n}-{n_s}); forward "
+                                  "only — a value_and_grad step of the reference costs ~3x that per sample"}
     line = {
         "metric": "gates/s",
-        "value": batch * n_gates / sec,
+        "value": batch * n_gates / sec_res,
         "unit": "gates/s",
         "n_gpus": 1,
-        "steps": args.steps,
-        "warmup": min(1, args.warmup),
-        "ms_per_step": sec * 1e3,
+        "steps": steps,
+        "warmup": max(1, min(1, warmup)),
+        "ms_per_step": sec_res * 1e3,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
@@ -740,14 +941,202 @@ def run_vqe(args: argparse.Namespace) -> None:
                                        "as fused sub-circuits)",
                    "vmap_path": tc.backend.last_vmap_path,
                    "energy_mean": float(vals.mean()), "grad_norm": float(grads.norm())},
-        "roofline": None,
-        "cpu_baseline": None,
+        "roofline": {"kernel": "whole value_and_grad step (fused passes + adjoint reductions + Pauli sum)",
+                     "bound": "hbm", "achieved": alg_bytes / sec_res / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg_bytes / sec_res / 1e9 / peak, "traffic": None,
+                     "alg_bytes_per_step": alg_bytes, "state_sized_launches_per_step": state_launches},
+        "cpu_baseline": cpu_baseline,
         "e2e": {"value": batch * n_gates / sec, "unit": "gates/s", "h2d_bytes_per_step": int(params_host.numel() * 4),
                 "d2h_bytes_per_step": int(batch * 4), "ms_per_step": sec * 1e3},
-        "gpu_launches": _lib.launch_count - l0,
+        "gpu_launches": launches,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    return line
+
+
+def parity_ops(n: int, depth: int, seed: int) -> List[Tuple[str, List[int], Dict[str, float]]]:
+    """A small random circuit over the gate kinds the sharded engine treats differently (dense / diagonal /
+    controlled, 1 and 2 qubits, on a per-layer random pairing so that global qubits are hit)."""
+    rng = np.random.default_rng(seed)
+    ops: List[Tuple[str, List[int], Dict[str, float]]] = []
+    for _ in range(depth):
+        for q in range(n):
+            th = float(rng.uniform(0, 2 * np.pi))
+            ops.append((("rx", "ry", "rz", "h", "t")[int(rng.integers(0, 5))], [q], {"theta": th}))
+        perm = rng.permutation(n)
+        for i in range(0, n - 1, 2):
+            a, b = int(perm[i]), int(perm[i + 1])
+            th = float(rng.uniform(0, 2 * np.pi))
+            ops.append((("cz", "cnot", "rzz", "crx", "rxx", "swap")[int(rng.integers(0, 6))], [a, b], {"theta": th}))
+    return ops
+
+
+def build_ops(mod: Any, n: int, ops: Any) -> Any:
+    c = mod.Circuit(n)
+    for name, qs, kw in ops:
+        if name in ("h", "t", "cz", "cnot", "swap"):
+            getattr(c, name)(*qs)
+        else:
+            getattr(c, name)(*qs, **kw)
+    return c
+
+
+def multi_gpu_parity(tc: Any, sharded: Any, comm: Any, ex: Any, world: int, rank: int, dev: Any) -> Dict[str, Any]:
+    """Driver-visible multi-GPU parity (run before the timed region, every rank takes part):
+    (1) a 20-qubit random circuit evolved SHARDED over the N ranks vs the numpy oracle on rank 0 — amplitudes,
+        three <Z..> strings, the norm;
+    (2) `DistributedContractor.value` (slices scattered over the ranks + one all-reduce) on a 4x4 depth-8 RCS
+        amplitude vs the oracle's statevector amplitude."""
+    import torch
+    import torch.distributed as dist
+
+    n, depth, seed = 20, 3, 5
+    g = world.bit_length() - 1
+    ops = parity_ops(n, depth, seed)
+    sv = sharded.evolve(build_ops(tc, n, ops), comm, ex, chunk_elems=1 << 14)
+    terms = [[0, n - 1], [2], [1, 3, 4]]
+    zz = sv.z_expectations(terms).cpu().numpy()
+    norm = float(sv.norm2()[0])
+    shard = sv.state.detach().reshape(-1)
+    parts = [torch.empty_like(shard) for _ in range(world)] if rank == 0 else None
+    dist.gather(shard, parts, dst=0)
+    from tensorcircuit_ng_b200.experimental import DistributedContractor
+
+    rows = cols = 4
+    bits = "01" * (rows * cols // 2)
+
+    def nodes_fn(_: Any) -> Any:
+        return build_rcs(tc, rows, cols, 8).amplitude_before(bits)
+
+    dc = DistributedContractor(nodes_fn, torch.zeros(1, device=dev), cotengra_options={"slicing_reconf_opts": {"target_size": 2**8}})
+    amp = complex(dc.value(torch.zeros(1, device=dev)).reshape(()).cpu())
+    res: Dict[str, Any] = {"ok": True}
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import tc_oracle
+
+        tc_oracle.set_contractor("plain")
+        ref = np.asarray(build_ops(tc_oracle, n, ops).wavefunction()).reshape(-1)
+        full = np.concatenate([p_.cpu().numpy() for p_ in parts])  # physical index = rank << nl | local
+        x = np.arange(1 << n, dtype=np.int64)
+        phys = np.zeros(1 << n, dtype=np.int64)
+        for q in range(n):
+            phys |= ((x >> (n - 1 - q)) & 1) << sv.pos_of[q]
+        dpsi = float(np.abs(full[phys] - ref).max())
+        prob = np.abs(ref.astype(np.complex128)) ** 2
+        want = []
+        for t in terms:
+            sgn = np.ones(1 << n)
+            for q in t:
+                sgn *= 1 - 2 * ((x >> (n - 1 - q)) & 1)
+            want.append(float(np.sum(prob * sgn)))
+        dz = float(np.abs(zz - np.asarray(want)).max())
+        ref_amp = complex(np.asarray(build_rcs(tc_oracle, rows, cols, 8).wavefunction()).reshape(-1)[int(bits, 2)])
+        damp = abs(amp - ref_amp)
+        res = {
+            "sharded_statevector": {"qubits": n, "gates": len(ops), "ranks": world, "global_qubits": g,
+                                    "swaps": int(sv.swaps_done), "max_abs_dpsi": dpsi, "max_abs_dz": dz,
+                                    "norm": norm, "tolerance": 1e-5},
+            "distributed_contractor": {"network": f"rcs_{rows}x{cols}_depth8 amplitude", "nslices": int(dc.nslices),
+                                       "ranks": world, "abs_damp": damp, "abs_amp": abs(ref_amp), "tolerance": 1e-5},
+        }
+        res["ok"] = bool(dpsi <= 1e-5 and dz <= 1e-5 and abs(norm - 1.0) <= 1e-5 and damp <= 1e-5)
+    flag = torch.tensor([1 if res["ok"] else 0], device=dev)
+    dist.broadcast(flag, src=0)
+    res["ok"] = bool(int(flag[0]))
+    return res
+
+
+def random_record(args: argparse.Namespace, tc: Any, sharded: Any, comm: Any, ex: Any, world: int, rank: int,
+                  dev: Any) -> Any:  # fmt: skip
+    """BASELINE.json configs[3] at its stated size: random circuit on n = 33 + log2 N qubits,
+    64 GiB of state per GPU, global<->local qubit swaps over NVLink.  One warm-up step (plans + programs), then
+    `--random-steps` timed steps; every number is the max over the ranks."""
+    import torch
+    import torch.distributed as dist
+
+    g = world.bit_length() - 1
+    n = 33 + g
+    depth = args.depth
+    rng = np.random.default_rng(0)
+    kinds = rng.integers(0, 3, size=(depth, n))
+    thetas = rng.uniform(0, 2 * np.pi, size=(depth, n)).astype(np.float32)
+    n_gates = sum(n + len(range(l % 2, n - 1, 2)) for l in range(depth))
+    c = build_random_circuit(tc, n, depth, thetas.tolist(), kinds)
+    sv = sharded.evolve(c, comm, ex)  # warm-up step: plans compiled, programs uploaded, one full evolution
+    plan, ops, gatebuf = sv.plan, sv.ops, sv.gatebuf
+    vecs = sharded.product_vectors(sv.prefix, gatebuf, n) if any(sv.prefix) else None
+    terms = [[0, n - 1]]
+    stream = torch.cuda.current_stream()
+    steps = max(1, args.random_steps)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    sent0 = sv.bytes_sent
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        sv.reset(vecs)
+        sv.run(plan, ops, gatebuf)
+        zz = sv.z_expectations(terms)
+    e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    sent = (sv.bytes_sent - sent0) / steps
+    norm = float(sv.norm2()[0])
+    # one instrumented step: time inside fused passes vs inside swaps
+    sv.reset(vecs)
+    evs = []
+    for si, seg in enumerate(plan.segments):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        if isinstance(seg, sharded.RunSegment):
+            cc = plan.cache[(rank, si)]
+            cc.run(sv.state, gatebuf, index_base=sv.index_base)
+            kind, cnt = "run", cc.plan.n_launches
+        else:
+            sv.swap(seg.pairs)
+            kind, cnt = "swap", len(seg.pairs)
+        b.record(stream)
+        evs.append((kind, a, b, cnt))
+    torch.cuda.synchronize()
+    run_ms = sum(a.elapsed_time(b) for k, a, b, _ in evs if k == "run")
+    swap_ms = sum(a.elapsed_time(b) for k, a, b, _ in evs if k == "swap")
+    n_launch = sum(x for k, _, _, x in evs if k == "run")
+    t = torch.tensor([ms_total, swap_ms, run_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, swap_ms, run_ms = (float(x) for x in t)
+    ms_per_step = ms_total / steps
+    nl = n - g
+    alg_bytes = 16.0 * 2.0**nl
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    achieved = alg_bytes / (run_ms / max(1, n_launch) * 1e-3) / 1e9
+    del sv
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {
+        "metric": "gates/s", "value": n_gates / (ms_per_step * 1e-3), "unit": "gates/s", "n_gpus": world,
+        "steps": steps, "warmup": 1, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "dtype": "complex64", "data": "synthetic",
+        "config": {"workload": f"random_circuit_sharded_n{n}_depth{depth}", "gates": n_gates, "qubits": n,
+                   "global_qubits": g, "state_bytes_per_gpu": 8 * 2**nl, "hbm_passes": n_launch,
+                   "swaps": plan.n_swaps, "swapped_qubits": plan.swapped_qubits,
+                   "amplitude_updates_per_s": n_gates * 2.0**n / (ms_per_step * 1e-3),
+                   "nvlink_bytes_sent_per_gpu_per_step": sent,
+                   "nvlink_gbs_per_gpu": sent / (swap_ms * 1e-3) / 1e9 if swap_ms > 0 else None,
+                   "nvlink_peak_gbs": 900.0, "swap_ms_per_step": swap_ms, "local_ms_per_step": run_ms,
+                   "norm": norm, "z0_zlast": float(zz[0])},
+        "roofline": {"kernel": "tcb::pass_kernel (fused tile pass), per GPU", "bound": "hbm", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "alg_bytes_per_launch": alg_bytes, "launches_per_step": n_launch},
+        "cpu_baseline": None,
+        "clocks": clocks,
+    }
 
 
 def run_sharded(args: argparse.Namespace) -> None:
@@ -771,6 +1160,14 @@ def run_sharded(args: argparse.Namespace) -> None:
     rng = np.random.default_rng(0)
     comm = sharded.TorchDistComm()
     ex = sharded.CudaExecutor(dev)
+    parity = None
+    if not args.no_sub_records:
+        parity = multi_gpu_parity(tc, sharded, comm, ex, world, rank, dev)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"parity": parity, "error": "multi-GPU parity failed; nothing was timed"}), flush=True)
+            dist.destroy_process_group()
+            raise SystemExit(3)
     if args.workload == "random":
         kinds = rng.integers(0, 3, size=(depth, n))
         thetas = rng.uniform(0, 2 * np.pi, size=(depth, n)).astype(np.float32)
@@ -948,7 +1345,35 @@ def run_sharded(args: argparse.Namespace) -> None:
             },
             "gpu_launches": launches,
             "clocks": clocks,
+            "parity": parity,
         }
+    subs: Dict[str, Any] = {}
+    if not args.no_sub_records and args.workload == "qaoa":
+        # the rest of BASELINE.json's metric in the same driver run: sliced contraction on the N ranks (configs[4])
+        # and configs[3] itself (random circuit, n = 33 + log2 N, 64 GiB of state per GPU)
+        del sv, plan, gatebuf
+        torch.cuda.empty_cache()
+        try:
+            rec = contraction_record(args, 2, 1)
+        except Exception as exc:  # pylint: disable=broad-except
+            rec = {"error": f"{type(exc).__name__}: {exc}"}
+        subs["contraction"] = rec
+        torch.cuda.empty_cache()
+        free = torch.cuda.mem_get_info(dev)[0]
+        ok = torch.tensor([1 if free >= 150 * 2**30 else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]) and not args.no_random:
+            try:
+                rec = random_record(args, tc, sharded, comm, ex, world, rank, dev)
+            except Exception as exc:  # pylint: disable=broad-except
+                rec = {"error": f"{type(exc).__name__}: {exc}"}
+        else:
+            rec = {"skipped": f"needs >= 150 GiB free per GPU (rank {rank}: {free >> 30} GiB)" if not args.no_random
+                   else "--no-random"}
+        subs["random_circuit"] = rec
+    if rank == 0:
+        if subs:
+            line["sub_records"] = subs
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
 
@@ -972,6 +1397,11 @@ def main() -> None:
     ap.add_argument("--ref-qubits", type=int, default=24, help="size of the bounded CPU sample (even: 3-regular graph)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--random-steps", type=int, default=1, help="timed steps of the configs[3] sub-record")
+    ap.add_argument("--no-random", action="store_true", help="N > 1: skip the configs[3] sub-record (64 GiB shards)")
+    ap.add_argument("--ref-extrapolate", action="store_true", help="reference arm: n = --ref-qubits sample, scaled")
+    ap.add_argument("--no-sub-records", action="store_true",
+                    help="default run: skip the contraction / vqe / configs[3] sub-records and the N > 1 parity block")
     args = ap.parse_args()
     args.qubits_set = args.qubits is not None
     if args.qubits is None:

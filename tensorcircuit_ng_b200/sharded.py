@@ -415,7 +415,7 @@ def evolve(circuit: Any, comm: Any = None, executor: Any = None, chunk_elems: in
     if executor is None:
         dev = svengine.pick_device([g[0].tensor for g in gates])
         executor = CudaExecutor(dev)
-    structure = tuple((g[1], svengine.gate_kind(g[0], g[2]), int(g[0].tensor.numel())) for g in gates)
+    structure = tuple((g[1], k, int(g[0].tensor.numel())) for g, k in zip(gates, svengine.gate_kinds(gates)))
     key = (n, comm.world, structure)
     hit = _plan_cache.get(key)
     if hit is None:

@@ -182,8 +182,19 @@ def extract_gate_stream(nodes: Sequence[Any], output_edge_order: Sequence[Any],
     return n, init_node, gates
 
 
-# names whose matrices are structurally diagonal / controlled in the reference's gates.py; used
-# only for nodes that do not carry our own `_b200_kind` hint (a real TensorCircuit-NG install).
+# ---- gate classification at a nodes-only boundary (SURVEY §7 "Diagonal / controlled detection") ---------
+# Nodes built by this package's gates.py carry `_b200_kind`.  Nodes coming from a real TensorCircuit-NG install
+# carry only `name` (overwritten with the method name, tensorcircuit/basecircuit.py:278 — user-overridable) and
+# their tensor.  For those:
+#   * a name of a gate family that is dense for generic parameters (rx, ry, h, u, r, swap ...) gives "dense"
+#     without looking at values — the safe direction, a dense treatment is correct for any matrix;
+#   * everything else (rz / cz / cnot / exp1 / any / unknown names ...) is classified by a STRUCTURAL probe of the
+#     tensor's exact-zero pattern: diagonal, or a 2x2 block controlled by the first k-1 qubits, else dense.  The
+#     probe reads the foreign tensors back ONCE per network topology (one batched device->host copy) and its result
+#     is cached with that topology, so a training loop pays no synchronisation after its first step.  Zero patterns
+#     are parameter independent except on measure-zero parameter values; an exactly-identity matrix is treated as
+#     dense, so a parametrised gate that happens to start at theta = 0 is not mistaken for a diagonal one.
+#   * `trust_gate_names = True` skips the probe for the reference's own names below.
 _NAME_KINDS: Dict[str, Tuple[Any, ...]] = {
     "z": ("diag",), "s": ("diag",), "t": ("diag",), "sd": ("diag",), "td": ("diag",), "i": ("diag",),
     "rz": ("diag",), "phase": ("diag",), "cz": ("diag",), "rzz": ("diag",), "cphase": ("diag",),
@@ -192,19 +203,86 @@ _NAME_KINDS: Dict[str, Tuple[Any, ...]] = {
     "cry": ("ctrl", 1, 1), "cu": ("ctrl", 1, 1), "cr": ("ctrl", 1, 1), "toffoli": ("ctrl", 2, 3),
     "ox": ("ctrl", 1, 0), "oy": ("ctrl", 1, 0), "orx": ("ctrl", 1, 0), "ory": ("ctrl", 1, 0),
 }  # fmt: skip
+_DENSE_NAMES = frozenset(["x", "y", "h", "rx", "ry", "r", "u", "wroot", "swap", "iswap", "rxx", "ryy", "fredkin"])
 
 trust_gate_names = False  # opt-in: node names are user-overridable in the reference
+_probe_cache: Dict[Any, Dict[int, Tuple[Any, ...]]] = {}
+probe_readbacks = 0  # device->host probe copies issued so far (tests pin "once per topology")
+
+
+def classify_matrix(m: np.ndarray) -> Tuple[Any, ...]:
+    """Structural kind of a 2^k x 2^k matrix from its exact-zero pattern."""
+    d = m.shape[0]
+    k = int(round(math.log2(d)))
+    off = m - np.diag(np.diagonal(m))
+    if not off.any():
+        return ("dense",) if np.all(np.diagonal(m) == 1) else ("diag",)
+    if 2 <= k <= 3:
+        nb = d // 2
+        blocks = [m[2 * b : 2 * b + 2, 2 * b : 2 * b + 2] for b in range(nb)]
+        rest = m.copy()
+        for b in range(nb):
+            rest[2 * b : 2 * b + 2, 2 * b : 2 * b + 2] = 0
+        if not rest.any():
+            eye = np.eye(2, dtype=m.dtype)
+            active = [b for b in range(nb) if not np.array_equal(blocks[b], eye)]
+            if len(active) == 1:
+                nctrl, b = k - 1, active[0]
+                pol = 0
+                for ci in range(nctrl):  # bit ci of pol = required value of control ci (control 0 = block-index MSB)
+                    pol |= ((b >> (nctrl - 1 - ci)) & 1) << ci
+                return ("ctrl", nctrl, pol)
+    return ("dense",)
 
 
 def gate_kind(node: Any, packed_diag: bool) -> Tuple[Any, ...]:
+    """Kind of one node WITHOUT looking at values (None: needs the structural probe)."""
     if packed_diag:
         return ("diagvec",)
     kind = getattr(node, "_b200_kind", None)
     if kind is not None:
         return tuple(kind) if kind[0] != "diagvec" else ("dense",)
-    if trust_gate_names:
-        return _NAME_KINDS.get(str(getattr(node, "name", "")), ("dense",))
-    return ("dense",)
+    name = str(getattr(node, "name", ""))
+    if name in _DENSE_NAMES:
+        return ("dense",)
+    if trust_gate_names and name in _NAME_KINDS:
+        return _NAME_KINDS[name]
+    return None  # type: ignore[return-value]
+
+
+def gate_kinds(gates: Sequence[Tuple[Any, Tuple[int, ...], bool]]) -> List[Tuple[Any, ...]]:
+    """Kinds of a whole gate stream; foreign nodes are probed once per topology (see above)."""
+    global probe_readbacks
+    kinds: List[Any] = [gate_kind(g[0], g[2]) for g in gates]
+    todo = [i for i, k in enumerate(kinds) if k is None]
+    if not todo:
+        return kinds
+    key = tuple((g[1], str(getattr(g[0], "name", "")), tuple(g[0].shape), g[2]) for g in gates)
+    hit = _probe_cache.get(key)
+    if hit is None:
+        from . import autograd
+
+        flat = []
+        for i in todo:
+            t = gates[i][0].tensor
+            while autograd.is_batched(t):  # under vmap: the structure of the first sample stands for the batch
+                t = torch._C._functorch.get_unwrapped(t)
+            t = t.detach()
+            d = 1 << len(gates[i][1])
+            flat.append(t.reshape(-1, d * d)[0].to(torch.complex64))
+        host = torch.cat(flat).cpu().numpy()  # ONE device->host copy for all foreign gates
+        probe_readbacks += 1
+        hit, off = {}, 0
+        for i in todo:
+            d = 1 << len(gates[i][1])
+            hit[i] = classify_matrix(host[off : off + d * d].reshape(d, d))
+            off += d * d
+        if len(_probe_cache) > 256:
+            _probe_cache.clear()
+        _probe_cache[key] = hit
+    for i in todo:
+        kinds[i] = hit[i]
+    return kinds
 
 
 # ---------------------------------------------------------------------------------------
@@ -516,7 +594,7 @@ def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) 
     n, init_node, gates = extract_gate_stream(nodes, output_edge_order)
     probe = [g[0]._lazy.theta if hasattr(g[0], "pending") and g[0].pending() else g[0].tensor for g in gates]
     device = pick_device(probe + ([init_node.tensor] if init_node is not None else []))
-    structure = [(g[1], gate_kind(g[0], g[2]), int(math.prod(g[0].shape))) for g in gates]
+    structure = [(g[1], k, int(math.prod(g[0].shape))) for g, k in zip(gates, gate_kinds(gates))]
     batched = any(autograd.is_batched(t) for t in probe)
     cc = compile_circuit(n, structure, device, absorb_prefix=init_node is None and not batched)
     if torch.is_grad_enabled():

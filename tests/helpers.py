@@ -109,3 +109,16 @@ def qaoa(n, p, seed=0):
         for q in g.nodes:
             ops.append(("rx", [int(q)], {"theta": float(betas[l])}))
     return ops, [(int(a), int(b)) for a, b in g.edges]
+
+
+def param_shift(f, params, idx, kind="half"):
+    """Exact derivative of an expectation value with respect to ONE gate parameter by the parameter-shift rule,
+    evaluated on the oracle: gates exp(-i theta/2 P) (rx, ry, rz, rzz, rxx, ryy; `kind="half"`) shift by pi/2 and
+    halve, gates exp(-i theta P) (exp1 with P^2 = 1; `kind="full"`) shift by pi/4.  The parameter must feed exactly
+    one gate.  No step-size error: the oracle's complex64 rounding (~1e-6) is all that is left."""
+    s = np.pi / 2 if kind == "half" else np.pi / 4
+    pp, pm = np.array(params, dtype=np.float64), np.array(params, dtype=np.float64)
+    pp[idx] += s
+    pm[idx] -= s
+    d = f(pp) - f(pm)
+    return d / 2 if kind == "half" else d

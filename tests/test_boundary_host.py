@@ -192,3 +192,85 @@ def test_untrusted_gates_are_flagged_for_the_adjoint_check():
     assert not gates.diagonal_gate(np.ones(2))._b200_unitary
     assert not gates.exp_gate(gates._x_matrix, -0.3j)._b200_unitary
     assert not gates.exp1_gate(np.array([[1.0, 0.0], [0.0, 2.0]]), torch.tensor(0.2))._b200_unitary
+
+
+# ---- foreign nodes: structural classification ----------------------------------------------------
+def test_classify_matrix_zero_patterns():
+    from tensorcircuit_ng_b200 import gates as G, svengine
+
+    def mat(g):
+        t = g.tensor
+        d = int(round(np.sqrt(t.numel())))
+        return t.reshape(d, d).numpy()
+
+    assert svengine.classify_matrix(mat(G.rz_gate(theta=0.3))) == ("diag",)
+    assert svengine.classify_matrix(mat(G.cz())) == ("diag",)
+    assert svengine.classify_matrix(mat(G.exp1_gate(G._zz_matrix, torch.tensor(0.4)))) == ("diag",)
+    assert svengine.classify_matrix(mat(G.cnot())) == ("ctrl", 1, 1)
+    assert svengine.classify_matrix(mat(G.ox())) == ("ctrl", 1, 0)
+    assert svengine.classify_matrix(mat(G.crx_gate(theta=0.7))) == ("ctrl", 1, 1)
+    assert svengine.classify_matrix(mat(G.toffoli())) == ("ctrl", 2, 3)
+    assert svengine.classify_matrix(mat(G.rx_gate(theta=0.3))) == ("dense",)
+    assert svengine.classify_matrix(mat(G.swap())) == ("dense",)
+    assert svengine.classify_matrix(mat(G.fredkin())) == ("dense",)
+    assert svengine.classify_matrix(np.eye(4, dtype=np.complex64)) == ("dense",)  # identity: never "diagonal"
+    # kinds found by the probe equal the factory hints for every gate the helpers use
+    for name, qs, kw in random_layers(5, 3, 1):
+        g = getattr(G, name if name in ("toffoli", "fredkin", "cnot", "cz", "swap", "h", "t", "ox") else name + "_gate"
+                    if hasattr(G, name + "_gate") else name)
+        node = g(**kw) if kw else g()
+        want = tuple(node._b200_kind)
+        got = svengine.classify_matrix(mat(node))
+        assert got == want or want == ("dense",) or got == ("dense",), (name, want, got)
+
+
+def _foreignize(nodes):
+    """Strip this package's structural hints: what a node list from a real TensorCircuit-NG install looks like."""
+    from tensorcircuit_ng_b200 import gates as G
+
+    for nd in nodes:
+        if hasattr(nd, "_b200_kind"):
+            t = nd.tensor
+            if isinstance(nd, G.LazyGate):
+                nd.__class__ = G.Gate
+                nd.__dict__.pop("_lazy", None)
+                nd.__dict__.pop("_own", None)
+                nd.tensor = t
+            del nd._b200_kind
+            nd.__dict__.pop("_b200_unitary", None)
+    return nodes
+
+
+def test_foreign_nodes_are_probed_once_per_topology():
+    import tensorcircuit_ng_b200 as tc
+    from tensorcircuit_ng_b200 import svengine
+
+    ops = [("h", [0], {}), ("rz", [1], {"theta": 0.3}), ("exp1", [0, 1], {"unitary": tc.gates._zz_matrix, "theta": 0.2}),
+           ("cnot", [1, 2], {}), ("crx", [2, 0], {"theta": 0.9}), ("any", [1], {"unitary": np.diag([1.0, 1j])}),
+           ("rx", [2], {"theta": 0.4})]  # fmt: skip
+
+    def stream(scale):
+        c = tc.Circuit(3)
+        for name, qs, kw in ops:
+            kw = {k: (v * scale if k == "theta" else v) for k, v in kw.items()}
+            getattr(c, name)(*qs, **kw)
+        nodes, edges = c._copy()
+        native = [tuple(k) for k in svengine.gate_kinds(svengine.extract_gate_stream(nodes, edges)[2])]
+        _foreignize(nodes)
+        return native, svengine.extract_gate_stream(nodes, edges)[2]
+
+    svengine._probe_cache.clear()
+    before = svengine.probe_readbacks
+    native, gates = stream(1.0)
+    assert svengine.gate_kinds(gates) == native
+    assert svengine.probe_readbacks == before + 1
+    _, gates2 = stream(1.7)  # same topology, other parameters: cached
+    assert svengine.gate_kinds(gates2) == native
+    assert svengine.probe_readbacks == before + 1
+    old = svengine.trust_gate_names
+    try:
+        svengine.trust_gate_names = True  # names decide for the reference's own gates; `exp1` / `any` still probed
+        svengine._probe_cache.clear()
+        assert svengine.gate_kinds(gates2) == native
+    finally:
+        svengine.trust_gate_names = old

@@ -338,7 +338,9 @@ def test_gradient_kat(cuda):
 
 
 @pytest.mark.parametrize("n", [4, 11])
-def test_gradients_match_finite_differences_of_oracle(cuda, n):
+def test_gradients_match_parameter_shift_of_oracle(cuda, n):
+    """north-star: gradients within 1e-4 relative.  The reference value of every derivative is the exact
+    parameter-shift rule evaluated on the oracle (no finite-difference step error)."""
     tc = _tc()
     rng = np.random.default_rng(n)
     p0 = rng.uniform(0, 1, size=(4, n))
@@ -356,13 +358,13 @@ def test_gradients_match_finite_differences_of_oracle(cuda, n):
     val.backward()
     g = param.grad.cpu().numpy()
     assert abs(float(val) - f_oracle(p0)) <= 1e-5
-    eps = 1e-3
-    for idx in [(0, 0), (1, n - 1), (2, 1), (3, 0)]:
-        pp, pm = p0.copy(), p0.copy()
-        pp[idx] += eps
-        pm[idx] -= eps
-        fd = (f_oracle(pp) - f_oracle(pm)) / (2 * eps)
-        assert abs(g[idx] - fd) <= 1e-4 * max(1.0, abs(fd)) + 2e-4, (idx, g[idx], fd)
+    from helpers import param_shift
+
+    checks = [(0, 0), (1, n - 1), (2, 1), (3, 0), (0, n - 2), (1, 0), (2, 0), (3, n - 1)]
+    ps = {idx: param_shift(f_oracle, p0, idx, "full" if idx[0] % 2 == 0 else "half") for idx in checks}
+    scale = max(abs(v) for v in ps.values())
+    for idx in checks:  # rows 0, 2: exp1(ZZ, theta) = exp(-i theta ZZ); rows 1, 3: rx(theta)
+        assert abs(g[idx] - ps[idx]) <= 1e-4 * max(abs(ps[idx]), scale), (idx, g[idx], ps[idx])
 
 
 def test_tn_route_gradient(cuda):
@@ -408,13 +410,13 @@ def test_vvag_tfim_vqe_batch(cuda):
     ref = lambda p: float(energy(tc_oracle, p, lambda v: np.real(v)))  # noqa: E731
     for b in range(batch):
         assert abs(float(vals[b]) - ref(params[b])) <= 1e-4
-    eps = 2e-2
-    for b, l, k, q in [(0, 0, 0, 0), (1, 1, 1, 3), (2, 0, 1, 7), (2, 1, 0, 5)]:
-        pp, pm = params[b].copy(), params[b].copy()
-        pp[l, k, q] += eps
-        pm[l, k, q] -= eps
-        fd = (ref(pp) - ref(pm)) / (2 * eps)
-        assert abs(float(grads[b, l, k, q]) - fd) <= 3e-3, (b, l, k, q, float(grads[b, l, k, q]), fd)
+    from helpers import param_shift
+
+    checks = [(0, 0, 0, 0), (1, 1, 1, 3), (2, 0, 1, 7), (2, 1, 0, 5), (0, 1, 0, 6), (1, 0, 1, 0)]
+    ps = {c: param_shift(ref, params[c[0]], c[1:], "half") for c in checks}  # rzz(theta), rx(theta): exp(-i theta/2 P)
+    scale = max(abs(v) for v in ps.values())
+    for c in checks:
+        assert abs(float(grads[c]) - ps[c]) <= 1e-4 * max(abs(ps[c]), scale), (c, float(grads[c]), ps[c])
 
 
 def test_vvag_batched_path_equals_loop(cuda):

@@ -38,18 +38,20 @@ def test_quantumnet_values_and_training_gradients(cuda):
     oracle = _qpred(otc, n, nlayers, np.stack, np.real)
     want = oracle(np.ones(n), w)
     assert np.abs(yp.detach().cpu().numpy() - want[None, :]).max() < 2e-5
-    # one optimiser step through the engine's vjps; gradient against central differences of the oracle
+    # one optimiser step through the engine's vjps; gradient against the exact parameter-shift rule on the oracle
     x = torch.linspace(0.1, 0.9, n)
     loss = ql(x[None, :])[0].sum()
     loss.backward()
     g = ql.q_weights[0].grad.cpu().numpy()
     xh = x.cpu().numpy().astype(np.float64)
     f0 = lambda ww: float(np.sum(oracle(xh, ww)))
-    for (a, b) in [(0, 0), (1, 3), (3, 5), (2, 2)]:
-        wp, wm = w.copy(), w.copy()
-        wp[a, b] += 1e-2  # (the oracle computes in complex64: a smaller step drowns in rounding)
-        wm[a, b] -= 1e-2
-        assert abs(g[a, b] - (f0(wp) - f0(wm)) / 2e-2) < 5e-3
+    from helpers import param_shift
+
+    checks = [(0, 0), (1, 3), (3, 5), (2, 2), (0, 4), (3, 0)]
+    ps = {c: param_shift(f0, w, c, "half") for c in checks}  # every weight feeds one rx / ry gate
+    scale = max(abs(v) for v in ps.values())
+    for c in checks:
+        assert abs(g[c] - ps[c]) <= 1e-4 * max(abs(ps[c]), scale), (c, g[c], ps[c])
     torch.optim.SGD(ql.parameters(), lr=0.1).step()
 
 
