@@ -29,6 +29,7 @@ workload family, bounded sample per step.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import math
 import os
@@ -485,7 +486,8 @@ def run_b200(args: argparse.Namespace) -> None:
             for name, fn in (("contraction", lambda: contraction_record(args, 2, 1)),
                              ("vqe", lambda: vqe_record(args, 3, 1))):  # fmt: skip
                 try:
-                    subs[name] = fn()
+                    with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly ONE JSON line
+                        subs[name] = fn()
                 except Exception as exc:  # pylint: disable=broad-except  (a sub-record must not lose the main line)
                     subs[name] = {"error": f"{type(exc).__name__}: {exc}"}
                 torch.cuda.empty_cache()
@@ -593,7 +595,8 @@ def run_contraction(args: argparse.Namespace) -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    line = contraction_record(args, args.steps, args.warmup)
+    with contextlib.redirect_stdout(sys.stderr):
+        line = contraction_record(args, args.steps, args.warmup)
     if line is not None:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -1162,7 +1165,8 @@ def run_sharded(args: argparse.Namespace) -> None:
     ex = sharded.CudaExecutor(dev)
     parity = None
     if not args.no_sub_records:
-        parity = multi_gpu_parity(tc, sharded, comm, ex, world, rank, dev)
+        with contextlib.redirect_stdout(sys.stderr):
+            parity = multi_gpu_parity(tc, sharded, comm, ex, world, rank, dev)
         if not parity["ok"]:
             if rank == 0:
                 print(json.dumps({"parity": parity, "error": "multi-GPU parity failed; nothing was timed"}), flush=True)
@@ -1354,7 +1358,8 @@ def run_sharded(args: argparse.Namespace) -> None:
         del sv, plan, gatebuf
         torch.cuda.empty_cache()
         try:
-            rec = contraction_record(args, 2, 1)
+            with contextlib.redirect_stdout(sys.stderr):
+                rec = contraction_record(args, 2, 1)
         except Exception as exc:  # pylint: disable=broad-except
             rec = {"error": f"{type(exc).__name__}: {exc}"}
         subs["contraction"] = rec

@@ -17,7 +17,7 @@ def _tc():
 
 
 # ---- set_contractor options through the tensor-network engine ------------------------------------
-@pytest.mark.parametrize("method,kw", [("greedy", {"preprocessing": True}), ("greedy", {}), ("optimal", {}),
+@pytest.mark.parametrize("method,kw", [("greedy", {"preprocessing": True}), ("greedy", {}), ("eager", {}),
                                         ("auto", {"preprocessing": True}), ("tn", {})])
 def test_named_contractors_match_oracle(cuda, method, kw):
     tc = _tc()
@@ -180,8 +180,8 @@ def test_gradient_through_non_unitary_gate_matches_dense_reference(cuda):
     ref = f_dense(th_r, m_r)
     ref.backward()
     assert abs(float(val) - float(ref)) <= 1e-5
-    assert np.abs(th.grad.cpu().numpy() - th_r.grad.numpy()).max() <= 1e-4 * max(1.0, float(th_r.grad.abs().max()))
-    assert np.abs(m.grad.cpu().numpy() - m_r.grad.numpy()).max() <= 1e-4 * max(1.0, float(m_r.grad.abs().max()))
+    assert np.abs(th.grad.cpu().numpy() - th_r.grad.cpu().numpy()).max() <= 1e-4 * max(1.0, float(th_r.grad.abs().max()))
+    assert np.abs(m.grad.cpu().numpy() - m_r.grad.cpu().numpy()).max() <= 1e-4 * max(1.0, float(m_r.grad.abs().max()))
 
 
 def test_gradient_with_respect_to_operator_and_pauli_weights(cuda):
