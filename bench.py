@@ -1000,7 +1000,7 @@ def multi_gpu_parity(tc: Any, sharded: Any, comm: Any, ex: Any, world: int, rank
     terms = [[0, n - 1], [2], [1, 3, 4]]
     zz = sv.z_expectations(terms).cpu().numpy()
     norm = float(sv.norm2()[0])
-    shard = sv.state.detach().reshape(-1)
+    shard = torch.view_as_real(sv.state.detach().reshape(-1)).contiguous()  # (NCCL has no complex types)
     parts = [torch.empty_like(shard) for _ in range(world)] if rank == 0 else None
     dist.gather(shard, parts, dst=0)
     from tensorcircuit_ng_b200.experimental import DistributedContractor
@@ -1020,7 +1020,7 @@ def multi_gpu_parity(tc: Any, sharded: Any, comm: Any, ex: Any, world: int, rank
 
         tc_oracle.set_contractor("plain")
         ref = np.asarray(build_ops(tc_oracle, n, ops).wavefunction()).reshape(-1)
-        full = np.concatenate([p_.cpu().numpy() for p_ in parts])  # physical index = rank << nl | local
+        full = np.concatenate([torch.view_as_complex(p_).cpu().numpy() for p_ in parts])  # physical index = rank << nl | local
         x = np.arange(1 << n, dtype=np.int64)
         phys = np.zeros(1 << n, dtype=np.int64)
         for q in range(n):
