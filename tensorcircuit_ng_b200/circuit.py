@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
+import math
+
 import numpy as np
 import torch
 
@@ -345,7 +347,61 @@ class Circuit:
         return (s.abs() ** 2).real
 
     def to_qir(self) -> List[Dict[str, Any]]:
-        return self._qir
+        """abstractcircuit.py:375-414: a shallow copy of the instruction list."""
+        return list(self._qir)
+
+    # ---- QIR / JSON circuit input and output (abstractcircuit.py:417-496, 1249-1268, 1354-1390) ----------
+    @classmethod
+    def from_qir(cls, qir: List[Dict[str, Any]], circuit_params: Optional[Dict[str, Any]] = None,
+                 allow_channel: bool = False) -> "Circuit":  # fmt: skip
+        """Rebuild a circuit from its instruction list (`abstractcircuit.py:417-496`): entries with `parameters`
+        re-evaluate `gatef(**parameters)`, the others call the fixed-gate factory."""
+        circuit_params = dict(circuit_params or {})
+        if "nqubits" not in circuit_params:
+            circuit_params["nqubits"] = 1 + max((max(d["index"]) for d in qir), default=0)
+        c = cls(**circuit_params)
+        for d in qir:
+            if d.get("is_channel", False):
+                if allow_channel:
+                    raise NotImplementedError("noise channels are outside the B200 hot-path scope (SURVEY §2.1)")
+                continue
+            if d.get("mpo", False) or d.get("split"):
+                raise NotImplementedError("split / mpo gates are outside the B200 hot-path scope (SURVEY §2.1)")
+            gatef = d["gatef"]
+            if "parameters" not in d:
+                c.apply_general_gate(gatef(), *d["index"], name=d["name"], ir_dict={"gatef": gatef})
+            else:
+                params = dict(d["parameters"])
+                c.apply_general_gate(gatef(**params), *d["index"], name=d["name"], diagonal=d.get("diagonal", False),
+                                     ir_dict={"gatef": gatef, "parameters": params})  # fmt: skip
+        return c
+
+    def to_json(self, file: Optional[str] = None, simplified: bool = False) -> Any:
+        """`abstractcircuit.py:1249-1268`: the circuit as the reference's JSON list (`translation.qir2json`)."""
+        import json
+
+        tcqasm = qir2json(self.to_qir(), simplified=simplified)
+        if file is not None:
+            with open(file, "w") as f:
+                json.dump(tcqasm, f)
+        return json.dumps(tcqasm)
+
+    @classmethod
+    def from_json(cls, jsonstr: Any, circuit_params: Optional[Dict[str, Any]] = None) -> "Circuit":
+        """`abstractcircuit.py:1354-1374`."""
+        import json
+
+        if isinstance(jsonstr, str):
+            jsonstr = json.loads(jsonstr)
+        return cls.from_qir(json2qir(jsonstr), circuit_params)
+
+    @classmethod
+    def from_json_file(cls, file: str, circuit_params: Optional[Dict[str, Any]] = None) -> "Circuit":
+        """`abstractcircuit.py:1376-1390`."""
+        import json
+
+        with open(file, "r") as f:
+            return cls.from_json(json.load(f), circuit_params)
 
     # basecircuit.py:626-640 ---------------------------------------------------------------------
     def probability(self) -> torch.Tensor:
@@ -498,6 +554,93 @@ class Circuit:
 
 
 _ZERO = np.array([1.0, 0.0])
+
+
+# ---- translation.py:602-719 (tensor <-> JSON lists, qir <-> JSON dicts) ------------------------------
+def tensor_to_json(a: Any) -> Any:
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    a = np.asarray(a)
+    if np.iscomplexobj(a):
+        return [np.real(a).tolist(), np.imag(a).tolist()]
+    return [np.real(a).tolist()]
+
+
+def json_to_tensor(a: Any) -> Any:
+    ar = np.array(a[0])
+    if len(a) == 1:
+        return ar
+    assert len(a) == 2
+    return ar + 1.0j * np.array(a[1])
+
+
+def gate_json_name(gatef: Any) -> str:
+    """The name the reference stores in JSON (`gatef.n`, translation.py:667): `rx`, `cnot`, `exp1`, `any` ..."""
+    n = getattr(gatef, "n", None)
+    if n is not None:
+        return str(n)
+    fn = getattr(gatef, "__name__", str(gatef))
+    special = {"exponential_gate_unity": "exp1", "exponential_gate": "exp", "g": None}
+    if fn in special and special[fn] is not None:
+        return special[fn]  # type: ignore[return-value]
+    for name in vgates + sgates + diaggates:
+        if getattr(gates, name + "_gate", None) is gatef or getattr(gates, name, None) is gatef:
+            return name
+    return fn[:-5] if fn.endswith("_gate") else fn
+
+
+def get_u_parameter(m: np.ndarray) -> Tuple[float, float, float]:
+    """gates.py:606-627: (theta, phi, lambda) of the U gate equal to a 2x2 unitary up to a global phase."""
+    u = np.linalg.det(m) ** (-1 / 2) * m
+    theta = 2 * np.arccos(min(1.0, float(np.abs(u[1, 1]))))
+    plus, minus = 2 * np.angle(u[1, 1]), -2 * np.angle(u[1, 0])
+    return float(theta), float((plus - minus) / 2), float((plus + minus) / 2)
+
+
+def qir2json(qir: List[Dict[str, Any]], simplified: bool = False) -> List[Dict[str, Any]]:
+    """translation.py:631-690."""
+    out = []
+    for r in qir:
+        if r.get("is_channel", False):
+            continue
+        t = r["gate"].tensor
+        d = int(round(math.sqrt(t.numel())))
+        nm = t.detach().cpu().numpy().reshape(d, d) if not r.get("diagonal", False) else np.diag(t.detach().cpu().numpy().reshape(-1))
+        nmr, nmi = tensor_to_json(nm.astype(np.complex64))
+        uparams = [float(p) for p in get_u_parameter(nm.astype(np.complex128))] if nm.shape == (2, 2) else []
+        params = {k: tensor_to_json(v) for k, v in r.get("parameters", {}).items()}
+        item: Dict[str, Any] = {"name": gate_json_name(r["gatef"]), "qubits": list(r["index"])}
+        unsupported = ["any", "unitary", "mpo", "exp", "exp1", "r", "cr"]
+        if not simplified:
+            item.update({"matrix": [nmr, nmi], "uparams": uparams, "parameters": params, "mpo": bool(r.get("mpo", False))})
+        else:
+            if item["name"] in unsupported and uparams:
+                item.update({"uparams": uparams})
+            elif item["name"] in unsupported:
+                item.update({"matrix": [nmr, nmi]})
+            if params:
+                item.update({"parameters": params})
+        out.append(item)
+    return out
+
+
+def json2qir(tcqasm: List[Dict[str, Any]]) -> List[Dict[str, Any]]:
+    """translation.py:693-719."""
+    qir = []
+    for d in tcqasm:
+        param = {k: json_to_tensor(v) for k, v in d.get("parameters", {}).items()}
+        if param.get("dim") is not None:
+            param["dim"] = int(np.asarray(param["dim"]))
+        name = d["name"]
+        gatef = getattr(gates, name + "_gate", None) or getattr(gates, name)
+        if name == "diagonal":
+            gatef = gates.diagonal_gate
+        entry = {"index": tuple(d["qubits"]), "mpo": d.get("mpo", False), "split": None, "parameters": param,
+                 "gatef": gatef, "name": name, "diagonal": name in diaggates}  # fmt: skip
+        if not param and name in sgates:
+            entry.pop("parameters")
+        qir.append(entry)
+    return qir
 
 
 def _register() -> None:  # abstractcircuit.py:242-373 `_meta_apply`

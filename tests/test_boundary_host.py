@@ -274,3 +274,42 @@ def test_foreign_nodes_are_probed_once_per_topology():
         assert svengine.gate_kinds(gates2) == native
     finally:
         svengine.trust_gate_names = old
+
+
+# ---- QIR / JSON circuit formats (abstractcircuit.py:417-496, 1249-1268, 1354-1390) ---------------
+def _format_circuit(tc):
+    n = 5
+    ops = random_layers(n, 2, 3) + [("exp1", [0, 1], {"unitary": tc.gates._zz_matrix, "theta": 0.3}),
+                                    ("any", [2], {"unitary": np.array([[0.0, 1.0], [1.0, 0.0]])})]  # fmt: skip
+    c = build(tc, n, ops)
+    c.diagonal(0, 1, diag=np.exp(1j * np.arange(4)))
+    return n, ops, c
+
+
+def test_json_and_qir_round_trips_preserve_every_gate():
+    import json
+
+    import tensorcircuit_ng_b200 as tc
+
+    n, ops, c = _format_circuit(tc)
+    items = json.loads(c.to_json())
+    assert len(items) == len(ops) + 1
+    assert set(items[0]) == {"name", "qubits", "matrix", "uparams", "parameters", "mpo"}  # translation.py:666-678
+    assert [it["name"] for it in items[:3]] == [ops[0][0], ops[1][0], ops[2][0]]
+    for variant in (c.to_json(), c.to_json(simplified=True)):
+        c2 = tc.Circuit.from_json(variant)
+        assert len(c2._qir) == len(c._qir)
+        for a, b in zip(c._qir, c2._qir):
+            assert a["index"] == b["index"] and a["diagonal"] == b["diagonal"]
+            assert np.allclose(a["gate"].tensor.reshape(-1).numpy(), b["gate"].tensor.reshape(-1).numpy(), atol=1e-6)
+    c3 = tc.Circuit.from_qir(c.to_qir(), circuit_params={"nqubits": n})
+    assert [d["name"] for d in c3.to_qir()] == [d["name"] for d in c.to_qir()]
+    assert c.to_qir() is not c._qir  # a shallow copy (abstractcircuit.py:410-414)
+    # uparams: the U gate with these angles equals the 2x2 matrix up to a global phase (gates.py:606-627)
+    for it in items:
+        if it["uparams"]:
+            m = np.array(it["matrix"][0]) + 1j * np.array(it["matrix"][1])
+            u = tc.gates.u_gate(*it["uparams"]).tensor.numpy()
+            k = np.argmax(np.abs(m))
+            ph = m.reshape(-1)[k] / u.reshape(-1)[k]
+            assert abs(abs(ph) - 1) < 1e-5 and np.allclose(ph * u, m, atol=5e-4), it["name"]  # arccos(|U11| ~ 1) of complex64 data

@@ -264,3 +264,52 @@ def test_qaoa_n30_p1_matches_closed_form(cuda):
               - 0.5 * np.sin(2 * beta) ** 2 * np.cos(gp) ** (d + e - 2 * f) * (1 - np.cos(2 * gp) ** f))  # fmt: skip
         got = float(c.expectation_ps(z=[int(u), int(v)]).real)
         assert abs(got + zz) <= 2e-5, (u, v, got, -zz)
+
+
+def test_json_round_trip_state_matches_oracle(cuda, tmp_path):
+    """(f)3: `to_json -> from_json(_file)` and `from_qir` give the oracle's state of the original gate list."""
+    tc = _tc()
+    from test_boundary_host import _format_circuit
+
+    n, ops, c = _format_circuit(tc)
+    oc = build(tc_oracle, n, ops)
+    oc.diagonal(0, 1, diag=np.exp(1j * np.arange(4)))
+    from tc_oracle import cons as ocons
+
+    with ocons.runtime_contractor("plain"):
+        ref = np.asarray(oc.wavefunction()).reshape(-1)
+    f = tmp_path / "c.json"
+    c.to_json(file=str(f))
+    for c2 in (tc.Circuit.from_json(c.to_json(simplified=True)), tc.Circuit.from_json_file(str(f)),
+               tc.Circuit.from_qir(c.to_qir())):  # fmt: skip
+        assert np.abs(c2.wavefunction().cpu().numpy().reshape(-1) - ref).max() <= 1e-5
+
+
+def test_copynode_network_through_tn_route_matches_oracle(cuda):
+    """R12: a hyperedge (CopyNode) network contracted by the tensor-network route (`use_primitives` path of
+    cons.py:898-908) — state and an expectation sandwich built with `reuse=False` — against the oracle."""
+    tc = _tc()
+
+    def circ(mod):
+        c = mod.Circuit(5)
+        for q in range(5):
+            c.h(q)
+        c.diagonal(0, 1, diag=np.exp(1j * np.arange(4)).astype(np.complex64))
+        c.rx(1, theta=0.3)
+        c.diagonal(2, diag=np.array([1.0, 1j], dtype=np.complex64))
+        c.cnot(2, 3)
+        c.diagonal(3, 4, 0, diag=np.exp(0.5j * np.arange(8)).astype(np.complex64))
+        c.ry(4, theta=-0.8)
+        return c
+
+    from tc_oracle import cons as ocons
+
+    with ocons.runtime_contractor("plain"):
+        ref = np.asarray(circ(tc_oracle).wavefunction()).reshape(-1)
+        eref = complex(circ(tc_oracle).expectation_ps(z=[1], x=[4]))
+    for method, kw in (("tn", {}), ("greedy", {}), ("custom", {"optimizer": None})):
+        with tc.runtime_contractor(method, **kw):
+            psi = circ(tc).wavefunction()
+            e = circ(tc).expectation((tc.gates.z(), [1]), (tc.gates.x(), [4]), reuse=False)
+        assert np.abs(psi.cpu().numpy().reshape(-1) - ref).max() <= 1e-5, method
+        assert abs(complex(e.cpu()) - eref) <= 1e-5, method
