@@ -771,20 +771,19 @@ def contraction_record(args: argparse.Namespace, steps: int, warmup: int) -> Any
                 "full_job_estimate_s": ms_per_step * 1e-3 / nsl * dc.nslices / world,
             },
             "roofline": {
-                "kernel": "tcb::stream_contract_kernel / tcb::tc::gemm_tc_kernel (plan is streaming-dominated)",
-                "bound": "hbm",
-                "achieved": gbs,
-                "peak": peak,
-                "unit": "GB/s",
-                "frac": gbs / peak,
+                "kernel": "tcb::tc::gemm_tc_kernel (tcgen05 / TMEM, 3xTF32 complex), per GPU",
+                "bound": "tensor",
+                "achieved": tflops / world,
+                "peak": tf32 / 3.0,
+                "unit": "TFLOP/s",
+                "frac": (tflops / world) / (tf32 / 3.0) if tf32 else None,
+                "peak_source": f"cuBLAS TF32 8192^3 measured in this run ({tf32:.0f} TFLOP/s) / 3 (3xTF32 complex: 24 "
+                               "issued flops per 8 algorithmic)",
                 "traffic": None,
-                "alg_bytes_per_slice": bytes_slice,
-                "plan_bytes_per_slice_unfused": plan_bytes_slice,
-                "tensor": {"bound": "tensor", "achieved": tflops / world, "peak": tf32 / 3.0, "unit": "TFLOP/s",
-                           "frac": (tflops / world) / (tf32 / 3.0) if tf32 else None,
-                           "peak_source": f"cuBLAS TF32 8192^3 measured in this run ({tf32:.0f} TFLOP/s) / 3 (3xTF32 "
-                                          "complex: 24 issued flops per 8 algorithmic)",
-                           "gemm_shaped_flops_share": gemm_flops / flops_slice if flops_slice else None},
+                "gemm_shaped_flops_share": gemm_flops / flops_slice if flops_slice else None,
+                "alg_flops_per_slice": flops_slice,
+                "hbm": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                        "alg_bytes_per_slice": bytes_slice, "plan_bytes_per_slice_unfused": plan_bytes_slice},
             },
             "cpu_baseline": cpu_baseline,
             "e2e": {

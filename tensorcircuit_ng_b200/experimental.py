@@ -133,13 +133,19 @@ class DistributedContractor:
         target = int((opts.get("slicing_reconf_opts") or {}).get("target_size", 2**28))
         hyper = bool(opts.get("hyper_diagonal", True))
         input_sets, output_set, size_dict, _, groups = DistributedContractor._network(nodes_fn, params, hyper)
-        td = planner.search_elimination(input_sets, output_set, size_dict, target_size=target, groups=groups)
-        if len(input_sets) <= 64:  # small networks: the pairwise greedy is sometimes better, keep the cheaper
-            tg = planner.search(input_sets, output_set, size_dict, target_size=target)
-            sa = planner.path_stats(input_sets, output_set, size_dict, td["path"], list(td["sliced_inds"]))
-            sb = planner.path_stats(input_sets, output_set, size_dict, tg["path"], list(tg["sliced_inds"]))
-            if sb["size"] <= target and sb["flops"] * sb["nslices"] < sa["flops"] * sa["nslices"]:
-                td = tg
+        def total(t: Dict[str, Any]) -> float:
+            st = planner.path_stats(input_sets, output_set, size_dict, t["path"], list(t["sliced_inds"]))
+            return st["flops"] * st["nslices"] * (1.0 if st["size"] <= target else 1e30)
+
+        cands = []
+        if len(set(groups.values())) >= 4:  # circuit-shaped: site-block sweep (GEMM-shaped boundary x site steps)
+            cands.append(planner.search_sites(input_sets, output_set, size_dict, groups, target_size=target,
+                                              max_slices_log2=int(opts.get("max_slices_log2", 48))))  # fmt: skip
+        if len(input_sets) <= 400 or not cands:
+            cands.append(planner.search_elimination(input_sets, output_set, size_dict, target_size=target, groups=groups))
+        if len(input_sets) <= 64:  # small networks: the pairwise greedy is sometimes better
+            cands.append(planner.search(input_sets, output_set, size_dict, target_size=target))
+        td = min(cands, key=total)
         td["hyper_diagonal"] = hyper
         return td
 

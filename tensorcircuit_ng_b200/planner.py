@@ -920,3 +920,184 @@ def search_elimination(inputs: Sequence[Sequence[str]], output: Sequence[str], s
         "sliced_inds": {s: size_dict[s] for s in sliced},
         "planner": "tensorcircuit_ng_b200.planner.search_elimination (ours; not cotengra)",
     }
+
+
+# ---------------------------------------------------------------------------------------------
+# Site-block sweep planner (round 2).  The wire-sweep elimination above removes ONE index at a time, so its
+# trees are made of skinny absorptions (a big tensor times a 2..64-element one) and its boundary carries every
+# half-finished wire: 2^57 slices on the 7x7 depth-20 amplitude.  Here the network is coarsened first —
+# every qubit wire's own tensors (inputs, one-qubit gates, closing one-hots) are contracted along the time
+# direction into ONE site tensor over the hyper-indices its couplers touch — and the sites are then absorbed
+# into a boundary tensor one at a time, couplers to already absorbed sites folded into the site tensor just
+# before (a PEPS boundary contraction).  Every big step is a boundary x site contraction over all the bonds
+# between them: GEMM shaped (K = 2^#bonds), which is what the tcgen05 kernel wants.  Site orders tried: RCM /
+# spectral sweeps of the wire graph and greedy boundary growth from low-degree corners; the cheapest sliced
+# tree wins.  This is the role cotengra's partition-based trees + slicing play for the reference
+# (tensorcircuit/experimental.py:930-954); cotengra itself is not installed here.
+class _Ssa:
+    def __init__(self, net: _Net, terms: Dict[int, int], nxt: int) -> None:
+        self.net, self.terms, self.nxt, self.out = net, terms, nxt, net.output
+        self.ssa: List[Tuple[int, int]] = []
+        self.occ = [0] * len(net.names)
+        for m in terms.values():
+            for i in _bits(m):
+                self.occ[i] += 1
+
+    def result(self, a: int, b: int) -> int:
+        ma, mb = self.terms[a], self.terms[b]
+        union, both = ma | mb, ma & mb
+        keep = union & self.out
+        for i in _bits(union & ~self.out):
+            if self.occ[i] - (2 if (both >> i) & 1 else 1) > 0:
+                keep |= 1 << i
+        return keep
+
+    def merge(self, a: int, b: int) -> int:
+        keep = self.result(a, b)
+        for t in (a, b):
+            for i in _bits(self.terms[t]):
+                self.occ[i] -= 1
+            del self.terms[t]
+        for i in _bits(keep):
+            self.occ[i] += 1
+        self.terms[self.nxt] = keep
+        self.ssa.append((a, b))
+        self.nxt += 1
+        return self.nxt - 1
+
+    def merge_all(self, ids: List[int]) -> int:
+        """Greedy by result size inside a small group."""
+        live = list(ids)
+        while len(live) > 1:
+            best = None
+            for x in range(len(live)):
+                for y in range(x + 1, len(live)):
+                    if not (self.terms[live[x]] & self.terms[live[y]]) and len(live) > 2:
+                        continue
+                    k = (_popcount(self.result(live[x], live[y])), live[x], live[y])
+                    if best is None or k < best[0]:
+                        best = (k, x, y)
+            if best is None:  # nothing shares an index: outer product of the two smallest
+                live.sort(key=lambda t: (_popcount(self.terms[t]), t))
+                best = ((0, 0, 0), 0, 1)
+            _, x, y = best
+            new = self.merge(live[x], live[y])
+            live = [t for k, t in enumerate(live) if k not in (x, y)] + [new]
+        return live[0]
+
+
+def _site_tree(net: _Net, gid: Sequence[Any], order_w: Sequence[Any], n_inputs: int) -> List[Tuple[int, int]]:
+    b = _Ssa(net, {i: m for i, m in enumerate(net.inputs)}, n_inputs)
+    wires_of = {t: frozenset(gid[i] for i in _bits(m)) for t, m in b.terms.items()}
+    own: Dict[Any, List[int]] = {}
+    couplers: List[int] = []
+    scalars: List[int] = []
+    for t, ws in wires_of.items():
+        if len(ws) == 1:
+            own.setdefault(next(iter(ws)), []).append(t)
+        elif len(ws) == 0:
+            scalars.append(t)
+        else:
+            couplers.append(t)
+    site: Dict[Any, int] = {}
+    for w in order_w:
+        if w in own:
+            site[w] = b.merge_all(sorted(own[w]))
+    done: set = set()
+    boundary: Optional[int] = None
+    pending = {c: wires_of[c] for c in couplers}
+    for w in order_w:
+        done.add(w)
+        t = site.get(w)
+        ready = sorted(c for c, ws in pending.items() if w in ws and ws <= done)
+        for c in ready:
+            del pending[c]
+            t = c if t is None else b.merge(t, c)
+        if t is None:
+            continue
+        boundary = t if boundary is None else b.merge(boundary, t)
+    rest = [x for x in list(pending) + scalars]
+    for x in rest:
+        boundary = x if boundary is None else b.merge(boundary, x)
+    return b.ssa
+
+
+def _greedy_site_orders(wg: Any, starts: int = 4) -> List[List[Any]]:
+    """Grow the absorbed set one site at a time, always taking the site that leaves the smallest cut."""
+    nodes = sorted(wg.nodes, key=str)
+    if not nodes:
+        return []
+    deg = {v: sum(d.get("weight", 1) for _, _, d in wg.edges(v, data=True)) for v in nodes}
+    firsts = sorted(nodes, key=lambda v: (deg[v], str(v)))[:starts]
+    out = []
+    for f in firsts:
+        inside = {f}
+        order = [f]
+        cut = {v: 0 for v in nodes}  # weight of edges from v into `inside`
+        for _, u, d in wg.edges(f, data=True):
+            cut[u] += d.get("weight", 1)
+        while len(order) < len(nodes):
+            best = None
+            for v in nodes:
+                if v in inside:
+                    continue
+                delta = deg[v] - 2 * cut[v]  # change of the cut when v joins
+                key = (0 if cut[v] > 0 else 1, delta, -cut[v], str(v))
+                if best is None or key < best[0]:
+                    best = (key, v)
+            v = best[1]
+            inside.add(v)
+            order.append(v)
+            for _, u, d in wg.edges(v, data=True):
+                if u not in inside:
+                    cut[u] += d.get("weight", 1)
+        out.append(order)
+    return out
+
+
+def search_sites(inputs: Sequence[Sequence[str]], output: Sequence[str], size_dict: Dict[str, int],
+                 groups: Dict[str, Any], target_size: Optional[int] = None, max_slices_log2: int = 48,
+                 keep: int = 3) -> Dict[str, Any]:  # fmt: skip
+    """Site-block sweep + greedy slicing; returns a `tree_data` dict (tensorcircuit/experimental.py:947-953)."""
+    inputs = [tuple(t) for t in inputs]
+    output = tuple(output)
+    net = _Net(inputs, output, size_dict)
+    gid, wg = _wire_graph(net, net.inputs, groups)
+    orders = _greedy_site_orders(wg) + _wire_orders(wg)
+    scored = []
+    seen = set()
+    for order_w in orders:
+        key = tuple(str(w) for w in order_w)
+        if key in seen:
+            continue
+        seen.add(key)
+        path = ssa_to_linear(_site_tree(net, gid, order_w, len(inputs)), len(inputs))
+        st = path_stats(inputs, output, size_dict, path)
+        scored.append((st["flops"], st["size"], path))
+    scored.sort(key=lambda x: (x[0], x[1]))
+    best: Optional[Tuple[float, List[Tuple[int, int]], List[str]]] = None
+    for _, _, path in scored[:keep]:
+        sliced: List[str] = []
+        st = path_stats(inputs, output, size_dict, path)
+        if target_size is not None:
+            while st["size"] > target_size and len(sliced) < max_slices_log2:
+                s = _pick_slice_index(inputs, output, size_dict, path, sliced, target_size)
+                if s is None:
+                    break
+                sliced.append(s)
+                st = path_stats(inputs, output, size_dict, path, sliced)
+        total = st["flops"] * st["nslices"]
+        if target_size is not None and st["size"] > target_size:
+            total *= 1e30
+        if best is None or total < best[0]:
+            best = (total, path, list(sliced))
+    assert best is not None
+    _, path, sliced = best
+    return {
+        "inputs": tuple(inputs),
+        "output": output,
+        "size_dict": dict(size_dict),
+        "path": [tuple(p) for p in path],
+        "sliced_inds": {s: size_dict[s] for s in sliced},
+        "planner": "tensorcircuit_ng_b200.planner.search_sites (ours; not cotengra)",
+    }

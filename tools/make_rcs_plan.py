@@ -13,7 +13,7 @@ lt = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 t0 = time.time()
 nodes_fn = lambda _: bench.build_rcs(tc, rows, cols, depth).amplitude_before("0" * (rows * cols))
 inp, out, sd, _, groups = DistributedContractor._network(nodes_fn, None, True)
-td = planner.search_elimination(inp, out, sd, target_size=2**lt, groups=groups, max_slices_log2=80)
+td = planner.search_sites(inp, out, sd, groups, target_size=2**lt, max_slices_log2=80)
 td["hyper_diagonal"] = True
 st = planner.path_stats(td["inputs"], td["output"], td["size_dict"], td["path"], list(td["sliced_inds"]))
 print(f"{rows}x{cols} d{depth}: tensors {len(inp)} log10 cmacs/slice {math.log10(st['flops']):.2f} log2 size {math.log2(st['size']):.0f} "
