@@ -28,6 +28,9 @@
 //   tile t+1 while the tensor core works on t and the epilogue drains t-1: the skinny steps of a
 //   contraction tree (one k block per tile) are latency-bound without that overlap.
 // Bound: HBM for the skinny steps of a contraction tree (K, N <~ 64), the TF32 pipe / 3 beyond.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "tn_common.cuh"
 #include "../../include/tcb200.h"
@@ -70,6 +73,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
   }
+}
+// TMA engine, non-tensor form: one elected thread moves a contiguous block global -> shared and the bytes are
+// accounted on the stage's mbarrier (SASS: UBLKCP + SYNCS.ARRIVE.TRANS64)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -164,7 +178,10 @@ __device__ __forceinline__ void load4(const float2* __restrict__ X, uint64_t bas
   }
 }
 
-template <int BN>
+// PACKED: A and B are pre-split operand images (pack_operand_kernel below): per (row tile, k block) the four TF32
+// planes of a stage in the exact shared-memory layout, so the producer side is one thread issuing two bulk copies
+// per stage — no gather, no conversions, no generic-proxy stores between the memory system and the tensor core.
+template <int BN, bool PACKED>
 __global__ void __launch_bounds__(N_THREADS, 1)
 gemm_tc_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float2* C, ContractParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -187,7 +204,7 @@ gemm_tc_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float
 
   if (tid == N_PROD) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full + s, N_PROD);
+      mbar_init(full + s, PACKED ? 1 : N_PROD);
       mbar_init(empty + s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -222,32 +239,77 @@ gemm_tc_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float
 
   uint32_t it = 0;      // k blocks processed by this CTA so far (stage ring position)
   uint32_t tcount = 0;  // tiles processed by this CTA so far
-  if (warp < MMA_WARP) {
+  if (PACKED && warp < MMA_WARP) {
+    // ===================== producer: bulk copies of pre-split stage images =====================
+    if (tid == 0) {
+      const unsigned char* PA = reinterpret_cast<const unsigned char*>(A);
+      const unsigned char* PB = reinterpret_cast<const unsigned char*>(B);
+      for (uint64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const uint64_t bt = tile / tiles_per_batch, tr = tile % tiles_per_batch;
+        const uint64_t mt = tr / tiles_n, nt = tr % tiles_n;
+        const unsigned char* a_src = PA + ((bt * tiles_m + mt) * nkb) * (uint64_t)(4 * St::A_TILE);
+        const unsigned char* b_src = PB + ((bt * tiles_n + nt) * nkb) * (uint64_t)(4 * St::B_TILE);
+        for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          unsigned char* st = stages + (size_t)s * St::BYTES;
+          mbar_expect_tx(full + s, St::BYTES);
+          bulk_g2s(st, a_src + (uint64_t)kb * (4 * St::A_TILE), 4 * St::A_TILE, full + s);
+          bulk_g2s(st + 4 * St::A_TILE, b_src + (uint64_t)kb * (4 * St::B_TILE), 4 * St::B_TILE, full + s);
+        }
+      }
+    }
+  } else if (warp < MMA_WARP) {
     // ===================== producers =====================
     // Work items = (tile, k block), flattened; the global loads of item w+1 are issued before item w
     // is split and stored, so every thread keeps two batches in flight (a skinny step has ONE k block
     // per tile: without the prefetch each tile pays a full DRAM latency).
-    const int row = tid & (BM - 1), half = tid >> 7;  // A: row `row`, k groups {2 half, 2 half + 1}
+    // A unit = (row, group of 4 k) of the 128 x 16 stage tile, two units per thread.  When the four lowest k modes
+    // are the four lowest address bits of the operand (tnengine's layout planning makes the contracted modes of
+    // every intermediate the lowest bits), the 16 k of a row are one contiguous 128-byte run and a warp takes one
+    // 8-row group with all four k groups (lane = 8 * group + row): its load instruction touches 8 cache lines
+    // instead of 32 (the gathers kept the L1 data pipe 45 % busy and the tensor pipe at 33 %), and every quarter
+    // warp still writes 8 different rows of one core-matrix column, i.e. 8 distinct 16-byte bank groups.
+    const bool contigA = p.nk >= 4 && p.k_a[0] == 0 && p.k_a[1] == 1 && p.k_a[2] == 2 && p.k_a[3] == 3;
+    const bool contigB = p.nk >= 4 && p.k_b[0] == 0 && p.k_b[1] == 1 && p.k_b[2] == 2 && p.k_b[3] == 3;
+    int rowA[2], grpA[2];
+#pragma unroll
+    for (int gg = 0; gg < 2; ++gg) {
+      const int u = tid + N_PROD * gg;
+      rowA[gg] = contigA ? (((u >> 5) << 3) | (u & 7)) : (tid & (BM - 1));
+      grpA[gg] = contigA ? ((u >> 3) & 3) : (2 * (tid >> 7) + gg);
+    }
     constexpr int UB = (BN * (KB / 4) + N_PROD - 1) / N_PROD;  // B units (row n, k group g) per thread
+    int rowB[UB], grpB[UB];
+#pragma unroll
+    for (int i = 0; i < UB; ++i) {
+      const int u = tid + i * N_PROD;
+      rowB[i] = contigB ? (((u >> 5) << 3) | (u & 7)) : (u % BN);
+      grpB[i] = contigB ? ((u >> 3) & 3) : (u / BN);
+    }
     struct Batch {
       float2 va[2][4];
       float2 vb[UB][4];
     };
-    uint64_t cur_tile = ~0ull, offAm = 0, offBn_r[UB];
-    bool row_ok = false, col_ok[UB];
+    uint64_t cur_tile = ~0ull, offAm[2] = {0, 0}, offBn_r[UB];
+    bool row_ok[2] = {false, false}, col_ok[UB];
     auto issue = [&](uint64_t tile, uint32_t kb, Batch& r) {
       if (tile != cur_tile) {  // new tile: row / column bases
         cur_tile = tile;
         const uint64_t bt = tile / tiles_per_batch, tr = tile % tiles_per_batch;
         const uint64_t m0 = (tr / tiles_n) * BM, n0 = (tr % tiles_n) * BN;
-        row_ok = m0 + row < Mtot;
-        offAm = deposit(bt, p.batch_a, p.nb) | deposit(m0 + row, p.m_a, p.nm);
+        const uint64_t a_b = deposit(bt, p.batch_a, p.nb);
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          row_ok[gg] = m0 + rowA[gg] < Mtot;
+          offAm[gg] = a_b | deposit(m0 + rowA[gg], p.m_a, p.nm);
+        }
         const uint64_t b_b = deposit(bt, p.batch_b, p.nb);
 #pragma unroll
         for (int i = 0; i < UB; ++i) {
-          const int u = tid + i * N_PROD, n = u % BN;
-          col_ok[i] = u < BN * (KB / 4) && n0 + n < Ntot;
-          offBn_r[i] = b_b | deposit(n0 + n, p.n_b, p.nn);
+          const int u = tid + i * N_PROD;
+          col_ok[i] = u < BN * (KB / 4) && n0 + rowB[i] < Ntot;
+          offBn_r[i] = b_b | deposit(n0 + rowB[i], p.n_b, p.nn);
         }
       }
       const uint64_t k0 = (uint64_t)kb * KB;
@@ -256,24 +318,23 @@ gemm_tc_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float
       const uint64_t hiB = p.nk > 4 ? deposit((uint64_t)kb, p.k_b + 4, p.nk - 4) : 0;
 #pragma unroll
       for (int gg = 0; gg < 2; ++gg)
-        load4(A, offAm | hiA, dAlo, 2 * half + gg, vecA, row_ok && k0 + 4 * (2 * half + gg) < Ktot, k0, Ktot,
+        load4(A, offAm[gg] | hiA, dAlo, grpA[gg], vecA, row_ok[gg] && k0 + 4 * grpA[gg] < Ktot, k0, Ktot,
               p.conj_a != 0, r.va[gg]);
 #pragma unroll
-      for (int i = 0; i < UB; ++i) {
-        const int g = (tid + i * N_PROD) / BN;
-        load4(B, offBn_r[i] | hiB, dBlo, g, vecB, col_ok[i] && k0 + 4 * g < Ktot, k0, Ktot, p.conj_b != 0, r.vb[i]);
-      }
+      for (int i = 0; i < UB; ++i)
+        load4(B, offBn_r[i] | hiB, dBlo, grpB[i], vecB, col_ok[i] && k0 + 4 * grpB[i] < Ktot, k0, Ktot,
+              p.conj_b != 0, r.vb[i]);
     };
     auto commit = [&](const Batch& r) {
       const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(empty + s, ph ^ 1);
       unsigned char* st = stages + (size_t)s * St::BYTES;
 #pragma unroll
-      for (int gg = 0; gg < 2; ++gg) split_store(st, St::A_TILE, tile_off(row, 2 * half + gg), r.va[gg]);
+      for (int gg = 0; gg < 2; ++gg) split_store(st, St::A_TILE, tile_off(rowA[gg], grpA[gg]), r.va[gg]);
 #pragma unroll
       for (int i = 0; i < UB; ++i) {
         const int u = tid + i * N_PROD;
-        if (u < BN * (KB / 4)) split_store(st + 4 * St::A_TILE, St::B_TILE, tile_off(u % BN, u / BN), r.vb[i]);
+        if (u < BN * (KB / 4)) split_store(st + 4 * St::A_TILE, St::B_TILE, tile_off(rowB[i], grpB[i]), r.vb[i]);
       }
       fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
       mbar_arrive(full + s);
@@ -411,17 +472,57 @@ gemm_tc_kernel(const float2* __restrict__ A, const float2* __restrict__ B, float
   }
 }
 
+// Pre-split operand image for the PACKED kernel.  X is A (rows = m) or B (rows = n) in its bit-deposited layout;
+// the image is [batch][row tile of ROWS][k block of KB] x 4 planes (re hi, re lo, im hi, im lo) x ROWS x KB TF32
+// values in the UMMA canonical K-major core-matrix layout.  One CTA per stage image; HBM bound (8 B read, 16 B
+// written per element).  Rows / k beyond the edge are zero.
+template <int ROWS>
+__global__ void __launch_bounds__(256) pack_operand_kernel(const float2* __restrict__ X, unsigned char* __restrict__ out,
+                                                           int nb, int nrow, int nk, const int8_t* __restrict__ pos,
+                                                           int conj) {
+  // pos: [32] batch, [32] row, [32] k bit positions
+  __shared__ int8_t sp[96];
+  __shared__ uint64_t dlo[KB];
+  if (threadIdx.x < 96) sp[threadIdx.x] = pos[threadIdx.x];
+  __syncthreads();
+  const int nklo = nk < 4 ? nk : 4;
+  if (threadIdx.x < KB) dlo[threadIdx.x] = deposit((uint64_t)threadIdx.x, sp + 64, nklo);
+  __syncthreads();
+  const uint64_t Rtot = 1ull << nrow, Ktot = 1ull << nk;
+  const uint64_t tiles_r = (Rtot + ROWS - 1) / ROWS;
+  const uint32_t nkb = (uint32_t)((Ktot + KB - 1) / KB);
+  const uint64_t total = (tiles_r << nb) * nkb;
+  const bool vec = nk >= 2 && sp[64] == 0 && sp[65] == 1;
+  constexpr uint32_t TILE = ROWS * KB * 4;
+  constexpr int UNITS = ROWS * (KB / 4);
+  for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const uint32_t kb = (uint32_t)(w % nkb);
+    const uint64_t rt = (w / nkb) % tiles_r, bt = (w / nkb) / tiles_r;
+    const uint64_t k0 = (uint64_t)kb * KB;
+    const uint64_t hi = (nk > 4 ? deposit((uint64_t)kb, sp + 68, nk - 4) : 0) | deposit(bt, sp, nb);
+    unsigned char* img = out + w * (uint64_t)(4 * TILE);
+    for (int u = threadIdx.x; u < UNITS; u += 256) {
+      const int row = ((u >> 5) << 3) | (u & 7), g = (u >> 3) & 3;  // a warp = one 8-row group x 4 k groups
+      const uint64_t r = rt * ROWS + row;
+      float2 v[4];
+      load4(X, hi | deposit(r, sp + 32, nrow), dlo, g, vec, r < Rtot && k0 + 4 * g < Ktot, k0, Ktot, conj != 0, v);
+      split_store(img, TILE, tile_off(row, g), v);
+    }
+  }
+}
+
 template <int BN>
 static size_t smem_bytes() {
   return (size_t)STAGES * Stage<BN>::BYTES + (2 * STAGES + 4) * 8 + 16 + (size_t)2 * BN * 8 + (size_t)2 * KB * 8 + 128;
 }
 
-template <int BN>
+template <int BN, bool PACKED>
 static int launch(const float2* a, const float2* b, float2* c, const ContractParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   const size_t smem = smem_bytes<BN>();
   if (!attr_set) {
-    TCB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
     attr_set = true;
   }
   const uint64_t Mtot = 1ull << p.nm, Ntot = 1ull << p.nn;
@@ -429,9 +530,54 @@ static int launch(const float2* a, const float2* b, float2* c, const ContractPar
   uint64_t grid = tiles;
   const uint64_t cap = (uint64_t)sm_count();
   if (grid > cap) grid = cap;
-  gemm_tc_kernel<BN><<<(unsigned)grid, N_THREADS, smem, stream>>>(a, b, c, p);
+  gemm_tc_kernel<BN, PACKED><<<(unsigned)grid, N_THREADS, smem, stream>>>(a, b, c, p);
   TCB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// pre-split both operands into a stream-ordered scratch allocation, then run the bulk-copy fed kernel
+static int launch_packed(const float2* a, const float2* b, float2* c, const ContractParams& p, cudaStream_t stream) {
+  constexpr int BN = 128;
+  const uint64_t Mtot = 1ull << p.nm, Ntot = 1ull << p.nn, Ktot = 1ull << p.nk;
+  const uint64_t tiles_m = (Mtot + BM - 1) / BM, tiles_n = (Ntot + BN - 1) / BN, nkb = (Ktot + KB - 1) / KB;
+  const size_t a_bytes = (size_t)((tiles_m << p.nb) * nkb) * 4 * Stage<BN>::A_TILE;
+  const size_t b_bytes = (size_t)((tiles_n << p.nb) * nkb) * 4 * Stage<BN>::B_TILE;
+  static bool pool_set = false;
+  if (!pool_set) {  // keep freed scratch in the pool: the next contraction of the tree reuses it
+    int dev = 0;
+    cudaMemPool_t pool;
+    TCB_CHECK_CUDA(cudaGetDevice(&dev));
+    TCB_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = ~0ull;
+    TCB_CHECK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    pool_set = true;
+  }
+  unsigned char* scratch = nullptr;
+  int8_t* d_pos = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), a_bytes + b_bytes + 256, stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1;  // no room for the operand images: the caller falls back to the gathering kernel
+  }
+  d_pos = reinterpret_cast<int8_t*>(scratch + a_bytes + b_bytes);
+  int8_t h_pos[192];
+  memcpy(h_pos, p.batch_a, 32);
+  memcpy(h_pos + 32, p.m_a, 32);
+  memcpy(h_pos + 64, p.k_a, 32);
+  memcpy(h_pos + 96, p.batch_b, 32);
+  memcpy(h_pos + 128, p.n_b, 32);
+  memcpy(h_pos + 160, p.k_b, 32);
+  TCB_CHECK_CUDA(cudaMemcpyAsync(d_pos, h_pos, 192, cudaMemcpyHostToDevice, stream));
+  const unsigned cap = (unsigned)sm_count() * 8;
+  const uint64_t wa = (tiles_m << p.nb) * nkb, wb = (tiles_n << p.nb) * nkb;
+  pack_operand_kernel<BM><<<(unsigned)(wa < cap ? wa : cap), 256, 0, stream>>>(a, scratch, p.nb, p.nm, p.nk, d_pos,
+                                                                              p.conj_a);
+  pack_operand_kernel<BN><<<(unsigned)(wb < cap ? wb : cap), 256, 0, stream>>>(b, scratch + a_bytes, p.nb, p.nn, p.nk,
+                                                                              d_pos + 96, p.conj_b);
+  TCB_CHECK_CUDA(cudaGetLastError());
+  const int rc = launch<BN, true>(reinterpret_cast<const float2*>(scratch),
+                                  reinterpret_cast<const float2*>(scratch + a_bytes), c, p, stream);
+  TCB_CHECK_CUDA(cudaFreeAsync(scratch, stream));
+  return rc;
 }
 
 }  // namespace tc
@@ -440,10 +586,20 @@ static int launch(const float2* a, const float2* b, float2* c, const ContractPar
 // beyond 128: every extra column of a tile amortises the hi / lo split of the A rows)
 int launch_contract_tc(const float2* a, const float2* b, float2* c, const ContractParams& p, cudaStream_t stream) {
   const uint64_t Ntot = 1ull << p.nn;
-  if (Ntot <= 16) return tc::launch<16>(a, b, c, p, stream);
-  if (Ntot <= 32) return tc::launch<32>(a, b, c, p, stream);
-  if (Ntot <= 64) return tc::launch<64>(a, b, c, p, stream);
-  return tc::launch<128>(a, b, c, p, stream);
+  // fat steps (every operand element is reused >= 128 times): split the operands once, feed the tensor core by
+  // bulk copies.  TCB_TN_PACKED=0 keeps the gathering kernel (parity tests run both).
+  static const int packed_mode = [] {
+    const char* e = getenv("TCB_TN_PACKED");
+    return e ? atoi(e) : 1;
+  }();
+  if (packed_mode && p.nn >= 7 && p.nm >= 7 && p.nk >= 6) {
+    const int rc = tc::launch_packed(a, b, c, p, stream);
+    if (rc >= 0) return rc;
+  }
+  if (Ntot <= 16) return tc::launch<16, false>(a, b, c, p, stream);
+  if (Ntot <= 32) return tc::launch<32, false>(a, b, c, p, stream);
+  if (Ntot <= 64) return tc::launch<64, false>(a, b, c, p, stream);
+  return tc::launch<128, false>(a, b, c, p, stream);
 }
 
 }  // namespace tcb

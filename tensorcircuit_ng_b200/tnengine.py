@@ -226,6 +226,7 @@ _FUSE_SMALL = 64  # elements: what the streaming kernel keeps in shared memory (
 _FUSE_BIG = 1 << 16
 _schedule_cache: Dict[Any, Any] = {}
 fuse_skinny_chains = True
+plan_layouts = True  # order every intermediate's modes for its consumer (contracted modes lowest)
 
 
 def _keep_modes(ta: Sequence[str], tb: Sequence[str], occ: Dict[str, int], out_set: set) -> List[str]:
@@ -259,7 +260,8 @@ def build_schedule(inputs: Sequence[Sequence[str]], output: Sequence[str], path:
     — the tensor-network form of fusing consecutive gates into one statevector pass.  Any association
     order of a tensor network is valid; kept modes are recomputed from occurrence counts."""
     fuse = fuse_skinny_chains if fuse is None else fuse
-    key = (tuple(tuple(t) for t in inputs), tuple(output), tuple(tuple(p) for p in path), tuple(sliced), fuse)
+    key = (tuple(tuple(t) for t in inputs), tuple(output), tuple(tuple(p) for p in path), tuple(sliced), fuse,
+           plan_layouts)
     hit = _schedule_cache.get(key)
     if hit is not None:
         return hit
@@ -284,14 +286,21 @@ def build_schedule(inputs: Sequence[Sequence[str]], output: Sequence[str], path:
     out_set = set(output)
 
     def forward(pairs: Sequence[Tuple[int, int, int]]):
-        """Recompute every step's kept modes for an SSA step list [(a, b, out)]."""
+        """Recompute every step's kept modes for an SSA step list [(a, b, out)].
+
+        Layout planning (round 2): the physical layout of an intermediate is free, so its mode list is ordered
+        for the step that CONSUMES it — the modes that step contracts come last (= the lowest address bits), in
+        one canonical order shared by both operands of that step.  The tensor-core kernel then reads 16
+        consecutive k of a row as one contiguous 128-byte run from either operand (tn_gemm_tc.cu: with scattered
+        k bits every lane of a gather touched its own cache line and the producers, not the tensor pipe, set
+        the pace)."""
         occ: Dict[str, int] = {}
         for t in list(terms.values())[:n]:
             for m in t:
                 occ[m] = occ.get(m, 0) + 1
         tm = {i: terms[i] for i in range(n)}
-        steps = []
-        for si, (a, b, o) in enumerate(pairs):
+        keeps: List[List[str]] = []
+        for si, (a, b, o) in enumerate(pairs):  # pass 1: which modes survive each step (order irrelevant)
             ta, tb = tm[a], tm[b]
             keep = list(output) if si == len(pairs) - 1 else _keep_modes(ta, tb, occ, out_set)
             for m in ta:
@@ -300,6 +309,32 @@ def build_schedule(inputs: Sequence[Sequence[str]], output: Sequence[str], path:
                 occ[m] -= 1
             for m in keep:
                 occ[m] = occ.get(m, 0) + 1
+            tm[o] = keep
+            keeps.append(keep)
+        consumer = {}
+        produced_by = {}
+        for si, (a, b, o) in enumerate(pairs):
+            consumer[a] = si
+            consumer[b] = si
+            produced_by[o] = si
+        rank = {}
+        for t in terms.values():
+            for m in t:
+                rank.setdefault(m, len(rank))
+        tm = {i: terms[i] for i in range(n)}
+        steps = []
+        for si, (a, b, o) in enumerate(pairs):  # pass 2: layouts
+            ta, tb = tm[a], tm[b]
+            keep = keeps[si]
+            c = consumer.get(o)
+            if plan_layouts and c is not None and si != len(pairs) - 1:
+                survive = set(keeps[c])
+                other = pairs[c][1] if pairs[c][0] == o else pairs[c][0]
+                # the partner's mode SET is known from pass 1 even when it is produced later
+                shared = set(terms[other]) if other < n else set(keeps[produced_by[other]])
+                kmodes = sorted((m for m in keep if m not in survive and m in shared), key=lambda m: rank[m])
+                ks = set(kmodes)
+                keep = [m for m in keep if m not in ks] + kmodes
             tm[o] = keep
             steps.append((a, b, list(ta), list(tb), keep, o))
         return steps, tm

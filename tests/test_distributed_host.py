@@ -137,7 +137,27 @@ def test_schedule_chain_fusion_is_exact(built, monkeypatch, shape, target):
         assert abs(v0 - v1) <= 1e-7 * max(1.0, abs(v0))
 
 
-def test_schedule_fusion_halves_the_traffic_of_the_committed_plan(built):
+def test_schedule_fusion_halves_the_traffic_of_an_elimination_plan(built):
+    """Variable-elimination trees (the committed 6x6 depth-14 plan) are made of skinny absorptions: fusing
+    chains of them halves the bytes moved.  (The 7x7 depth-20 plan is a site-block sweep since round 2 — its
+    steps are GEMM shaped and have nothing to fuse.)"""
+    import pickle
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from tensorcircuit_ng_b200 import tnengine
+
+    td = pickle.load(open(bench.rcs_plan_path(6, 6, 14, 26), "rb"))
+    sl = sorted(td["sliced_inds"])
+    s0 = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sl, fuse=False)
+    s1 = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sl, fuse=True)
+    traffic = lambda st: sum(8.0 * (2 ** len(ta) + 2 ** len(tb) + 2 ** len(k)) for _, _, ta, tb, k, _ in st)  # noqa: E731
+    assert traffic(s1) < 0.7 * traffic(s0)
+
+
+def test_layout_planning_puts_the_contracted_modes_lowest(built):
+    """build_schedule orders every intermediate for its consumer: the modes the consuming step contracts are the
+    LAST of the producer's mode list (lowest address bits), in the same relative order in both operands."""
     import pickle
 
     sys.path.insert(0, ROOT)
@@ -145,12 +165,18 @@ def test_schedule_fusion_halves_the_traffic_of_the_committed_plan(built):
     from tensorcircuit_ng_b200 import tnengine
 
     td = pickle.load(open(bench.rcs_plan_path(7, 7, 20, 30), "rb"))
-    sl = sorted(td["sliced_inds"])
-    s0 = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sl, fuse=False)
-    s1 = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sl, fuse=True)
-    traffic = lambda st: sum(8.0 * (2 ** len(ta) + 2 ** len(tb) + 2 ** len(k)) for _, _, ta, tb, k, _ in st)  # noqa: E731
-    assert traffic(s1) < 0.6 * traffic(s0)
-
+    steps = tnengine.build_schedule(td["inputs"], td["output"], td["path"], sorted(td["sliced_inds"]))
+    nleaf = len(td["inputs"])
+    big = 0
+    for a, b, ta, tb, keep, o in steps:
+        if a < nleaf or b < nleaf:
+            continue  # leaves keep the layout they were given
+        ks = [m for m in ta if m in set(tb) and m not in set(keep)]
+        if not ks:
+            continue
+        assert ta[-len(ks):] == ks and tb[-len(ks):] == ks, (a, b)
+        big += len(ta) >= 20
+    assert big >= 20  # the boundary x site steps of the sweep
 
 def test_numpy_tree_executor_matches_oracle_statevector():
     """oracle/tc_oracle/treeexec.py (the CPU leg of the contraction bench): sliced pairwise execution of a
