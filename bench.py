@@ -491,6 +491,7 @@ def run_b200(args: argparse.Namespace) -> None:
                 except Exception as exc:  # pylint: disable=broad-except  (a sub-record must not lose the main line)
                     subs[name] = {"error": f"{type(exc).__name__}: {exc}"}
                 torch.cuda.empty_cache()
+                _lib.call("tcb_release_scratch")
             line["sub_records"] = subs
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -1363,6 +1364,7 @@ def run_sharded(args: argparse.Namespace) -> None:
             rec = {"error": f"{type(exc).__name__}: {exc}"}
         subs["contraction"] = rec
         torch.cuda.empty_cache()
+        _lib.call("tcb_release_scratch")  # the contraction kernels' cached operand-image scratch
         free = torch.cuda.mem_get_info(dev)[0]
         ok = torch.tensor([1 if free >= 150 * 2**30 else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)

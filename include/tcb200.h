@@ -40,6 +40,10 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 int tcb_abi_version(void);
 const char* tcb_last_error(void);
+/* The tensor-core contraction path keeps its operand-image scratch (stream-ordered allocations from the device's
+ * default memory pool) cached between calls; this hands it back to the driver (e.g. before a 64 GiB state is
+ * allocated on the same device). */
+int tcb_release_scratch(void);
 /* number of SMs / total global memory of the current device */
 int tcb_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
 

@@ -57,6 +57,7 @@ class ContractDesc(Structure):
 SYMBOLS = {
     "tcb_abi_version": (c_int, []),
     "tcb_last_error": (c_char_p, []),
+    "tcb_release_scratch": (c_int, []),
     "tcb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_uint64)]),
     "tcb_sv_init_zero": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     "tcb_sv_init_product": (c_int, [c_void_p, c_int, c_void_p, c_int, c_uint64, c_void_p]),

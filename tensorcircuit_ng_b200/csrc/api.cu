@@ -66,6 +66,15 @@ extern "C" {
 
 int tcb_abi_version(void) { return TCB_ABI_VERSION; }
 const char* tcb_last_error(void) { return g_err; }
+int tcb_release_scratch(void) {
+  int dev = 0;
+  cudaMemPool_t pool;
+  TCB_CHECK_CUDA(cudaGetDevice(&dev));
+  TCB_CHECK_CUDA(cudaDeviceSynchronize());
+  TCB_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  TCB_CHECK_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return 0;
+}
 
 int tcb_device_info(int* sm, int* cc_major, int* cc_minor, uint64_t* total_mem) {
   int dev = 0;

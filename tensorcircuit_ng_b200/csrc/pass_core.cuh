@@ -59,6 +59,11 @@ static inline float4 make_float4(float a, float b, float c, float d) {
 }
 #endif
 
+#ifndef TCB_SUBPROF
+#define TCB_SUBPROF(slot)  // (PASS_PROFILE build of pass_kernel.cu: cycle stamps inside a register sub-pass)
+#define TCB_SUBPROF_DECL
+#endif
+
 namespace tcb {
 
 // ---- program layout (int32 words) -------------------------------------------
@@ -512,6 +517,7 @@ TCB_DEV void round_bit_simple(float2 (&a)[1 << R], const int32_t* rd, int flags,
 template <int R>
 TCB_DEV void run_reg_subpass(float2* tile, const int32_t* sp, int tbase, uint64_t cta_bits) {
   static_assert(R >= 2 && R <= 5, "register bits");
+  TCB_SUBPROF_DECL
   // shared-memory address of amplitude i:  tbase and the register offsets have disjoint bits and
   // the swizzle is GF(2)-linear, so  swz(tbase | off_i) = swz(tbase) ^ XOR_j swz(1 << r_j).
   // Slot 0 is tile bit 0 (never swizzled): amplitudes 2p and 2p+1 are one 16-byte chunk.
@@ -532,6 +538,7 @@ TCB_DEV void run_reg_subpass(float2* tile, const int32_t* sp, int tbase, uint64_
     a[i + 1] = make_float2(v.z, v.w);
   }
 
+  TCB_SUBPROF(8);
   const int nrounds = sp[S_NROUNDS];
   const int32_t* rd = sp + SUB_HDR_WORDS;
   TCB_NOUNROLL
@@ -567,6 +574,7 @@ TCB_DEV void run_reg_subpass(float2* tile, const int32_t* sp, int tbase, uint64_
     round_bit<R, 4>(a, rd, flags, tbase, cta_bits, tt);
     rd += rd[RD_WORDS];
   }
+  TCB_SUBPROF(9);
 
   TCB_UNROLL
   for (int i = 0; i < (1 << R); i += 2) {
@@ -576,6 +584,7 @@ TCB_DEV void run_reg_subpass(float2* tile, const int32_t* sp, int tbase, uint64_
       if ((i >> j) & 1) ad ^= rsw[j];
     *reinterpret_cast<float4*>(tile + ad) = make_float4(a[i].x, a[i].y, a[i + 1].x, a[i + 1].y);
   }
+  TCB_SUBPROF(10);
 }
 
 // ---- shared-memory dense sub-pass (k = 1..4 qubits, all inside the tile) ------------

@@ -18,13 +18,27 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#ifdef PASS_PROFILE
+// sub-phase stamps of warp 0 (LDS phase / rounds / STS phase of every register sub-pass), see tools/phase_prof.py
+namespace tcb {
+__device__ unsigned long long g_pass_prof[16];
+}
+#define TCB_SUBPROF_DECL unsigned long long _st = clock64();
+#define TCB_SUBPROF(slot)                                                        \
+  do {                                                                           \
+    if (threadIdx.x == 0) {                                                      \
+      const unsigned long long _n = clock64();                                   \
+      atomicAdd(&::tcb::g_pass_prof[slot], _n - _st);                            \
+      _st = _n;                                                                  \
+    }                                                                            \
+  } while (0)
+#endif
 #include "pass_core.cuh"
 #include "../../include/tcb200.h"
 
 namespace tcb {
 
 #ifdef PASS_PROFILE
-__device__ unsigned long long g_pass_prof[16];
 // timeline of the CTAs resident on SM 0: [cta slot][tile][phase stamp] (globaltimer ns)
 __device__ unsigned long long g_trace[8][64][6];
 __device__ int g_trace_slots;
@@ -254,7 +268,13 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
       } else {
         run_smem_dense(tile, hdr, sp, gates, tid, NT);
       }
+#ifdef PASS_PROFILE
+      const unsigned long long _bt = clock64();
+#endif
       __syncthreads();
+#ifdef PASS_PROFILE
+      if (threadIdx.x == 0) atomicAdd(&g_pass_prof[11], clock64() - _bt);
+#endif
       sp += sp[S_WORDS];
     }
     PROF_MARK(4);

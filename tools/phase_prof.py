@@ -38,3 +38,4 @@ for case, gates in cases.items():
     ntiles = 2 ** (n - 12)
     tot = sum(out[i] for i in range(7))
     print(f"{case}: {e0.elapsed_time(e1):.3f} ms; cycles per tile: " + ", ".join(f"{names[i]} {out[i]/ntiles:.0f}" for i in range(7)) + f"  total {tot/ntiles:.0f}")
+    print(f"    inside the register sub-passes (warp 0, cycles per tile): LDS phase {out[8]/ntiles:.0f}, rounds {out[9]/ntiles:.0f}, STS phase {out[10]/ntiles:.0f}, barrier wait {out[11]/ntiles:.0f}")
