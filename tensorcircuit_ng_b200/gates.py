@@ -557,7 +557,7 @@ def memoised_gate(gatef: Callable[..., Gate], kws: Dict[str, Any]) -> Gate:
         if pk is None:
             return gatef(**kws)
         parts.append((k, pk))
-    key = (getattr(gatef, "__name__", id(gatef)), tuple(parts), torch.is_grad_enabled())
+    key = (getattr(gatef, "__name__", id(gatef)), tuple(parts), torch.is_grad_enabled(), str(_device()))
     hit = _gate_memo.get(key)
     if hit is None:
         g = gatef(**kws)
