@@ -21,6 +21,7 @@ decided Belady-style (farthest next dense use).
 
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -166,9 +167,12 @@ class CudaExecutor:
 
     def pack(self, state: Any, buf: Any, nl: int, sel: Sequence[int], pattern: int, first: int, count: int,
              unpack: bool) -> None:  # fmt: skip
+        """`buf`: a tensor, or a raw device address (a peer GPU's staging buffer mapped into this process:
+        the pack kernel then writes straight over NVLink)."""
         from . import _lib
 
-        _lib.call("tcb_sv_unpack_bits" if unpack else "tcb_sv_pack_bits", state.data_ptr(), buf.data_ptr(), nl,
+        ptr = buf if isinstance(buf, int) else buf.data_ptr()
+        _lib.call("tcb_sv_unpack_bits" if unpack else "tcb_sv_pack_bits", state.data_ptr(), ptr, nl,
                   len(sel), _lib.int_array(sel), pattern, first, count, _lib.stream_ptr())  # fmt: skip
 
     def expect_z(self, state: Any, nl: int, masks: Sequence[int], index_base: int) -> Any:
@@ -226,6 +230,38 @@ class TorchDistComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def peer_staging(self, nbytes: int, device: Any) -> Any:
+        """A staging buffer of `nbytes` on every rank that all ranks can write directly (NVLink peer stores):
+        torch symmetric memory (CUDA VMM allocations exchanged between the local processes).  Returns
+        (local uint8 tensor, [device address of the buffer of rank r], barrier) or None when the ranks cannot
+        map each other's memory (no NVLink / P2P, CPU test tier, TCB_SWAP_P2P=0); `barrier(channel)` is a
+        device-side barrier of all ranks on the current stream."""
+        import os
+
+        import torch
+
+        if os.environ.get("TCB_SWAP_P2P", "1") == "0" or getattr(device, "type", "cpu") != "cuda":
+            return None
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            group = self.group if self.group is not None else self.dist.group.WORLD
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+            hdl = symm.rendezvous(buf, group=group.group_name)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+        except Exception as exc:  # pylint: disable=broad-except
+            import sys
+
+            print(f"[tensorcircuit_ng_b200.sharded] peer staging unavailable ({type(exc).__name__}: {exc}); "
+                  "qubit swaps go through NCCL send/recv", file=sys.stderr)  # fmt: skip
+            ok = 0
+        flag = torch.tensor([ok], device=device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        if not int(flag[0]):
+            return None
+        return buf, ptrs, (lambda channel=0: hdl.barrier(channel=channel))
+
 
 class ShardedStatevector:
     """One rank's shard of an n-qubit state + the collective operations on it."""
@@ -249,6 +285,8 @@ class ShardedStatevector:
         self.pos_of = [nqubits - 1 - q for q in range(nqubits)]
         self.chunk = max(2, min(chunk_elems, 1 << self.nl))
         self._bufs: Optional[Tuple[Any, Any]] = None
+        self._peer: Any = None  # peer-memory staging (buffer, addresses per rank, barrier); False = unavailable
+        self._side: Any = None  # side stream of the peer-memory exchange (unpacking)
         self._cache: Dict[Any, Any] = {}
         self.bytes_sent = 0
         self.swaps_done = 0
@@ -290,6 +328,8 @@ class ShardedStatevector:
         block = 1 << (self.nl - m)
         chunk = min(self.chunk, block)
         nb = chunk * ((1 << m) - 1)
+        if self._peer_swap(pairs, sel, jbits, mine, block, chunk, nb):
+            return
         if self._bufs is None or self._bufs[0].numel() < nb:
             # two send + two receive staging buffers: chunk c+1 is packed while chunk c is on the wire
             self._bufs = tuple(self.ex.empty(nb) for _ in range(4))
@@ -335,11 +375,78 @@ class ShardedStatevector:
             pending = (ci, first, cnt, works)
         if pending is not None:
             finish(*pending)
+        self._finish_swap(pairs)
+
+    def _finish_swap(self, pairs: Sequence[Tuple[int, int]]) -> None:
         inv = {p: q for q, p in enumerate(self.pos_of)}
         for P, p in pairs:
             qa, qb = inv[P], inv[p]
             self.pos_of[qa], self.pos_of[qb] = p, P
         self.swaps_done += 1
+
+    def _peer_swap(self, pairs: Sequence[Tuple[int, int]], sel: List[int], jbits: List[int], mine: int, block: int,
+                   chunk: int, nb: int) -> bool:  # fmt: skip
+        """The exchange over peer memory: the pack kernel of every outgoing sub-block writes straight into the
+        receiver's staging buffer (one local read + NVLink stores, no send buffer and no copy engine), a
+        device-side barrier, then the receiver unpacks.  Two staging halves alternate, so the barrier of chunk
+        c + 1 also tells that every rank is done unpacking chunk c - 1.  False: not available (NCCL path)."""
+        if self._peer is None and hasattr(self.comm, "peer_staging"):
+            self._peer = self.comm.peer_staging(2 * 8 * self._peer_elems(), getattr(self.state, "device", None)) or False
+        if not self._peer or nb > self._peer_elems():
+            return False
+        buf, ptrs, barrier = self._peer
+        import torch
+
+        local = buf.view(torch.complex64)
+        half = self._peer_elems()
+        m = len(sel)
+        peers = []
+        for x in range(1 << m):
+            if x == mine:
+                continue
+            peer = self.rank
+            for k, j in enumerate(jbits):
+                peer = (peer & ~(1 << j)) | (((x >> k) & 1) << j)
+            peers.append((x, peer))
+        # unpacking runs on a side stream, so that it overlaps the next chunk's pushes (the wire never waits):
+        #   main : push(c) .. [wait: own unpack(c - 1) done] barrier(c) .. push(c + 1) ..
+        #   side : [wait: barrier(c)] unpack(c)
+        # passing barrier(c) therefore means that every rank has unpacked chunk c - 1, whose staging half the
+        # pushes of chunk c + 1 overwrite.
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        prev_unpacked = None
+        for ci, first in enumerate(range(0, block, chunk)):
+            cnt = min(chunk, block - first)
+            par = ci & 1
+            for x, peer in peers:
+                # my slot in the receiver's buffer: its senders are ordered by pattern, its own pattern (x) left out
+                slot = mine - (1 if x < mine else 0)
+                dst = ptrs[peer] + 8 * (par * half + slot * chunk)
+                self.ex.pack(self.state, dst, self.nl, sel, x, first, cnt, False)
+            if prev_unpacked is not None:
+                main.wait_event(prev_unpacked)
+            barrier(par)
+            arrived = torch.cuda.Event()
+            arrived.record(main)
+            side.wait_event(arrived)
+            with torch.cuda.stream(side):
+                for i, (x, peer) in enumerate(peers):
+                    src = local[par * half + i * chunk : par * half + i * chunk + cnt]
+                    self.ex.pack(self.state, src, self.nl, sel, x, first, cnt, True)
+                prev_unpacked = torch.cuda.Event()
+                prev_unpacked.record(side)
+            self.bytes_sent += 8 * cnt * len(peers)
+        main.wait_stream(side)
+        barrier(2)  # (the staging halves may be reused by the next swap)
+        self._finish_swap(pairs)
+        return True
+
+    def _peer_elems(self) -> int:
+        """Complex elements of one staging half: a chunk from each of the (world - 1) possible senders."""
+        return self.chunk * max(1, self.comm.world - 1)
 
     # -- read-out ----------------------------------------------------------------------------
     def _mask(self, qubits: Sequence[int]) -> int:
@@ -413,9 +520,11 @@ def evolve(circuit: Any, comm: Any = None, executor: Any = None, chunk_elems: in
     if init is not None:
         raise NotImplementedError("sharded evolution starts from |0...0>")
     if executor is None:
-        dev = svengine.pick_device([g[0].tensor for g in gates])
-        executor = CudaExecutor(dev)
-    structure = tuple((g[1], k, int(g[0].tensor.numel())) for g, k in zip(gates, svengine.gate_kinds(gates)))
+        # (deferred gates are looked at through their parameter: building 600 matrices one by one would cost
+        # more host time than the evolution itself)
+        probe = [g[0]._lazy.theta if hasattr(g[0], "pending") and g[0].pending() else g[0].tensor for g in gates]
+        executor = CudaExecutor(svengine.pick_device(probe))
+    structure = tuple((g[1], k, int(math.prod(g[0].shape))) for g, k in zip(gates, svengine.gate_kinds(gates)))
     key = (n, comm.world, structure)
     hit = _plan_cache.get(key)
     if hit is None:
@@ -430,11 +539,10 @@ def evolve(circuit: Any, comm: Any = None, executor: Any = None, chunk_elems: in
             _plan_cache.clear()
         _plan_cache[key] = hit = (plan, ops, prefix)
     plan, ops, prefix = hit
-    tensors = [g[0].tensor for g in gates]
     if isinstance(executor, CudaExecutor):
-        gatebuf = svengine.build_gatebuf(tensors, executor.device)
+        gatebuf = svengine.assemble_gatebuf([g[0] for g in gates], executor.device)  # one batched build per gate family
     else:
-        gatebuf = torch.cat([t.reshape(-1).to(torch.complex64) for t in tensors])
+        gatebuf = torch.cat([g[0].tensor.reshape(-1).to(torch.complex64) for g in gates])
     vecs = product_vectors(prefix, gatebuf, n) if any(prefix) else None
     if reuse is not None and reuse.n == n:
         sv = reuse
