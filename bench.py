@@ -1118,6 +1118,7 @@ def random_record(args: argparse.Namespace, tc: Any, sharded: Any, comm: Any, ex
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
     achieved = alg_bytes / (run_ms / max(1, n_launch) * 1e-3) / 1e9
+    swap_path = "peer memory (symmetric-memory staging, NVLink stores)" if getattr(sv, "_peer", None) else "NCCL send/recv"
     del sv
     torch.cuda.empty_cache()
     if rank != 0:
@@ -1132,7 +1133,8 @@ def random_record(args: argparse.Namespace, tc: Any, sharded: Any, comm: Any, ex
                    "amplitude_updates_per_s": n_gates * 2.0**n / (ms_per_step * 1e-3),
                    "nvlink_bytes_sent_per_gpu_per_step": sent,
                    "nvlink_gbs_per_gpu": sent / (swap_ms * 1e-3) / 1e9 if swap_ms > 0 else None,
-                   "nvlink_peak_gbs": 900.0, "swap_ms_per_step": swap_ms, "local_ms_per_step": run_ms,
+                   "nvlink_peak_gbs": 900.0, "swap_path": swap_path, "swap_ms_per_step": swap_ms,
+                   "local_ms_per_step": run_ms,
                    "norm": norm, "z0_zlast": float(zz[0])},
         "roofline": {"kernel": "tcb::pass_kernel (fused tile pass), per GPU", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -1312,7 +1314,9 @@ def run_sharded(args: argparse.Namespace) -> None:
                 "global_qubits": g,
                 "state_bytes_per_gpu": 8 * 2**nl,
                 "l2": "inputs larger than L2",
-                "multi_gpu": "statevector sharded over the ranks, global<->local qubit swaps over NCCL P2P",
+                "multi_gpu": "statevector sharded over the ranks, global<->local qubit swaps over "
+                             + ("peer memory (pack kernels store into the receiver's symmetric-memory staging buffer)"
+                                if getattr(sv, "_peer", None) else "NCCL send/recv"),
                 "hbm_passes": n_pass,
                 "swaps": plan.n_swaps,
                 "swapped_qubits": plan.swapped_qubits,

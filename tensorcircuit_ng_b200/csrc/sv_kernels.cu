@@ -1342,6 +1342,181 @@ cross_rdm_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi,
   }
 }
 
+// Register / shuffle form (states of >= 2^(3 + nsel + 1) amplitudes): a thread holds the 8 amplitudes of the three
+// lowest address bits of BOTH states in registers (64 contiguous bytes each: 8 independent 16-byte loads in flight),
+// thread-index bit j < nsel stands for the selected bit sel[j] and the higher thread-index bits pick one of the
+// 2^(8 - nsel) units a CTA works on at a time.  Per bit the partial traces need
+//   low bits      : both partners are registers of the same thread;
+//   lane bits     : the partner's psi comes through 16 shuffles, the thread with bit = 0 accumulates
+//                   lam[x] conj(psi[x | t]) (-> C[0][1]), its partner lam[x | t] conj(psi[x]) (-> C[1][0]);
+//   warp bits     : the same through one shared-memory exchange of psi per iteration;
+//   C[0][0]       : needs no partner — the thread's running sum of lam conj(psi), counted at the end by the
+//                   threads whose bit is 0 (C[1][1] = total - C[0][0]).
+// No tile in shared memory and 2 instead of ~20 shared-memory bytes per byte of HBM traffic: the tile form above
+// ran at 1.06 TB/s, bound by its shared-memory reads.
+__global__ void __launch_bounds__(256, 2)
+cross_rdm_reg_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi, int nbits, CrBits cb, int t_begin,
+                     double* out, long long out_bstride) {
+  lam += (size_t)blockIdx.y << nbits;
+  psi += (size_t)blockIdx.y << nbits;
+  out += (size_t)blockIdx.y * out_bstride;
+  __shared__ __align__(16) float4 xch[256 * 4];        // psi of every thread (warp-bit partners)
+  __shared__ double sacc[CR_MAXB * 3 * 2 + 2];
+  const int tid = threadIdx.x;
+  const int nsel = cb.nsel;
+  for (int e = tid; e < CR_MAXB * 6 + 2; e += blockDim.x) sacc[e] = 0.0;
+  uint64_t toff = 0;
+  for (int j = 0; j < nsel; ++j) toff |= (uint64_t)((tid >> j) & 1) << cb.sel[j];
+  const unsigned unit_in_cta = (unsigned)tid >> nsel, units_per_cta = 256u >> nsel;
+  const uint64_t nunits = 1ull << (nbits - 3 - nsel);
+  const uint64_t niter = (nunits + (uint64_t)units_per_cta * gridDim.x - 1) / ((uint64_t)units_per_cta * gridDim.x);
+  const bool do_low = t_begin == 0;
+
+  float2 s = make_float2(0.f, 0.f);       // sum of lam conj(psi)
+  float2 lo[3][3];                         // low bit t: [0][0], [0][1], [1][0]
+  float2 hi[7];                            // selected bit j: lam_own conj(psi_partner)
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) lo[t][c] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 7; ++j) hi[j] = make_float2(0.f, 0.f);
+
+  auto cmac = [](float2& acc, float2 l, float2 q) {  // acc += l conj(q)
+    acc.x = fmaf(l.x, q.x, fmaf(l.y, q.y, acc.x));
+    acc.y = fmaf(l.y, q.x, fmaf(-l.x, q.y, acc.y));
+  };
+  auto warp_add = [&](float re, float im, int slot) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      re += __shfl_xor_sync(0xffffffffu, re, o);
+      im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&sacc[2 * slot], (double)re);
+      atomicAdd(&sacc[2 * slot + 1], (double)im);
+    }
+  };
+  auto flush = [&]() {
+    if (do_low) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) warp_add(lo[t][c].x, lo[t][c].y, t * 3 + c);
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      if (j < nsel) {  // (uniform)
+        const bool one = (tid >> j) & 1;
+        warp_add(one ? 0.f : s.x, one ? 0.f : s.y, (3 + j) * 3 + 0);
+        warp_add(one ? 0.f : hi[j].x, one ? 0.f : hi[j].y, (3 + j) * 3 + 1);
+        warp_add(one ? hi[j].x : 0.f, one ? hi[j].y : 0.f, (3 + j) * 3 + 2);
+      }
+      hi[j] = make_float2(0.f, 0.f);
+    }
+    warp_add(s.x, s.y, CR_MAXB * 3);
+    s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) lo[t][c] = make_float2(0.f, 0.f);
+  };
+
+  __syncthreads();
+  int since_flush = 0;
+  // software pipeline: the loads of iteration it + 1 are in flight while iteration it is computed (a CTA's
+  // threads move in lockstep through the shared-memory exchange, so nothing else hides the DRAM latency)
+  float4 rl[4], rq[4];
+  auto issue = [&](uint64_t it) -> bool {
+    const uint64_t unit = (it * gridDim.x + blockIdx.x) * units_per_cta + unit_in_cta;
+    const bool live = it < niter && unit < nunits;  // (a CTA's last iteration may have idle units; they still join the barriers)
+    if (live) {
+      uint64_t base = unit << 3;
+      for (int j = 0; j < nsel; ++j) base = insert_zero(base, cb.sel[j]);  // sel ascending
+      const float4* pl = reinterpret_cast<const float4*>(lam + (base | toff));
+      const float4* pq = reinterpret_cast<const float4*>(psi + (base | toff));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        rl[k] = ldg_stream(pl + k);
+        rq[k] = ldg_stream(pq + k);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rl[k] = rq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return live;
+  };
+  issue(0);
+  for (uint64_t it = 0; it < niter; ++it) {
+    float2 l[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      l[2 * k] = make_float2(rl[k].x, rl[k].y);
+      l[2 * k + 1] = make_float2(rl[k].z, rl[k].w);
+      q[2 * k] = make_float2(rq[k].x, rq[k].y);
+      q[2 * k + 1] = make_float2(rq[k].z, rq[k].w);
+    }
+    issue(it + 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cmac(s, l[i], q[i]);
+    if (do_low) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (!((i >> t) & 1)) {
+            cmac(lo[t][0], l[i], q[i]);
+            cmac(lo[t][1], l[i], q[i | (1 << t)]);
+            cmac(lo[t][2], l[i | (1 << t)], q[i]);
+          }
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (j < nsel) {  // lane bits (uniform branch)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float2 pq2;
+          pq2.x = __shfl_xor_sync(0xffffffffu, q[i].x, 1 << j);
+          pq2.y = __shfl_xor_sync(0xffffffffu, q[i].y, 1 << j);
+          cmac(hi[j], l[i], pq2);
+        }
+      }
+    }
+    if (nsel > 5) {  // warp bits: psi goes through shared memory once
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xch[k * 256 + tid] = make_float4(q[2 * k].x, q[2 * k].y, q[2 * k + 1].x, q[2 * k + 1].y);
+      __syncthreads();
+#pragma unroll
+      for (int j = 5; j < 7; ++j) {
+        if (j < nsel) {
+          const int partner = tid ^ (1 << j);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 w = xch[k * 256 + partner];
+            cmac(hi[j], l[2 * k], make_float2(w.x, w.y));
+            cmac(hi[j], l[2 * k + 1], make_float2(w.z, w.w));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (++since_flush == 64) {
+      flush();
+      since_flush = 0;
+    }
+  }
+  flush();
+  __syncthreads();
+  // out[t][r][c]: [0][0], [0][1], [1][0] as accumulated, [1][1] = total - [0][0]
+  const int tb = 3 + nsel;
+  for (int e = tid; e < tb * 8; e += blockDim.x) {
+    const int t = e >> 3, c = (e >> 1) & 3, ri = e & 1;
+    if (t < t_begin) continue;
+    const double v = c < 3 ? sacc[(t * 3 + c) * 2 + ri] : sacc[CR_MAXB * 6 + ri] - sacc[(t * 3) * 2 + ri];
+    atomicAdd(out + e, v);
+  }
+}
+
 int launch_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch, int nsel, const int* sel_bits,
                      int skip_low, double* out, int64_t out_bstride, cudaStream_t stream) {
   TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_cross_rdm: nbits=%d", nbits);
@@ -1355,6 +1530,19 @@ int launch_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch,
     cb.sel[j] = sel_bits[j];
     TCB_REQUIRE(sel_bits[j] >= cb.nlow && sel_bits[j] < nbits && (j == 0 || sel_bits[j] > sel_bits[j - 1]),
                 "tcb_sv_cross_rdm: selected bits must be ascending, >= %d and < nbits (bit %d)", cb.nlow, sel_bits[j]);
+  }
+  if (cb.nlow == 3 && nbits >= 3 + nsel + 1) {
+    const uint64_t nunits = 1ull << (nbits - 3 - nsel);
+    const uint64_t per_cta = 256u >> nsel;
+    uint64_t grid = (nunits + per_cta - 1) / per_cta;
+    uint64_t cap = (uint64_t)sm_count() * 2;
+    if (batch > 1 && cap > (uint64_t)sm_count()) cap = batch >= 4 ? (uint64_t)sm_count() / 2 : sm_count();  // (batch rows share the SMs)
+    if (grid > cap) grid = cap;
+    dim3 g2((unsigned)grid, (unsigned)batch);
+    cross_rdm_reg_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const float2*>(lam), reinterpret_cast<const float2*>(psi),
+                                                 nbits, cb, skip_low ? 3 : 0, out, 2 * out_bstride);
+    TCB_CHECK_CUDA(cudaGetLastError());
+    return 0;
   }
   const uint64_t ntiles = 1ull << (nbits - cb.nlow - nsel);
   uint64_t grid = (uint64_t)sm_count() * 4;

@@ -391,7 +391,11 @@ class ShardedStatevector:
         device-side barrier, then the receiver unpacks.  Two staging halves alternate, so the barrier of chunk
         c + 1 also tells that every rank is done unpacking chunk c - 1.  False: not available (NCCL path)."""
         if self._peer is None and hasattr(self.comm, "peer_staging"):
-            self._peer = self.comm.peer_staging(2 * 8 * self._peer_elems(), getattr(self.state, "device", None)) or False
+            # one staging buffer per process and size (every rank asks in the same order: the rendezvous is collective)
+            key = (self.comm.world, 2 * 8 * self._peer_elems())
+            if key not in _peer_staging_cache:
+                _peer_staging_cache[key] = self.comm.peer_staging(key[1], getattr(self.state, "device", None)) or False
+            self._peer = _peer_staging_cache[key]
         if not self._peer or nb > self._peer_elems():
             return False
         buf, ptrs, barrier = self._peer
@@ -421,7 +425,10 @@ class ShardedStatevector:
         for ci, first in enumerate(range(0, block, chunk)):
             cnt = min(chunk, block - first)
             par = ci & 1
-            for x, peer in peers:
+            # destinations in the order x = mine ^ d, d = 1, 2, ..: at every d the ranks pair up (a perfect
+            # matching), so no receiver takes two senders at once (in pattern order every rank starts on the
+            # same receiver and the exchange runs at 1 / (#peers) of the link rate)
+            for x, peer in sorted(peers, key=lambda xp: xp[0] ^ mine):
                 # my slot in the receiver's buffer: its senders are ordered by pattern, its own pattern (x) left out
                 slot = mine - (1 if x < mine else 0)
                 dst = ptrs[peer] + 8 * (par * half + slot * chunk)
@@ -487,6 +494,7 @@ class ShardedStatevector:
 
 # ---------------------------------------------------------------------------------------------
 _plan_cache: Dict[Any, Any] = {}
+_peer_staging_cache: Dict[Any, Any] = {}
 
 
 def product_vectors(prefix: Sequence[Sequence[GateOp]], gatebuf: Any, n: int) -> Any:
