@@ -3,6 +3,8 @@
 // expectations (tensorcircuit/circuit.py:899-902 without a materialised bra), the
 // adjoint-mode gate-gradient reduction and the pack/unpack halves of a qubit swap.
 // All are HBM-bound streaming kernels: 128-bit accesses, grid = multiple of the SM count.
+#include <vector>
+
 #include "common.cuh"
 #include "pass_core.cuh"  // cmul / cfma
 
@@ -1052,33 +1054,33 @@ int launch_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
 // for every gate j of the run (unit-modulus d): the only state-sized work is the marginal of the
 // elementwise product over the gate's one or two bits.  Up to CM_G gates per launch (moment sums,
 // predicated adds; two-level float accumulation, double across threads).
-constexpr int CM_G = 8;
+// A gate's four bins are combinations of the +-1 MOMENTS  M_S = sum_i (-1)^popc(i & S) q_i,  q = lam conj(psi),
+// over S in {0, a, b, ab}: the launcher collects the DISTINCT masks of the whole run (a TFIM layer of 23 rzz and
+// 24 rz gates has 47 of them, not 141: every single-bit moment is shared by three gates), CM_M masks per read.
+constexpr int CM_M = 24;
 
-struct CmGates {
-  int a[CM_G], b[CM_G];  // bit of matrix-index MSB / LSB; a = -1 for a one-qubit gate (its bit is the LSB)
+struct CmMasks {
+  unsigned long long m[CM_M];
 };
 
 __device__ __forceinline__ float2 cm_flip(float2 v, unsigned sign_bit) {  // sign_bit: 0 or 0x80000000
   return make_float2(__uint_as_float(__float_as_uint(v.x) ^ sign_bit), __uint_as_float(__float_as_uint(v.y) ^ sign_bit));
 }
 
-// Accumulates the +-1 MOMENTS of q = lam * conj(psi) per gate (M_a, M_b, M_ab; M_0 = sum q is shared) instead of
-// the four bins: a sign flip and three complex adds per gate per PAIR of amplitudes (the two amplitudes of a
-// 16-byte load share every sign except bit 0's), and the launcher's epilogue kernel turns moments into bins.
+// mom[0] += M_0 (first launch of a series only), mom[1 + first + j] += M_{g.m[j]}.  A sign flip and one complex
+// add per mask per PAIR of amplitudes (the two amplitudes of a 16-byte load share every sign except bit 0's).
 __global__ void __launch_bounds__(256, 2)
-cross_marginals_kernel(const float4* __restrict__ lam, const float4* __restrict__ psi, uint64_t nvec, CmGates g,
-                       int ngates, double* mom, long long mom_bstride) {
+cross_moments_kernel(const float4* __restrict__ lam, const float4* __restrict__ psi, uint64_t nvec, CmMasks g,
+                     int nmasks, int write_m0, double* mom, long long mom_bstride) {
   lam += (size_t)blockIdx.y * nvec;
   psi += (size_t)blockIdx.y * nvec;
   mom += (size_t)blockIdx.y * mom_bstride;
   // first-level sums in registers, second level per thread in shared memory ([slot][thread], conflict-free)
   extern __shared__ float cm_acc2[];
-  float2 acc[CM_G][3], m0 = make_float2(0.f, 0.f);
+  float2 acc[CM_M], m0 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < CM_G; ++j)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) acc[j][c] = make_float2(0.f, 0.f);
-  for (int e = 0; e < CM_G * 6 + 2; ++e) cm_acc2[e * 256 + threadIdx.x] = 0.f;
+  for (int j = 0; j < CM_M; ++j) acc[j] = make_float2(0.f, 0.f);
+  for (int e = 0; e < CM_M * 2 + 2; ++e) cm_acc2[e * 256 + threadIdx.x] = 0.f;
   int cnt = 0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 2;
   for (uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; p0 < nvec; p0 += stride) {
@@ -1097,70 +1099,68 @@ cross_marginals_kernel(const float4* __restrict__ lam, const float4* __restrict_
       const float2 qs = make_float2(q0.x + q1.x, q0.y + q1.y), qd = make_float2(q0.x - q1.x, q0.y - q1.y);
       m0.x += qs.x;
       m0.y += qs.y;
-      const uint64_t i0 = (p0 + k) << 1;
+      const uint64_t i0 = (p0 + k) << 1;  // (bit 0 clear)
 #pragma unroll
-      for (int j = 0; j < CM_G; ++j) {
-        const int a = g.a[j], b = g.b[j];
-        const unsigned sa = a > 0 ? (unsigned)((i0 >> a) & 1ull) << 31 : 0u;
-        const unsigned sb = b > 0 ? (unsigned)((i0 >> b) & 1ull) << 31 : 0u;
-        const float2 ua = a == 0 ? qd : cm_flip(qs, sa);
-        const float2 ub = b == 0 ? qd : cm_flip(qs, sb);
-        const float2 uab = (a == 0 || b == 0) ? cm_flip(qd, sa ^ sb) : cm_flip(qs, sa ^ sb);
-        acc[j][0].x += ua.x;  acc[j][0].y += ua.y;
-        acc[j][1].x += ub.x;  acc[j][1].y += ub.y;
-        acc[j][2].x += uab.x; acc[j][2].y += uab.y;
+      for (int j = 0; j < CM_M; ++j) {
+        const unsigned long long m = g.m[j];
+        const unsigned sg = (unsigned)(__popcll(i0 & m) & 1) << 31;
+        const float2 u = cm_flip((m & 1ull) ? qd : qs, sg);
+        acc[j].x += u.x;
+        acc[j].y += u.y;
       }
     }
     if ((++cnt & 15) == 0) {
-      cm_acc2[(CM_G * 6) * 256 + threadIdx.x] += m0.x;
-      cm_acc2[(CM_G * 6 + 1) * 256 + threadIdx.x] += m0.y;
+      cm_acc2[(CM_M * 2) * 256 + threadIdx.x] += m0.x;
+      cm_acc2[(CM_M * 2 + 1) * 256 + threadIdx.x] += m0.y;
       m0 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < CM_G; ++j)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          cm_acc2[((j * 3 + c) * 2) * 256 + threadIdx.x] += acc[j][c].x;
-          cm_acc2[((j * 3 + c) * 2 + 1) * 256 + threadIdx.x] += acc[j][c].y;
-          acc[j][c] = make_float2(0.f, 0.f);
-        }
+      for (int j = 0; j < CM_M; ++j) {
+        cm_acc2[(j * 2) * 256 + threadIdx.x] += acc[j].x;
+        cm_acc2[(j * 2 + 1) * 256 + threadIdx.x] += acc[j].y;
+        acc[j] = make_float2(0.f, 0.f);
+      }
     }
   }
-  const float2 m02 = make_float2(cm_acc2[(CM_G * 6) * 256 + threadIdx.x], cm_acc2[(CM_G * 6 + 1) * 256 + threadIdx.x]);
-  // moments of gate j at mom[4 j + {0: M_0, 1: M_b, 2: M_a, 3: M_ab}] (index = (sa << 1) | sb)
-  __shared__ double s0[2];
-  if (threadIdx.x == 0) s0[0] = s0[1] = 0.0;
-  __syncthreads();
-  block_reduce_add2((double)m02.x + (double)m0.x, (double)m02.y + (double)m0.y, s0);
-  __syncthreads();
+  if (write_m0) {
+    block_reduce_add2((double)cm_acc2[(CM_M * 2) * 256 + threadIdx.x] + (double)m0.x,
+                      (double)cm_acc2[(CM_M * 2 + 1) * 256 + threadIdx.x] + (double)m0.y, mom);
+    __syncthreads();
+  }
 #pragma unroll
-  for (int j = 0; j < CM_G; ++j) {
-    if (j < ngates) {  // (uniform)
-      if (threadIdx.x == 0) {
-        atomicAdd(mom + 2 * (4 * j), s0[0]);
-        atomicAdd(mom + 2 * (4 * j) + 1, s0[1]);
-      }
-      const int slot[3] = {2, 1, 3};
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        block_reduce_add2((double)cm_acc2[((j * 3 + c) * 2) * 256 + threadIdx.x] + (double)acc[j][c].x,
-                          (double)cm_acc2[((j * 3 + c) * 2 + 1) * 256 + threadIdx.x] + (double)acc[j][c].y,
-                          mom + 2 * (4 * j + slot[c]));
-        __syncthreads();
-      }
+  for (int j = 0; j < CM_M; ++j) {
+    if (j < nmasks) {  // (uniform)
+      block_reduce_add2((double)cm_acc2[(j * 2) * 256 + threadIdx.x] + (double)acc[j].x,
+                        (double)cm_acc2[(j * 2 + 1) * 256 + threadIdx.x] + (double)acc[j].y, mom + 2 * (1 + j));
+      __syncthreads();
     }
   }
 }
 
-// moments -> bins, in place: bins[(ca << 1) | cb] = 1/4 sum_{sa, sb} (-1)^(ca sa + cb sb) M[(sa << 1) | sb]
-__global__ void cm_moments_to_bins_kernel(double* mom, int ngates_total) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= ngates_total) return;
-  double* m = mom + 8 * (size_t)j;
+// moments -> bins: out[j][(ca << 1) | cb] = 1/4 sum_{sa, sb} (-1)^(ca sa + cb sb) M[(sa << 1) | sb] with
+// M = {M_0, M_b, M_a, M_ab}; a one-qubit gate (no bit a) has M_a = M_0, M_ab = M_b.  `mom` may BE `out` (the
+// moments of a run fit its output: 1 + #masks <= 4 #gates): one block per batch row reads every gate's moments
+// before any bin is written.
+constexpr int CM_BINS_G = 256;
+struct CmGateIdx {
+  short ia[CM_BINS_G], ib[CM_BINS_G], iab[CM_BINS_G];  // slots in the moments buffer; ia < 0: one-qubit gate
+};
+__global__ void __launch_bounds__(CM_BINS_G)
+cm_moments_to_bins_kernel(const double* mom, long long mom_bstride, CmGateIdx gi, int ngates, double* out,
+                          long long out_bstride) {
+  const int j = threadIdx.x;
+  const double* mb = mom + (size_t)blockIdx.y * mom_bstride;
+  double* o = out + (size_t)blockIdx.y * out_bstride + 8 * (size_t)j;
   double re[4], im[4];
-  for (int s = 0; s < 4; ++s) {
-    re[s] = m[2 * s];
-    im[s] = m[2 * s + 1];
+  if (j < ngates) {
+    const int ia = gi.ia[j], ib = gi.ib[j], iab = gi.iab[j];
+    const int slot[4] = {0, ib, ia < 0 ? 0 : ia, ia < 0 ? ib : iab};
+    for (int s = 0; s < 4; ++s) {
+      re[s] = mb[2 * slot[s]];
+      im[s] = mb[2 * slot[s] + 1];
+    }
   }
+  __syncthreads();
+  if (j >= ngates) return;
   for (int c = 0; c < 4; ++c) {
     double r = 0.0, i = 0.0;
     for (int s = 0; s < 4; ++s) {
@@ -1168,8 +1168,8 @@ __global__ void cm_moments_to_bins_kernel(double* mom, int ngates_total) {
       r += sg * re[s];
       i += sg * im[s];
     }
-    m[2 * c] = r;
-    m[2 * c + 1] = i;
+    o[2 * c] = r;
+    o[2 * c + 1] = i;
   }
 }
 
@@ -1178,44 +1178,82 @@ int launch_cross_marginals(const void* lam, const void* psi, int nbits, int64_t 
   TCB_REQUIRE(nbits >= 1 && nbits <= 40, "tcb_sv_cross_marginals: nbits=%d", nbits);
   TCB_REQUIRE(batch >= 1 && batch <= 65535, "tcb_sv_cross_marginals: batch=%lld", (long long)batch);
   TCB_REQUIRE(ngates >= 0, "tcb_sv_cross_marginals: ngates=%d", ngates);
-  TCB_REQUIRE(batch == 1 || out_bstride == (int64_t)4 * ngates,
-              "tcb_sv_cross_marginals: batched output must be dense (out_batch_stride = 4 * ngates)");
+  TCB_REQUIRE(batch == 1 || out_bstride >= (int64_t)4 * ngates,
+              "tcb_sv_cross_marginals: out_batch_stride must be >= 4 * ngates");
   if (ngates == 0) return 0;
-  // The kernels accumulate moments and convert them to bins IN PLACE, so `out` must start from zero for this
-  // call: a scratch-free contract that the += of the header would break; enforce by clearing here.
-  TCB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 8 * (size_t)ngates * (size_t)batch, stream));
+  // distinct masks of the run, and for every gate the moment slots of {a, b, ab} (slot 0 = M_0)
+  std::vector<unsigned long long> masks;
+  std::vector<int> ia(ngates), ib(ngates), iab(ngates);
+  auto slot_of = [&](unsigned long long m) {
+    for (size_t k = 0; k < masks.size(); ++k)
+      if (masks[k] == m) return (int)k + 1;
+    masks.push_back(m);
+    return (int)masks.size();
+  };
+  for (int j = 0; j < ngates; ++j) {
+    int a = gate_bits[2 * j], b = gate_bits[2 * j + 1];
+    TCB_REQUIRE(a >= 0 && a < nbits && b >= -1 && b < nbits && a != b,
+                "tcb_sv_cross_marginals: gate %d has bits (%d, %d)", j, a, b);
+    if (b < 0) {  // one-qubit gate: its bit plays the LSB of the bin index
+      ia[j] = -1;
+      ib[j] = slot_of(1ull << a);
+      iab[j] = ib[j];
+    } else {
+      ia[j] = slot_of(1ull << a);
+      ib[j] = slot_of(1ull << b);
+      iab[j] = slot_of((1ull << a) | (1ull << b));
+    }
+  }
+  const int nmom = (int)masks.size();
+  TCB_REQUIRE(nmom < 32000, "tcb_sv_cross_marginals: %d distinct masks in one run", nmom);
+  // the moments live in `out` itself (1 + nmom <= 4 ngates slots) when one block can turn them into bins;
+  // longer runs take a stream-ordered scratch buffer
+  const bool in_place = ngates <= CM_BINS_G;
+  long long mom_bstride = 2 * out_bstride;  // doubles per batch element
+  double* mom = out;
+  if (in_place) {
+    if (batch == 1)
+      TCB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 8 * (size_t)ngates, stream));
+    else
+      TCB_CHECK_CUDA(cudaMemset2DAsync(out, sizeof(double) * 2 * (size_t)out_bstride, 0, sizeof(double) * 8 * (size_t)ngates,
+                                       (size_t)batch, stream));
+  } else {
+    mom_bstride = 2 * (long long)(1 + nmom);
+    const size_t mom_bytes = sizeof(double) * (size_t)mom_bstride * (size_t)batch;
+    TCB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&mom), mom_bytes, stream));
+    TCB_CHECK_CUDA(cudaMemsetAsync(mom, 0, mom_bytes, stream));
+  }
   const uint64_t nvec = 1ull << (nbits - 1);
-  for (int first = 0; first < ngates; first += CM_G) {
-    const int cnt = ngates - first < CM_G ? ngates - first : CM_G;
-    CmGates g;
-    for (int j = 0; j < CM_G; ++j) {
-      const int src = first + (j < cnt ? j : 0);  // padding repeats a real gate; its moments are not written
-      int a = gate_bits[2 * src], b = gate_bits[2 * src + 1];
-      TCB_REQUIRE(a >= 0 && a < nbits && b >= -1 && b < nbits && a != b,
-                  "tcb_sv_cross_marginals: gate %d has bits (%d, %d)", src, a, b);
-      if (b < 0) {  // one-qubit gate: its bit plays the LSB, the MSB is a constant 0
-        b = a;
-        a = -1;
-      }
-      g.a[j] = a;
-      g.b[j] = b;
-    }
+  constexpr size_t cm_smem = sizeof(float) * 256 * (CM_M * 2 + 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TCB_CHECK_CUDA(cudaFuncSetAttribute(cross_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cm_smem));
+    attr_set = true;
+  }
+  for (int first = 0; first < nmom; first += CM_M) {
+    const int cnt = nmom - first < CM_M ? nmom - first : CM_M;
+    CmMasks g;
+    for (int j = 0; j < CM_M; ++j) g.m[j] = j < cnt ? masks[first + j] : 0ull;
     dim3 grid(grid_for((nvec + 1) / 2, 256, 2), (unsigned)batch);
-    constexpr size_t cm_smem = sizeof(float) * 256 * (CM_G * 6 + 2);
-    static bool attr_set = false;
-    if (!attr_set) {
-      TCB_CHECK_CUDA(cudaFuncSetAttribute(cross_marginals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)cm_smem));
-      attr_set = true;
-    }
-    cross_marginals_kernel<<<grid, 256, cm_smem, stream>>>(reinterpret_cast<const float4*>(lam),
-                                                     reinterpret_cast<const float4*>(psi), nvec, g, cnt,
-                                                     out + 8 * first, 2 * out_bstride);
+    cross_moments_kernel<<<grid, 256, cm_smem, stream>>>(reinterpret_cast<const float4*>(lam),
+                                                         reinterpret_cast<const float4*>(psi), nvec, g, cnt,
+                                                         first == 0 ? 1 : 0, mom + 2 * first, mom_bstride);
     TCB_CHECK_CUDA(cudaGetLastError());
   }
-  const int total = ngates * (int)batch;
-  cm_moments_to_bins_kernel<<<(total + 127) / 128, 128, 0, stream>>>(out, total);
-  TCB_CHECK_CUDA(cudaGetLastError());
+  for (int first = 0; first < ngates; first += CM_BINS_G) {
+    const int cnt = ngates - first < CM_BINS_G ? ngates - first : CM_BINS_G;
+    CmGateIdx gi;
+    for (int j = 0; j < CM_BINS_G; ++j) {
+      const int src = first + (j < cnt ? j : 0);
+      gi.ia[j] = (short)ia[src];
+      gi.ib[j] = (short)ib[src];
+      gi.iab[j] = (short)iab[src];
+    }
+    dim3 grid(1, (unsigned)batch);
+    cm_moments_to_bins_kernel<<<grid, CM_BINS_G, 0, stream>>>(mom, mom_bstride, gi, cnt, out + 8 * first, 2 * out_bstride);
+    TCB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (!in_place) TCB_CHECK_CUDA(cudaFreeAsync(mom, stream));
   return 0;
 }
 

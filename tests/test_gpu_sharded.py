@@ -42,9 +42,10 @@ def test_pack_bits_kernel(cuda):
             assert np.array_equal(st2.cpu().numpy(), want)
 
 
-def _nccl_worker(rank, world, port, n, seed, out):
+def _nccl_worker(rank, world, port, n, seed, out, p2p):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["TCB_SWAP_P2P"] = str(p2p)
     import torch.distributed as dist
 
     torch.cuda.set_device(rank)
@@ -61,12 +62,16 @@ def _nccl_worker(rank, world, port, n, seed, out):
     zz = sv.z_expectations([[0, n - 1], [2], [1, 3, 4]])
     amp = sv.amplitude([1, 0] * (n // 2))
     torch.save({"state": sv.state.cpu(), "pos_of": sv.pos_of, "zz": zz.cpu(), "amp": amp.cpu(), "swaps": sv.swaps_done,
-                "norm": float(sv.norm2()[0])}, f"{out}.{rank}")  # fmt: skip
+                "norm": float(sv.norm2()[0]), "peer": bool(sv._peer)}, f"{out}.{rank}")  # fmt: skip
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [1, 0])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_nccl_matches_oracle(cuda, tmp_path, world):
+def test_sharded_nccl_matches_oracle(cuda, tmp_path, world, p2p):
+    """p2p = 1: qubit swaps over peer memory (pack kernels store into the receiver's symmetric-memory staging
+    buffer, several chunks per swap so both staging halves and the side-stream unpack are exercised);
+    p2p = 0: the NCCL send/recv path."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -77,11 +82,13 @@ def test_sharded_nccl_matches_oracle(cuda, tmp_path, world):
 
     n, seed = 16, 11
     g = world.bit_length() - 1
-    port = 29600 + (os.getpid() % 2000)
+    port = 29600 + (os.getpid() % 2000) + 7 * p2p
     out = str(tmp_path / "shard")
-    mp.spawn(_nccl_worker, args=(world, port, n, seed, out), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, port, n, seed, out, p2p), nprocs=world, join=True)
     parts = [torch.load(f"{out}.{r}", weights_only=False) for r in range(world)]
     assert parts[0]["swaps"] >= 1
+    if not p2p:
+        assert not any(p["peer"] for p in parts)
     ref = build(tc_oracle, n, random_layers(n, 3, seed)).wavefunction()
     full = gather_logical([p["state"].numpy() for p in parts], parts[0]["pos_of"], n, n - g)
     assert np.abs(full - ref).max() <= 1e-5
