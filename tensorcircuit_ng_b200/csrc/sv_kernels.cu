@@ -1067,13 +1067,17 @@ __device__ __forceinline__ float2 cm_flip(float2 v, unsigned sign_bit) {  // sig
   return make_float2(__uint_as_float(__float_as_uint(v.x) ^ sign_bit), __uint_as_float(__float_as_uint(v.y) ^ sign_bit));
 }
 
-// mom[0] += M_0 (first launch of a series only), mom[1 + first + j] += M_{g.m[j]}.  A sign flip and one complex
-// add per mask per PAIR of amplitudes (the two amplitudes of a 16-byte load share every sign except bit 0's).
+// mom[0] += M_0 (first launch of a series only), mom[1 + j] += M_{g.m[j]}.  A thread takes the 8 amplitudes of the
+// three lowest address bits of both states per iteration (64 contiguous bytes each).  LOW = false: no mask touches
+// those bits, so the sign of a mask is one value for all 8 products — one parity, one sign flip and one complex add
+// per mask per EIGHT amplitudes (the round-1 form paid that per pair and was ALU-bound at 1.9 TB/s).  LOW = true:
+// the 3-bit Walsh-Hadamard transform of the 8 products first, every mask then picks the entry of its low part.
+template <bool LOW>
 __global__ void __launch_bounds__(256, 2)
-cross_moments_kernel(const float4* __restrict__ lam, const float4* __restrict__ psi, uint64_t nvec, CmMasks g,
+cross_moments_kernel(const float4* __restrict__ lam, const float4* __restrict__ psi, uint64_t noct, CmMasks g,
                      int nmasks, int write_m0, double* mom, long long mom_bstride) {
-  lam += (size_t)blockIdx.y * nvec;
-  psi += (size_t)blockIdx.y * nvec;
+  lam += (size_t)blockIdx.y * noct * 4;
+  psi += (size_t)blockIdx.y * noct * 4;
   mom += (size_t)blockIdx.y * mom_bstride;
   // first-level sums in registers, second level per thread in shared memory ([slot][thread], conflict-free)
   extern __shared__ float cm_acc2[];
@@ -1082,32 +1086,59 @@ cross_moments_kernel(const float4* __restrict__ lam, const float4* __restrict__ 
   for (int j = 0; j < CM_M; ++j) acc[j] = make_float2(0.f, 0.f);
   for (int e = 0; e < CM_M * 2 + 2; ++e) cm_acc2[e * 256 + threadIdx.x] = 0.f;
   int cnt = 0;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 2;
-  for (uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; p0 < nvec; p0 += stride) {
-    float4 l[2], s[2];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < noct; p += stride) {
+    float4 l[4], s[4];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {  // four independent 16-byte loads in flight
-      const bool ok = p0 + k < nvec;
-      l[k] = ok ? ldg_stream(lam + p0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s[k] = ok ? ldg_stream(psi + p0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 4; ++k) {  // eight independent 16-byte loads in flight
+      l[k] = ldg_stream(lam + 4 * p + k);
+      s[k] = ldg_stream(psi + 4 * p + k);
     }
+    float2 w[8];  // q_i = lam_i conj(psi_i)
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      // q = lam * conj(psi) for the two amplitudes 2p, 2p + 1; their sum and difference
-      const float2 q0 = make_float2(l[k].x * s[k].x + l[k].y * s[k].y, l[k].y * s[k].x - l[k].x * s[k].y);
-      const float2 q1 = make_float2(l[k].z * s[k].z + l[k].w * s[k].w, l[k].w * s[k].z - l[k].z * s[k].w);
-      const float2 qs = make_float2(q0.x + q1.x, q0.y + q1.y), qd = make_float2(q0.x - q1.x, q0.y - q1.y);
-      m0.x += qs.x;
-      m0.y += qs.y;
-      const uint64_t i0 = (p0 + k) << 1;  // (bit 0 clear)
+    for (int k = 0; k < 4; ++k) {
+      w[2 * k] = make_float2(l[k].x * s[k].x + l[k].y * s[k].y, l[k].y * s[k].x - l[k].x * s[k].y);
+      w[2 * k + 1] = make_float2(l[k].z * s[k].z + l[k].w * s[k].w, l[k].w * s[k].z - l[k].z * s[k].w);
+    }
+    if (LOW) {  // in-place Walsh-Hadamard over the three low bits: w[S] = sum_i (-1)^popc(i & S) q_i
 #pragma unroll
-      for (int j = 0; j < CM_M; ++j) {
-        const unsigned long long m = g.m[j];
-        const unsigned sg = (unsigned)(__popcll(i0 & m) & 1) << 31;
-        const float2 u = cm_flip((m & 1ull) ? qd : qs, sg);
-        acc[j].x += u.x;
-        acc[j].y += u.y;
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (!((i >> b) & 1)) {
+            const float2 x = w[i], y = w[i | (1 << b)];
+            w[i] = make_float2(x.x + y.x, x.y + y.y);
+            w[i | (1 << b)] = make_float2(x.x - y.x, x.y - y.y);
+          }
+    } else {
+#pragma unroll
+      for (int i = 1; i < 8; ++i) {
+        w[0].x += w[i].x;
+        w[0].y += w[i].y;
       }
+    }
+    m0.x += w[0].x;
+    m0.y += w[0].y;
+#pragma unroll
+    for (int j = 0; j < CM_M; ++j) {
+      const unsigned long long m = g.m[j];
+      const unsigned sg = (unsigned)(__popcll(p & (m >> 3)) & 1) << 31;
+      float2 base = w[0];
+      if (LOW) {
+        switch ((int)(m & 7ull)) {  // (uniform: the masks are kernel parameters)
+          case 1: base = w[1]; break;
+          case 2: base = w[2]; break;
+          case 3: base = w[3]; break;
+          case 4: base = w[4]; break;
+          case 5: base = w[5]; break;
+          case 6: base = w[6]; break;
+          case 7: base = w[7]; break;
+          default: break;
+        }
+      }
+      const float2 u = cm_flip(base, sg);
+      acc[j].x += u.x;
+      acc[j].y += u.y;
     }
     if ((++cnt & 15) == 0) {
       cm_acc2[(CM_M * 2) * 256 + threadIdx.x] += m0.x;
@@ -1133,6 +1164,27 @@ cross_moments_kernel(const float4* __restrict__ lam, const float4* __restrict__ 
                         (double)cm_acc2[(j * 2 + 1) * 256 + threadIdx.x] + (double)acc[j].y, mom + 2 * (1 + j));
       __syncthreads();
     }
+  }
+}
+
+// states of fewer than 8 amplitudes: one thread, plain loops (every mask may touch every bit)
+__global__ void cross_moments_tiny_kernel(const float2* __restrict__ lam, const float2* __restrict__ psi, int nbits,
+                                          const CmMasks g, int nmasks, int write_m0, double* mom, long long mom_bstride) {
+  if (threadIdx.x != 0) return;
+  lam += (size_t)blockIdx.y << nbits;
+  psi += (size_t)blockIdx.y << nbits;
+  mom += (size_t)blockIdx.y * mom_bstride;
+  for (int j = -1; j < nmasks; ++j) {
+    if (j < 0 && !write_m0) continue;
+    double re = 0.0, im = 0.0;
+    for (unsigned i = 0; i < (1u << nbits); ++i) {
+      const float2 l = lam[i], s = psi[i];
+      const double sg = (j >= 0 && (__popcll((unsigned long long)i & g.m[j]) & 1)) ? -1.0 : 1.0;
+      re += sg * ((double)l.x * s.x + (double)l.y * s.y);
+      im += sg * ((double)l.y * s.x - (double)l.x * s.y);
+    }
+    mom[2 * (1 + j)] += re;
+    mom[2 * (1 + j) + 1] += im;
   }
 }
 
@@ -1181,19 +1233,33 @@ int launch_cross_marginals(const void* lam, const void* psi, int nbits, int64_t 
   TCB_REQUIRE(batch == 1 || out_bstride >= (int64_t)4 * ngates,
               "tcb_sv_cross_marginals: out_batch_stride must be >= 4 * ngates");
   if (ngates == 0) return 0;
-  // distinct masks of the run, and for every gate the moment slots of {a, b, ab} (slot 0 = M_0)
+  // distinct masks of the run, and for every gate the moment slots of {a, b, ab} (slot 0 = M_0); the masks that
+  // touch the three lowest bits come first (they take the Walsh-Hadamard variant of the kernel)
   std::vector<unsigned long long> masks;
-  std::vector<int> ia(ngates), ib(ngates), iab(ngates);
+  auto add_mask = [&](unsigned long long m) {
+    for (size_t k = 0; k < masks.size(); ++k)
+      if (masks[k] == m) return;
+    masks.push_back(m);
+  };
+  for (int pass = 0; pass < 2; ++pass)  // pass 0: low-touching masks, pass 1: the rest
+    for (int j = 0; j < ngates; ++j) {
+      const int a = gate_bits[2 * j], b = gate_bits[2 * j + 1];
+      TCB_REQUIRE(a >= 0 && a < nbits && b >= -1 && b < nbits && a != b,
+                  "tcb_sv_cross_marginals: gate %d has bits (%d, %d)", j, a, b);
+      unsigned long long cand[3] = {1ull << a, b < 0 ? 0ull : 1ull << b, b < 0 ? 0ull : (1ull << a) | (1ull << b)};
+      for (int c = 0; c < 3; ++c)
+        if (cand[c] != 0ull && (((cand[c] & 7ull) != 0ull) == (pass == 0))) add_mask(cand[c]);
+    }
+  int nlow = 0;
+  while (nlow < (int)masks.size() && (masks[nlow] & 7ull) != 0ull) ++nlow;
   auto slot_of = [&](unsigned long long m) {
     for (size_t k = 0; k < masks.size(); ++k)
       if (masks[k] == m) return (int)k + 1;
-    masks.push_back(m);
-    return (int)masks.size();
+    return 0;
   };
+  std::vector<int> ia(ngates), ib(ngates), iab(ngates);
   for (int j = 0; j < ngates; ++j) {
-    int a = gate_bits[2 * j], b = gate_bits[2 * j + 1];
-    TCB_REQUIRE(a >= 0 && a < nbits && b >= -1 && b < nbits && a != b,
-                "tcb_sv_cross_marginals: gate %d has bits (%d, %d)", j, a, b);
+    const int a = gate_bits[2 * j], b = gate_bits[2 * j + 1];
     if (b < 0) {  // one-qubit gate: its bit plays the LSB of the bin index
       ia[j] = -1;
       ib[j] = slot_of(1ull << a);
@@ -1223,23 +1289,45 @@ int launch_cross_marginals(const void* lam, const void* psi, int nbits, int64_t 
     TCB_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&mom), mom_bytes, stream));
     TCB_CHECK_CUDA(cudaMemsetAsync(mom, 0, mom_bytes, stream));
   }
-  const uint64_t nvec = 1ull << (nbits - 1);
   constexpr size_t cm_smem = sizeof(float) * 256 * (CM_M * 2 + 2);
   static bool attr_set = false;
   if (!attr_set) {
-    TCB_CHECK_CUDA(cudaFuncSetAttribute(cross_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cm_smem));
+    TCB_CHECK_CUDA(cudaFuncSetAttribute(cross_moments_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cm_smem));
+    TCB_CHECK_CUDA(cudaFuncSetAttribute(cross_moments_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cm_smem));
     attr_set = true;
   }
-  for (int first = 0; first < nmom; first += CM_M) {
-    const int cnt = nmom - first < CM_M ? nmom - first : CM_M;
-    CmMasks g;
-    for (int j = 0; j < CM_M; ++j) g.m[j] = j < cnt ? masks[first + j] : 0ull;
-    dim3 grid(grid_for((nvec + 1) / 2, 256, 2), (unsigned)batch);
-    cross_moments_kernel<<<grid, 256, cm_smem, stream>>>(reinterpret_cast<const float4*>(lam),
-                                                         reinterpret_cast<const float4*>(psi), nvec, g, cnt,
-                                                         first == 0 ? 1 : 0, mom + 2 * first, mom_bstride);
-    TCB_CHECK_CUDA(cudaGetLastError());
-  }
+  bool m0_done = false;
+  auto run_range = [&](int lo, int hi, bool low) -> int {
+    for (int first = lo; first < hi; first += CM_M) {
+      const int cnt = hi - first < CM_M ? hi - first : CM_M;
+      CmMasks g;
+      for (int j = 0; j < CM_M; ++j) g.m[j] = j < cnt ? masks[first + j] : 0ull;
+      double* dst = mom + 2 * first;
+      const int wm0 = m0_done ? 0 : 1;
+      if (nbits < 3) {
+        cross_moments_tiny_kernel<<<dim3(1, (unsigned)batch), 32, 0, stream>>>(
+            reinterpret_cast<const float2*>(lam), reinterpret_cast<const float2*>(psi), nbits, g, cnt, wm0,
+            first == 0 ? mom : dst, mom_bstride);
+      } else {
+        const uint64_t noct = 1ull << (nbits - 3);
+        dim3 grid(grid_for(noct, 256, 2), (unsigned)batch);
+        if (low)
+          cross_moments_kernel<true><<<grid, 256, cm_smem, stream>>>(reinterpret_cast<const float4*>(lam),
+                                                                     reinterpret_cast<const float4*>(psi), noct, g, cnt,
+                                                                     wm0, dst, mom_bstride);
+        else
+          cross_moments_kernel<false><<<grid, 256, cm_smem, stream>>>(reinterpret_cast<const float4*>(lam),
+                                                                      reinterpret_cast<const float4*>(psi), noct, g, cnt,
+                                                                      wm0, dst, mom_bstride);
+      }
+      TCB_CHECK_CUDA(cudaGetLastError());
+      m0_done = true;
+    }
+    return 0;
+  };
+  if (int rc = run_range(0, nbits < 3 ? nmom : nlow, true)) return rc;
+  if (nbits >= 3)
+    if (int rc = run_range(nlow, nmom, false)) return rc;
   for (int first = 0; first < ngates; first += CM_BINS_G) {
     const int cnt = ngates - first < CM_BINS_G ? ngates - first : CM_BINS_G;
     CmGateIdx gi;
