@@ -15,7 +15,7 @@ for l in open("gpurun_out/bench_n${N}_r2c.json"):
     if l.startswith("{"):
         d = json.loads(l)
         c = d["config"]
-        print("qaoa", d["value"], d["ms_per_step"], "swap_ms", c.get("swap_ms_per_step"), "nvlink", c.get("nvlink_gbs_per_gpu"), "local", c.get("local_ms_per_step"), "e2e", d["e2e"]["ms_per_step"], "parity", d.get("parity", {}).get("ok"))
+        print("qaoa", d["value"], d["ms_per_step"], "swaps", c.get("swaps"), "passes", c.get("hbm_passes"), "swap_ms", c.get("swap_ms_per_step"), "nvlink", c.get("nvlink_gbs_per_gpu"), "local", c.get("local_ms_per_step"), "e2e", d["e2e"]["ms_per_step"], "parity", (d.get("parity") or {}).get("ok"))
         for k, v in d.get("sub_records", {}).items():
             print(k, {x: v.get(x) for x in ("value", "ms_per_step", "skipped", "error")}, (v.get("config") or {}).get("nvlink_gbs_per_gpu"), (v.get("config") or {}).get("swap_ms_per_step"), (v.get("config") or {}).get("local_ms_per_step"))
 PY
