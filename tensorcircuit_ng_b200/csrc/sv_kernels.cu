@@ -561,26 +561,36 @@ pauli_sum_kernel(const float4* __restrict__ state, uint64_t nblk_per_state,
             }
         }
       }
-      float2 d[A];
+      float2 d[A], du = make_float2(0.f, 0.f);
 #pragma unroll
       for (int jj = 0; jj < A; ++jj) d[jj] = make_float2(0.f, 0.f);
       do {
         const unsigned long long z = sz[t];
         const float2 c = sc[t];
-        unsigned m = slm[t];
-        if (__popcll((ihi ^ (x >> LB)) & (z >> LB)) & 1) m = ~m;
+        const bool odd = __popcll((ihi ^ (x >> LB)) & (z >> LB)) & 1;
+        if ((z & (unsigned long long)(A - 1)) == 0ull) {
+          // (uniform branch) no Z on the thread's own bits: one sign for all its amplitudes — the term costs one
+          // signed add per THREAD (most terms of a lattice Hamiltonian: every X term, every ZZ bond above bit 2)
+          const float sg = odd ? -1.f : 1.f;
+          du.x = fmaf(sg, c.x, du.x);
+          du.y = fmaf(sg, c.y, du.y);
+        } else {
+          unsigned m = slm[t];
+          if (odd) m = ~m;
 #pragma unroll
-        for (int jj = 0; jj < A; ++jj) {
-          const float sg = __uint_as_float(0x3f800000u | ((m << (31 - jj)) & 0x80000000u));
-          d[jj].x = fmaf(sg, c.x, d[jj].x);
-          d[jj].y = fmaf(sg, c.y, d[jj].y);
+          for (int jj = 0; jj < A; ++jj) {
+            const float sg = __uint_as_float(0x3f800000u | ((m << (31 - jj)) & 0x80000000u));
+            d[jj].x = fmaf(sg, c.x, d[jj].x);
+            d[jj].y = fmaf(sg, c.y, d[jj].y);
+          }
         }
         ++t;
       } while (t < nterms && sx[t] == x);
 #pragma unroll
       for (int jj = 0; jj < A; ++jj) {
-        acc[jj].x += d[jj].x * v[jj].x - d[jj].y * v[jj].y;
-        acc[jj].y += d[jj].x * v[jj].y + d[jj].y * v[jj].x;
+        const float2 dt = make_float2(d[jj].x + du.x, d[jj].y + du.y);
+        acc[jj].x += dt.x * v[jj].x - dt.y * v[jj].y;
+        acc[jj].y += dt.x * v[jj].y + dt.y * v[jj].x;
       }
     }
     if (kValue) {
