@@ -107,14 +107,6 @@ int tcb_sv_expect_pauli(const void* state, int nbits, int64_t batch, uint64_t xm
 int tcb_sv_pauli_sum(const void* state, int nbits, int64_t batch, const uint64_t* xmask,
                      const uint64_t* zmask, const void* coef, int nterms, uint64_t index_base,
                      void* out_state, int accumulate, double* out_value, void* stream);
-/* Tile form of tcb_sv_pauli_sum for terms whose flip masks all lie inside {bits 0, 1, 2} + the nsel (<= 8)
- * selected bits (host array, ascending, >= 3; nbits >= 3 + nsel): the partners of an amplitude then sit in
- * the same CTA, so the state is read ONCE per call however many distinct flip masks there are.  Same outputs
- * and term-array conventions as tcb_sv_pauli_sum; the caller groups the terms of a Hamiltonian into such
- * calls (tensorcircuit_ng_b200/quantum.py, `PauliStringSum._plan_tiles`), accumulate != 0 from the second on. */
-int tcb_sv_pauli_sum_tile(const void* state, int nbits, int64_t batch, int nsel, const int* sel_bits_host,
-                          const uint64_t* xmask, const uint64_t* zmask, const void* coef, int nterms,
-                          uint64_t index_base, void* out_state, int accumulate, double* out_value, void* stream);
 /* out[b] (2 x float64) += <a_b | b_b>  */
 int tcb_sv_inner(const void* a, const void* b, int nbits, int64_t batch, double* out, void* stream);
 
@@ -139,15 +131,16 @@ int tcb_sv_adjoint_step(void* lam, void* psi, int nbits, int64_t batch, const in
  * psi, lam the states after the run, dL/dd_j[c] = d_j[c] * out[j][c]):
  *   out[j][c] (complex128 pairs, =) = sum over amplitudes i whose gate-j bits read c of lam[i] conj(psi[i]),
  * c = bit_a(i) for a one-qubit gate (gate_bits = {a, -1}), (bit_a(i) << 1) | bit_b(i) for two qubits; out has
- * 4 slots per gate.
- * batch: states [batch][2^nbits]; out_batch_stride in complex128 elements.                          */
+ * 4 slots per gate.  (The bins are combinations of +-1 moments; the distinct moment masks of the whole run are
+ * accumulated 24 per read of the two states, in `out` itself for runs of up to 256 gates.)
+ * batch: states [batch][2^nbits]; out_batch_stride (>= 4 * ngates) in complex128 elements.          */
 int tcb_sv_cross_marginals(const void* lam, const void* psi, int nbits, int64_t batch, int ngates,
                            const int* gate_bits_host, double* out, int64_t out_batch_stride, void* stream);
 
 /* Cross reduced density matrices of single qubits between two states, up to 10 qubits per read of both:
  *   out[t][r][c] (complex128 pairs, +=) = sum_rest lam[rest, bit_t = r] conj(psi[rest, bit_t = c])
- * for the tile bits t = 0..min(3,nbits)-1 (the lowest address bits, always in the tile) followed by the nsel
- * (<= 7) selected bits (ascending, >= 3).  With lam, psi the states BEFORE a layer of one-qubit gates on
+ * for the bits t = 0..min(3,nbits)-1 (the lowest address bits, always included: a thread holds them in registers)
+ * followed by the nsel (<= 7) selected bits (ascending, >= 3; they map onto lane and warp index bits).  With lam, psi the states BEFORE a layer of one-qubit gates on
  * distinct qubits, dL/dU_q = U_q out[q] for every gate of the layer (same convention as tcb_sv_gate_grad).
  * skip_low != 0: leave the low-bit entries untouched (a later call of a series only adds its selected bits). */
 int tcb_sv_cross_rdm(const void* lam, const void* psi, int nbits, int64_t batch, int nsel, const int* sel_bits_host,

@@ -92,11 +92,6 @@ SYMBOLS = {
         [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_uint64, c_void_p, c_int, c_void_p,
          c_void_p],
     ),  # fmt: skip
-    "tcb_sv_pauli_sum_tile": (
-        c_int,
-        [c_void_p, c_int, c_int64, c_int, POINTER(c_int), c_void_p, c_void_p, c_void_p, c_int, c_uint64, c_void_p,
-         c_int, c_void_p, c_void_p],
-    ),  # fmt: skip
     "tcb_sv_inner": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "tcb_sv_gate_grad": (
         c_int,

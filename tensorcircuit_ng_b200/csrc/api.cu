@@ -40,8 +40,6 @@ int launch_expect_z(const void*, int, int64_t, const uint64_t*, int, uint64_t, d
 int launch_expect_pauli(const void*, int, int64_t, uint64_t, uint64_t, int, uint64_t, double*,
                         cudaStream_t);
 int launch_inner(const void*, const void*, int, int64_t, double*, cudaStream_t);
-int launch_pauli_sum_tile(const void*, int, int64_t, int, const int*, const uint64_t*, const uint64_t*, const void*, int,
-                          uint64_t, void*, int, double*, cudaStream_t);
 int launch_pauli_sum(const void*, int, int64_t, const uint64_t*, const uint64_t*, const void*, int, uint64_t,
                      void*, int, double*, cudaStream_t);
 int launch_gate_grad(const void*, const void*, int, int64_t, const int*, int, void*, int64_t,
@@ -168,20 +166,6 @@ int tcb_sv_pauli_sum(const void* state, int nbits, int64_t batch, const uint64_t
   }
   return launch_pauli_sum(state, nbits, batch, xmask, zmask, coef, nterms, index_base, out_state,
                           accumulate, out_value, S(stream));
-}
-
-int tcb_sv_pauli_sum_tile(const void* state, int nbits, int64_t batch, int nsel, const int* sel_bits_host,
-                          const uint64_t* xmask, const uint64_t* zmask, const void* coef, int nterms,
-                          uint64_t index_base, void* out_state, int accumulate, double* out_value, void* stream) {
-  NOTNULL(state, "tcb_sv_pauli_sum_tile");
-  if (nsel > 0) NOTNULL(sel_bits_host, "tcb_sv_pauli_sum_tile");
-  if (nterms > 0) {
-    NOTNULL(xmask, "tcb_sv_pauli_sum_tile");
-    NOTNULL(zmask, "tcb_sv_pauli_sum_tile");
-    NOTNULL(coef, "tcb_sv_pauli_sum_tile");
-  }
-  return launch_pauli_sum_tile(state, nbits, batch, nsel, sel_bits_host, xmask, zmask, coef, nterms, index_base,
-                               out_state, accumulate, out_value, S(stream));
 }
 
 int tcb_sv_inner(const void* a, const void* b, int nbits, int64_t batch, double* out, void* stream) {

@@ -22,8 +22,6 @@ import torch
 
 from . import _lib
 
-tile_kernel = __import__("os").environ.get("TCB_PAULI_TILE", "1") != "0"  # 0: always the one-read-per-flip-mask kernel
-
 _PAULI_NP = [
     np.eye(2, dtype=np.complex64),
     np.array([[0, 1], [1, 0]], dtype=np.complex64),
@@ -123,77 +121,15 @@ class PauliStringSum:
         return psi.to(torch.complex64).resolve_conj().contiguous().reshape(-1)
 
     # -- raw launches -----------------------------------------------------------------------------
-    def _plan_tiles(self) -> List[Tuple[Optional[List[int]], np.ndarray]]:
-        """Group the terms into launches: (selected bits, term indices) for the tile kernel
-        (`tcb_sv_pauli_sum_tile`: every flip mask of the group inside {bits 0, 1, 2} + <= 8 selected bits, ONE read of
-        the state for the whole group) and, last, (None, indices) for terms no such window holds (general kernel:
-        one read per distinct flip mask).  Greedy over the distinct flip patterns: seed a window with the narrowest one
-        left, widen it by whichever pattern adds the fewest new bits while it holds 8.
-        A TFIM Hamiltonian on n qubits: ceil((n - 3) / 8) groups instead of n + 1 reads."""
-        plan = getattr(self, "_tiles", None)
-        if plan is not None:
-            return plan
-        plan = []
-        remaining = np.arange(self.nterms)
-        if self.n >= 4 and tile_kernel:
-            xh = (self.xmask >> np.uint64(3)).astype(np.uint64)
-            uniq = sorted({int(v) for v in xh.tolist()}, key=lambda v: (bin(v).count("1"), v))  # distinct high flip patterns
-            left = [v for v in uniq if bin(v).count("1") <= 8]
-            while left:
-                window = left[0]  # seed: the narrowest pattern still to place
-                grown = True
-                while grown:  # widen by the pattern that adds the fewest new bits, while the window holds 8
-                    grown = False
-                    best = None
-                    for v in left:
-                        if v & ~window:
-                            extra = bin(v & ~window).count("1")
-                            if bin(window | v).count("1") <= 8 and (best is None or extra < best[0]):
-                                best = (extra, v)
-                    if best is not None:
-                        window |= best[1]
-                        grown = True
-                left = [v for v in left if v & ~window]
-                inside = (xh[remaining] & ~np.uint64(window)) == 0
-                plan.append(([b + 3 for b in range(self.n - 3) if (window >> b) & 1], remaining[inside]))
-                remaining = remaining[~inside]
-        if remaining.size:
-            plan.append((None, remaining))
-        self._tiles = plan
-        return plan
-
-    def _group_tables(self, device: torch.device) -> List[Tuple[bool, Any, int, torch.Tensor, torch.Tensor, torch.Tensor, int]]:
-        key = "groups:" + str(device)
-        t = self._dev.get(key)
-        if t is None:  # uploaded once per device, reused by every step
-            t = []
-            for sel, idx in self._plan_tiles():
-                t.append((sel is not None, _lib.int_array(sel) if sel else None, len(sel or []),
-                          torch.from_numpy(self.xmask[idx].view(np.int64).copy()).to(device),
-                          torch.from_numpy(self.zmask[idx].view(np.int64).copy()).to(device),
-                          torch.from_numpy(self.coef[idx].copy()).to(device), int(len(idx))))  # fmt: skip
-            self._dev[key] = t  # type: ignore[assignment]
-        return t  # type: ignore[return-value]
-
     def _launch(self, psi: torch.Tensor, want_state: bool, want_value: bool) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:  # fmt: skip
         """psi: [2^n] or a batch [B, 2^n] (contiguous); value: float64 [2] or [B, 2]."""
+        xs, zs, cs = self._tables(psi.device)
         nb = 1 if psi.dim() == 1 else int(psi.shape[0])
         out = torch.empty_like(psi) if want_state else None
         val = torch.zeros((2,) if psi.dim() == 1 else (nb, 2), dtype=torch.float64, device=psi.device) if want_value else None
-        op, vp = out.data_ptr() if out is not None else None, val.data_ptr() if val is not None else None
-        groups = self._group_tables(psi.device)
-        if not groups:  # the empty sum
-            xs, zs, cs = self._tables(psi.device)
-            _lib.call("tcb_sv_pauli_sum", psi.data_ptr(), self.n, nb, xs.data_ptr(), zs.data_ptr(), cs.data_ptr(),
-                      0, 0, op, 0, vp, _lib.stream_ptr())  # fmt: skip
-        for gi, (tile, sel, nsel, xs, zs, cs, cnt) in enumerate(groups):
-            acc = 1 if gi > 0 else 0  # (the first launch writes H psi, the others add to it; the value always adds)
-            if not tile:
-                _lib.call("tcb_sv_pauli_sum", psi.data_ptr(), self.n, nb, xs.data_ptr(), zs.data_ptr(), cs.data_ptr(),
-                          cnt, 0, op, acc, vp, _lib.stream_ptr())  # fmt: skip
-            else:
-                _lib.call("tcb_sv_pauli_sum_tile", psi.data_ptr(), self.n, nb, nsel, sel, xs.data_ptr(), zs.data_ptr(),
-                          cs.data_ptr(), cnt, 0, op, acc, vp, _lib.stream_ptr())  # fmt: skip
+        _lib.call("tcb_sv_pauli_sum", psi.data_ptr(), self.n, nb, xs.data_ptr(), zs.data_ptr(), cs.data_ptr(),
+                  self.nterms, 0, out.data_ptr() if out is not None else None, 0,
+                  val.data_ptr() if val is not None else None, _lib.stream_ptr())  # fmt: skip
         return out, val
 
     # -- differentiable entry points --------------------------------------------------------------

@@ -264,69 +264,3 @@ def test_gpu_tfim_energy_matches_per_term_expectation_ps(cuda):
     assert float((g1 - g2).abs().max()) < 5e-5
     want = oq.operator_expectation(ansatz(otc, p.cpu().numpy()), oq.PauliStringSum2Dense(ls, ws))
     assert abs(float(v2) - want) < 2e-5 * n
-
-
-def test_tile_plan_groups_terms_by_flip_window():
-    """Host plan of the tile kernel: a TFIM Hamiltonian needs ceil((n - 3) / 8) reads of the state instead of n + 1;
-    a term whose flips do not fit any 3 + 8 bit window goes to the general kernel; every term exactly once."""
-    from tensorcircuit_ng_b200 import quantum as q
-
-    n = 24
-    ls, w = [], []
-    for i in range(n - 1):
-        s = [0] * n
-        s[i] = s[i + 1] = 3
-        ls.append(s)
-        w.append(-1.0)
-    for i in range(n):
-        s = [0] * n
-        s[i] = 1
-        ls.append(s)
-        w.append(-0.5)
-    wide = [1] * 14 + [0] * (n - 14)  # 14 flipped qubits, 11+ of them above bit 2 whatever the window
-    h = q.PauliStringSum(ls + [wide], w + [0.25])
-    plan = h._plan_tiles()
-    assert [sel is not None for sel, _ in plan] == [True, True, True, False]
-    assert all(len(sel) <= 8 and sel == sorted(sel) and min(sel) >= 3 for sel, _ in plan[:3])
-    assert sorted(np.concatenate([idx for _, idx in plan]).tolist()) == list(range(h.nterms))
-    for sel, idx in plan[:3]:
-        window = 7 | sum(1 << b for b in sel)
-        assert all(int(x) & ~window == 0 for x in h.xmask[idx])
-    assert len(plan[3][1]) == 1
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("n,batch", [(5, 1), (11, 2), (14, 3), (17, 1)])
-def test_gpu_tile_kernel_equals_general_kernel(cuda, n, batch):
-    """`tcb_sv_pauli_sum_tile` (one read per group of terms) against `tcb_sv_pauli_sum` (one read per flip mask)
-    on sums with 1-3 flipped qubits per term plus a few wide terms (fallback group), value and H psi, batched."""
-    import torch
-
-    from tensorcircuit_ng_b200 import quantum as q
-
-    rng = np.random.default_rng(n)
-    ls, w = [], []
-    for _ in range(90):
-        s = [0] * n
-        for k in rng.choice(n, size=int(rng.integers(1, 4)), replace=False):
-            s[int(k)] = int(rng.integers(1, 4))
-        ls.append(s)
-        w.append(float(rng.normal()))
-    for _ in range(3):
-        ls.append([int(v) for v in rng.integers(0, 4, size=n)])
-        w.append(float(rng.normal()))
-    psi = (rng.normal(size=(batch, 2**n)) + 1j * rng.normal(size=(batch, 2**n))).astype(np.complex64)
-    t = torch.from_numpy(psi).cuda()
-    res = {}
-    for tile in (True, False):
-        q.tile_kernel = tile
-        try:
-            h = q.PauliStringSum(ls, w)
-            assert any(sel is not None for sel, _ in h._plan_tiles()) == (tile and n >= 4)
-            out, val = h._launch(t if batch > 1 else t[0], True, True)
-            res[tile] = (out.cpu().numpy(), val.cpu().numpy())
-        finally:
-            q.tile_kernel = True
-    scale = np.abs(res[False][0]).max()
-    assert np.abs(res[True][0] - res[False][0]).max() <= 2e-5 * scale
-    assert np.abs(res[True][1] - res[False][1]).max() <= 2e-5 * np.abs(res[False][1]).max() + 1e-4 * scale
