@@ -1730,15 +1730,33 @@ __global__ void __launch_bounds__(256)
 pack_bits_kernel(V* __restrict__ state, V* __restrict__ buf, uint64_t first, uint64_t count, SelBits sb,
                  uint64_t patmask, int unpack) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-    uint64_t x = first + i;
+  // four independent elements per thread and iteration: when `buf` is a peer GPU's staging buffer (sharded.py) the
+  // stores are NVLink writes, and the wire wants many of them in flight
+  for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < count; i0 += 4 * stride) {
+    uint64_t xs[4];
+    V vals[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint64_t x = first + i0 + u * stride;
 #pragma unroll 1
-    for (int k = 0; k < sb.n; ++k) x = insert_zero(x, sb.pos[k]);
-    x |= patmask;
-    if (unpack)
-      state[x] = buf[i];
-    else
-      buf[i] = state[x];
+      for (int k = 0; k < sb.n; ++k) x = insert_zero(x, sb.pos[k]);
+      xs[u] = x | patmask;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t i = i0 + u * stride;
+      if (i < count) vals[u] = unpack ? buf[i] : state[xs[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t i = i0 + u * stride;
+      if (i < count) {
+        if (unpack)
+          state[xs[u]] = vals[u];
+        else
+          buf[i] = vals[u];
+      }
+    }
   }
 }
 
