@@ -134,6 +134,18 @@ class Circuit:
     def _copy(self, conj: Optional[bool] = False) -> Tuple[List[tn.Node], List[tn.Edge]]:
         return self.copy_nodes(self._nodes, self._front, conj)
 
+    def __del__(self) -> None:
+        # Node <-> Edge reference cycles: without this every dropped circuit (630 nodes, ~3000 edges for the QAOA
+        # workload) waits for the cyclic collector, whose full collections cost ~200 ms in a process with torch
+        # loaded (measured: +26 ms per step on average).  Cutting the node -> edge references lets reference
+        # counting free the network at once.  (`_copy()` hands out copies, so nothing outside depends on these.)
+        try:
+            for nd in self._nodes:
+                nd.edges = []
+            self._front = []
+        except Exception:  # pylint: disable=broad-except  (interpreter shutdown)
+            pass
+
     # basecircuit.py:183-371 ------------------------------------------------------------------
     def apply_general_gate(self, gate: Gate, *index: int, name: Optional[str] = None,
                            split: Optional[Dict[str, Any]] = None, mpo: bool = False,

@@ -545,9 +545,13 @@ def _memo_key(v: Any) -> Any:
 def memoised_gate(gatef: Callable[..., Gate], kws: Dict[str, Any]) -> Gate:
     """gatef(**kws), reusing the tensor of an earlier call with the same parameter elements."""
     parts = []
-    if (getattr(gatef, "_lazy_family", False) and _lazy_ok(kws.get("theta"))
-            and isinstance(kws.get("unitary", _i_matrix), np.ndarray)):  # fmt: skip
-        return gatef(**kws)  # deferred: built with its whole family in one batched expression
+    if getattr(gatef, "_lazy_family", False) and isinstance(kws.get("unitary", _i_matrix), np.ndarray):
+        # deferred gates only LOOK at their parameter (dtype, grad state, one detached copy): no tensor is created,
+        # so an active torch-function mode (`torch.set_default_device`, the reference's usual set-up) has nothing to
+        # contribute here — and costs a Python call per attribute read, as much again as building the node
+        with torch._C.DisableTorchFunction():
+            if _lazy_ok(kws.get("theta")):
+                return gatef(**kws)  # deferred: built with its whole family in one batched expression
     for k in sorted(kws):
         v = kws[k]
         if isinstance(v, torch.Tensor) and (_is_functorch(v) or v.grad_fn is not None

@@ -562,8 +562,11 @@ def assemble_gatebuf(gate_nodes: Sequence[Any], device: torch.device) -> torch.T
     pieces = [build_gatebuf([gate_nodes[i].tensor for i in eager], device)] if eager else []
     order: List[Tuple[int, int]] = [(i, int(gate_nodes[i].tensor.numel())) for i in eager]  # (gate, numel) in cat order
     for fam, idx in fams.values():
-        ths = [gate_nodes[i]._lazy.current_theta() for i in idx]
-        if all(not t.is_cuda and not t.requires_grad and t.grad_fn is None and not autograd_is_batched(t) for t in ths):
+        with torch._C.DisableTorchFunction():  # (attribute reads only: no active torch-function mode has a say)
+            ths = [gate_nodes[i]._lazy.current_theta() for i in idx]
+            host_side = all(not t.is_cuda and not t.requires_grad and t.grad_fn is None and not autograd_is_batched(t)
+                            for t in ths)  # fmt: skip
+        if host_side:
             # host snapshots (gates._LazySpec): one upload for the whole family
             thetas = torch.tensor([float(t) for t in ths], dtype=torch.float32).to(device)
         else:
@@ -593,9 +596,11 @@ def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) 
 
     n, init_node, gates = extract_gate_stream(nodes, output_edge_order)
     probe = [g[0]._lazy.theta if hasattr(g[0], "pending") and g[0].pending() else g[0].tensor for g in gates]
-    device = pick_device(probe + ([init_node.tensor] if init_node is not None else []))
+    with torch._C.DisableTorchFunction():  # (attribute reads on ~600 tensors)
+        device = pick_device(probe + ([init_node.tensor] if init_node is not None else []))
+        batched = any(autograd.is_batched(t) for t in probe)
+        wants = [autograd.wants_grad(t) for t in probe] if torch.is_grad_enabled() else []
     structure = [(g[1], k, int(math.prod(g[0].shape))) for g, k in zip(gates, gate_kinds(gates))]
-    batched = any(autograd.is_batched(t) for t in probe)
     cc = compile_circuit(n, structure, device, absorb_prefix=init_node is None and not batched)
     if torch.is_grad_enabled():
         for g in gates:
@@ -607,16 +612,12 @@ def run_circuit_network(nodes: Sequence[Any], output_edge_order: Sequence[Any]) 
     init = None
     if init_node is not None:
         init = init_node.tensor.to(torch.complex64).to(device).reshape(-1)
-    if torch.is_grad_enabled() and (any(autograd.wants_grad(t) for t in probe)
-                                    or (init is not None and autograd.wants_grad(init))):  # fmt: skip
+    if torch.is_grad_enabled() and (any(wants) or (init is not None and autograd.wants_grad(init))):
         _require_unitary_for_adjoint(gates)
     gatebuf = assemble_gatebuf([g[0] for g in gates], device)
     const_mask = None
     if torch.is_grad_enabled() and len(gates) == len(cc.ops):
         # which gates are constants (no gradient wanted): the backward walk un-applies runs of them in fused passes
-        const_mask = tuple(
-            not autograd.wants_grad(g[0]._lazy.theta if hasattr(g[0], "pending") and g[0].pending() else g[0].tensor)
-            for g in gates
-        )
+        const_mask = tuple(not w for w in wants)
     state = autograd.evolve(cc, gatebuf, init, const_mask)
     return state.reshape([2] * n)
