@@ -185,6 +185,17 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
   __syncthreads();
   const int32_t* hdr = sprog;
   for (int h = tid; h < (1 << (T - L)); h += NT) hi_flat[h] = (uint32_t)(tile_to_flat(h << L, hdr) >> L);
+  // tile number -> CTA-constant flat bits through 6-bit lookup tables (the bit-deposit loop over the 18+ non-tile
+  // bits ran once per tile in every thread)
+  __shared__ unsigned long long tb_lut[7][64];
+  const int tb_chunks = (hdr[H_NNONTILE] + 5) / 6;
+  for (int e = tid; e < tb_chunks * 64; e += NT) {
+    const int c = e >> 6, v = e & 63;
+    unsigned long long g = 0;
+    for (int i = 0; i < 6; ++i)
+      if (c * 6 + i < hdr[H_NNONTILE]) g |= (unsigned long long)((v >> i) & 1) << hdr[H_NONTILEPOS + c * 6 + i];
+    tb_lut[c][v] = g;
+  }
   const int npool = hdr[H_NPOOL];
   const int nfill = hdr[H_NFILL];
   const int nstatic = hdr[H_NFILL_STATIC];
@@ -223,7 +234,11 @@ __global__ void __launch_bounds__(1 << LT, MINB) pass_kernel(const PassArgs A) {
   long long cur_batch = -1;
   for (unsigned long long tg = blockIdx.x; tg < A.total_tiles; tg += gridDim.x) {
     const long long b = (long long)(tg >> A.log_tiles_per_state);
-    const uint64_t base = tile_base(tg & tps_mask, hdr);
+    uint64_t base = 0;  // = tile_base(tg & tps_mask, hdr)
+    {
+      const unsigned long long tnum = tg & tps_mask;
+      for (int c = 0; c < tb_chunks; ++c) base |= tb_lut[c][(tnum >> (6 * c)) & 63ull];
+    }
     const uint64_t cta_bits = base | A.index_base;
     const float2* gates = A.gatebuf + (size_t)b * A.gate_bstride;
     PROF_DECL
