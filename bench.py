@@ -341,8 +341,9 @@ def run_b200(args: argparse.Namespace) -> None:
     stream = torch.cuda.current_stream()
 
     def step_resident() -> "torch.Tensor":
-        cc.start(state, gatebuf)  # |0..0> with every qubit's leading 1q gates folded in (one write pass)
-        cc.run(state, gatebuf)
+        # |0..0> with every qubit's leading 1q gates folded in is a product state: the first pass generates it in
+        # shared memory (no write + read of the initial state), then the other passes run in place
+        cc.start_and_run(state, gatebuf)
         return expect.z_expectations(state, n, [[a, b] for a, b in edges])
 
     def barrier() -> None:

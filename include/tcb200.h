@@ -86,6 +86,15 @@ int tcb_sv_run_pass_oop(const void* src, void* dst, int nbits, int64_t batch,
                         int low_bits, int pool_elems, const void* gatebuf, int64_t gate_batch_stride,
                         uint64_t index_base, void* stream);
 
+/* The FIRST pass of a circuit that starts from the product state  prod_p vecs[p][x_p]  (vecs: [total_bits][2]
+ * complex64 by flat bit position, as tcb_sv_init_product takes it; |0...0> is the product of (1, 0)): every tile is
+ * generated in shared memory instead of loaded, so the initial state is never written to or read from HBM —
+ * tcb_sv_init_product + tcb_sv_run_pass in one launch that only WRITES `dst`.  total_bits > nbits: the rank bits of
+ * a sharded state, read from index_base.  Only tile_bits == 12, batch 1 (callers fall back to init + pass).      */
+int tcb_sv_run_pass_generate(void* dst, int nbits, const int32_t* program, int32_t program_words, int tile_bits,
+                             int low_bits, int pool_elems, const void* gatebuf, uint64_t index_base, const void* vecs,
+                             int total_bits, void* stream);
+
 /* ---- statevector: reductions (K3/K4 without materialising the bra) --------
  * out[b][t] (float64) += sum_x sign_t(x) |psi_b[x]|^2, sign = (-1)^popc((x|index_base) & zmask[t]).
  * One read of the state serves all nterms Z-strings.                          */

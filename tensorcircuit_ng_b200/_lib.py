@@ -74,6 +74,10 @@ SYMBOLS = {
         [c_void_p, c_int, c_int64, c_void_p, c_int32, c_int, c_int, c_int, c_void_p, c_int64, c_uint64,
          c_void_p],
     ),
+    "tcb_sv_run_pass_generate": (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_int32, c_int, c_int, c_int, c_void_p, c_uint64, c_void_p, c_int, c_void_p],
+    ),
     "tcb_sv_run_pass_oop": (
         c_int,
         [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int32, c_int, c_int, c_int, c_void_p, c_int64,

@@ -34,7 +34,8 @@ def _forward(cc: "svengine.CompiledCircuit", gatebuf: torch.Tensor, init: Option
     if init is None:
         state = torch.empty(1 << nbits, dtype=torch.complex64, device=gatebuf.device)
         _lib.require_cuda(state, "state")
-        cc.start(state, gatebuf)
+        cc.start_and_run(state, gatebuf)
+        return state
     else:
         if cc.prefix_levels:
             raise _lib.EngineError("a circuit compiled with absorbed leading gates cannot start from `inputs`")

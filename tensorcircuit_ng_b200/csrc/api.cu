@@ -34,6 +34,8 @@ int launch_init_product(void*, int, const void*, int, uint64_t, cudaStream_t);
 int launch_dense(void*, int, int64_t, const int*, int, const void*, int64_t, cudaStream_t);
 int launch_diag(void*, int, int64_t, const int*, int, const void*, int64_t, int64_t, uint64_t,
                 cudaStream_t);
+int launch_pass_generate(void*, int, const int32_t*, int32_t, int, int, int, const void*, uint64_t, const void*, int,
+                         cudaStream_t);
 int launch_pass(const void*, void*, int, int64_t, const int32_t*, int32_t, int, int, int, const void*,
                 int64_t, uint64_t, cudaStream_t);
 int launch_expect_z(const void*, int, int64_t, const uint64_t*, int, uint64_t, double*, cudaStream_t);
@@ -138,6 +140,17 @@ int tcb_sv_run_pass_oop(const void* src, void* dst, int nbits, int64_t batch, co
   NOTNULL(gatebuf, "tcb_sv_run_pass_oop");
   return launch_pass(src, dst, nbits, batch, program, program_words, tile_bits, low_bits, pool_elems,
                      gatebuf, gate_batch_stride, index_base, S(stream));
+}
+
+int tcb_sv_run_pass_generate(void* dst, int nbits, const int32_t* program, int32_t program_words, int tile_bits,
+                             int low_bits, int pool_elems, const void* gatebuf, uint64_t index_base, const void* vecs,
+                             int total_bits, void* stream) {
+  NOTNULL(dst, "tcb_sv_run_pass_generate");
+  NOTNULL(program, "tcb_sv_run_pass_generate");
+  NOTNULL(gatebuf, "tcb_sv_run_pass_generate");
+  NOTNULL(vecs, "tcb_sv_run_pass_generate");
+  return launch_pass_generate(dst, nbits, program, program_words, tile_bits, low_bits, pool_elems, gatebuf, index_base,
+                              vecs, total_bits, S(stream));
 }
 
 int tcb_sv_expect_z(const void* state, int nbits, int64_t batch, const uint64_t* zmasks, int nterms,

@@ -407,6 +407,17 @@ class CompiledCircuit:
                                                      grad.data_ptr(), _lib.stream_ptr()))  # fmt: skip
         _lib.launch_count += sum(1 if g.k <= 2 else 2 for g in self.ops[first:last])
 
+    def _product_vectors(self, gatebuf: torch.Tensor) -> torch.Tensor:
+        """[nq, 2] complex64 by flat bit position: what the absorbed leading 1q gates make of |0> on every qubit."""
+        v = torch.zeros(self.nq, 2, dtype=torch.complex64, device=self.device)
+        v[:, 0] = 1.0
+        if self.prefix_levels:
+            gb = torch.cat([gatebuf.detach(), torch.zeros(1, dtype=gatebuf.dtype, device=gatebuf.device)])
+            for pos, idx in self.prefix_levels:
+                m = gb[idx].reshape(-1, 2, 2)
+                v[pos] = torch.bmm(m, v[pos].unsqueeze(-1)).squeeze(-1)
+        return v
+
     def start(self, state: torch.Tensor, gatebuf: torch.Tensor) -> None:
         """Write the initial state of the compiled part: |0...0>, or the product state that the
         absorbed leading 1q gates make of it (one write pass, no read)."""
@@ -414,13 +425,26 @@ class CompiledCircuit:
         if not self.prefix_levels:
             _lib.call("tcb_sv_init_zero", state.data_ptr(), nbits, 1, _lib.stream_ptr())
             return
-        gb = torch.cat([gatebuf.detach(), torch.zeros(1, dtype=gatebuf.dtype, device=gatebuf.device)])
-        v = torch.zeros(self.nq, 2, dtype=torch.complex64, device=self.device)
-        v[:, 0] = 1.0
-        for pos, idx in self.prefix_levels:
-            m = gb[idx].reshape(-1, 2, 2)
-            v[pos] = torch.bmm(m, v[pos].unsqueeze(-1)).squeeze(-1)
+        v = self._product_vectors(gatebuf)
         _lib.call("tcb_sv_init_product", state.data_ptr(), nbits, v.data_ptr(), self.nq, 0, _lib.stream_ptr())
+
+    def start_and_run(self, state: torch.Tensor, gatebuf: torch.Tensor) -> None:
+        """`start` + `run` for one state.  When the plan opens with a fused pass of the default tile size, that pass
+        GENERATES its tiles from the product vectors (`tcb_sv_run_pass_generate`): the initial state is never written
+        to or read from HBM (one write pass and half a pass of traffic less per evolution)."""
+        steps = self.plan.steps
+        if not (fuse_start and steps and isinstance(steps[0], PassStep) and steps[0].tile_bits == 12):
+            self.start(state, gatebuf)
+            self.run(state, gatebuf)
+            return
+        _lib.require_cuda(state, "state")
+        _lib.require_cuda(gatebuf, "gate buffer")
+        v = self._product_vectors(gatebuf)
+        st0 = steps[0]
+        _lib.call("tcb_sv_run_pass_generate", state.data_ptr(), self.plan.nbits, self.programs.data_ptr(),
+                  len(st0.program), st0.tile_bits, st0.low_bits, st0.pool_elems, gatebuf.data_ptr(), 0, v.data_ptr(),
+                  self.nq, _lib.stream_ptr())  # fmt: skip
+        self.run_steps(state, gatebuf, first=1)
 
     def run(self, state: torch.Tensor, gatebuf: torch.Tensor, batch: int = 1, gate_batch_stride: int = 0,
             index_base: int = 0) -> None:  # fmt: skip
@@ -435,18 +459,24 @@ class CompiledCircuit:
             _lib.launch_count += self._n_launch
             return
         # step by step through the kernel-level entry points (TCB_NATIVE_PLANS=0; same launches)
+        self.run_steps(state, gatebuf, batch, gate_batch_stride, index_base)
+
+    def run_steps(self, state: torch.Tensor, gatebuf: torch.Tensor, batch: int = 1, gate_batch_stride: int = 0,
+                  index_base: int = 0, first: int = 0) -> None:  # fmt: skip
+        """Steps [first:] of the plan, one C-ABI call per step, in place."""
         nbits = self.plan.nbits
         stream = _lib.stream_ptr()
         sp = state.data_ptr()
         gp = gatebuf.data_ptr()
         pi = 0
-        for step in self.plan.steps:
+        for si, step in enumerate(self.plan.steps):
             if isinstance(step, PassStep):
                 prog_ptr = self.programs.data_ptr() + 4 * self.offsets[pi]
                 pi += 1
-                _lib.call("tcb_sv_run_pass", sp, nbits, batch, prog_ptr, len(step.program), step.tile_bits,
-                          step.low_bits, step.pool_elems, gp, gate_batch_stride, index_base, stream)  # fmt: skip
-            else:
+                if si >= first:
+                    _lib.call("tcb_sv_run_pass", sp, nbits, batch, prog_ptr, len(step.program), step.tile_bits,
+                              step.low_bits, step.pool_elems, gp, gate_batch_stride, index_base, stream)  # fmt: skip
+            elif si >= first:
                 g = step.gate
                 bp = _lib.int_array(step.bitpos)
                 mp = gp + 8 * g.mat_off
@@ -462,6 +492,7 @@ _plan_cache: Dict[Any, CompiledCircuit] = {}
 import os as _os
 
 use_native_plans = _os.environ.get("TCB_NATIVE_PLANS", "1") != "0"
+fuse_start = _os.environ.get("TCB_FUSE_START", "1") != "0"  # 0: always init kernel + passes (CompiledCircuit.start_and_run)
 
 auto_low_bits = "TCB_LOW_BITS" not in _os.environ  # unset: the planner may pick L = 2 when it saves a pass
 plan_options: Dict[str, Any] = {

@@ -38,7 +38,7 @@ state = svengine.new_zero_state(n, 1, torch.device("cuda:0"))
 for it in range(3):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); cc.start(state, gatebuf); cc.run(state, gatebuf); e1.record(); torch.cuda.synchronize()
+    e0.record(); cc.start_and_run(state, gatebuf); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     byt = plan.n_passes * 16 * 2**n
     print(f"iter {it}: {ms:.2f} ms  {len(gates)/ms*1e3:.0f} gates/s  pass-GB/s {byt/ms/1e6:.0f}  per-pass {ms/plan.n_passes:.3f} ms")
