@@ -1094,7 +1094,7 @@ def random_record(args: argparse.Namespace, tc: Any, sharded: Any, comm: Any, ex
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
-        sv.reset(vecs)
+        sv.reset(vecs, lazy=True)  # (the first pass of the first segment generates the shard)
         sv.run(plan, ops, gatebuf)
         zz = sv.z_expectations(terms)
     e1.record(stream)
@@ -1219,7 +1219,7 @@ def run_sharded(args: argparse.Namespace) -> None:
     vecs = sharded.product_vectors(sv.prefix, gatebuf, n) if any(sv.prefix) else None
 
     def step_resident() -> Any:
-        sv.reset(vecs)
+        sv.reset(vecs, lazy=True)  # (the first pass of the first segment generates the shard)
         sv.run(plan, ops, gatebuf)
         return sv.z_expectations(terms)
 

@@ -201,8 +201,9 @@ class CudaExecutor:
 
         _lib.call("tcb_sv_init_product", state.data_ptr(), nl, vecs.data_ptr(), nq, index_base, _lib.stream_ptr())
 
-    def run_gates(self, state: Any, ops: Sequence[GateOp], gatebuf: Any, nq: int, nl: int, pos_of: Sequence[int],
-                  index_base: int, cache: Dict[Any, Any], key: Any) -> None:  # fmt: skip
+    def compiled(self, ops: Sequence[GateOp], nq: int, nl: int, pos_of: Sequence[int], cache: Dict[Any, Any],
+                 key: Any) -> Any:  # fmt: skip
+        """The segment's fused-pass plan with its device programs (`svengine.CompiledCircuit`), cached."""
         from . import svengine
 
         cc = cache.get(key)
@@ -219,7 +220,32 @@ class CudaExecutor:
                         plan = alt
             cc = svengine.CompiledCircuit(plan, list(ops), self.device)
             cache[key] = cc
-        cc.run(state, gatebuf, index_base=index_base)
+        return cc
+
+    def run_gates(self, state: Any, ops: Sequence[GateOp], gatebuf: Any, nq: int, nl: int, pos_of: Sequence[int],
+                  index_base: int, cache: Dict[Any, Any], key: Any) -> None:  # fmt: skip
+        self.compiled(ops, nq, nl, pos_of, cache, key).run(state, gatebuf, index_base=index_base)
+
+    def run_gates_generate(self, state: Any, ops: Sequence[GateOp], gatebuf: Any, nq: int, nl: int,
+                           pos_of: Sequence[int], index_base: int, cache: Dict[Any, Any], key: Any, vecs: Any) -> bool:  # fmt: skip
+        """The first segment of an evolution that starts from the product state `vecs` ([nq, 2] by flat bit
+        position; None = |0...0>): its first pass generates the shard in shared memory (no init pass, no read).
+        False when the segment does not open with a fused pass of the default tile size (caller initialises)."""
+        from . import _lib, svengine
+
+        cc = self.compiled(ops, nq, nl, pos_of, cache, key)
+        steps = cc.plan.steps
+        if not (svengine.fuse_start and steps and isinstance(steps[0], passplan.PassStep) and steps[0].tile_bits == 12):
+            return False
+        if vecs is None:
+            vecs = self.torch.zeros(nq, 2, dtype=self.torch.complex64, device=self.device)
+            vecs[:, 0] = 1.0
+        st0 = steps[0]
+        _lib.call("tcb_sv_run_pass_generate", state.data_ptr(), nl, cc.programs.data_ptr(), len(st0.program),
+                  st0.tile_bits, st0.low_bits, st0.pool_elems, gatebuf.data_ptr(), index_base, vecs.data_ptr(), nq,
+                  _lib.stream_ptr())  # fmt: skip
+        cc.run_steps(state, gatebuf, index_base=index_base, first=1)
+        return True
 
     def pack(self, state: Any, buf: Any, nl: int, sel: Sequence[int], pattern: int, first: int, count: int,
              unpack: bool) -> None:  # fmt: skip
@@ -343,20 +369,36 @@ class ShardedStatevector:
         self._bufs: Optional[Tuple[Any, Any]] = None
         self._peer: Any = None  # peer-memory staging (buffer, addresses per rank, barrier); False = unavailable
         self._side: Any = None  # side stream of the peer-memory exchange (unpacking)
+        self._pending: Any = None  # (product vectors,) of an initial state that has not been written yet (reset lazy)
         self._cache: Dict[Any, Any] = {}
         self.bytes_sent = 0
         self.swaps_done = 0
 
-    def reset(self, vecs: Any = None) -> None:
+    def reset(self, vecs: Any = None, lazy: bool = False) -> None:
         """Back to |0...0> in the canonical layout (the shard buffer is reused), or to the product state
-        prod_p vecs[p][x_p] (vecs: [n, 2] complex64 indexed by flat bit position; one write pass)."""
+        prod_p vecs[p][x_p] (vecs: [n, 2] complex64 indexed by flat bit position; one write pass).
+        `lazy`: do not write the shard now — the first segment of the next `run` generates it inside its first
+        pass when it can (`CudaExecutor.run_gates_generate`); anything else that needs the shard writes it first."""
         self.pos_of = [self.n - 1 - q for q in range(self.n)]
+        self._pending = None
+        if lazy and hasattr(self.ex, "run_gates_generate"):
+            self._pending = (vecs,)
+            return
+        self._write_initial(vecs)
+
+    def _write_initial(self, vecs: Any) -> None:
         if vecs is not None:
             self.ex.init_product(self.state, self.nl, vecs, self.n, self.index_base)
             return
         self.state.zero_()
         if self.rank == 0:
             self.ex.set_one(self.state)
+
+    def _materialize(self) -> None:
+        if getattr(self, "_pending", None) is not None:
+            (vecs,) = self._pending
+            self._pending = None
+            self._write_initial(vecs)
 
     # -- evolution ---------------------------------------------------------------------------
     def run(self, plan: ShardedPlan, gates: Sequence[GateOp], gatebuf: Any) -> None:
@@ -365,9 +407,17 @@ class ShardedStatevector:
             if isinstance(seg, RunSegment):
                 assert seg.pos_of == self.pos_of, "segment compiled for a different qubit layout"
                 ops = [gates[gi] for gi in seg.gate_ids]
+                if getattr(self, "_pending", None) is not None:
+                    (vecs,) = self._pending
+                    if self.ex.run_gates_generate(self.state, ops, gatebuf, self.n, self.nl, seg.pos_of,
+                                                  self.index_base, plan.cache, (self.rank, si), vecs):  # fmt: skip
+                        self._pending = None
+                        continue
+                    self._materialize()
                 self.ex.run_gates(self.state, ops, gatebuf, self.n, self.nl, seg.pos_of, self.index_base,
                                   plan.cache, (self.rank, si))  # fmt: skip
             else:
+                self._materialize()
                 self.swap(seg.pairs)
                 assert self.pos_of == seg.pos_of_after
 
@@ -520,10 +570,12 @@ class ShardedStatevector:
 
     def z_expectations(self, terms: Sequence[Sequence[int]]) -> Any:
         """<Z_S> for every term (qubit lists), all-reduced over the ranks (float64)."""
+        self._materialize()
         out = self.ex.expect_z(self.state, self.nl, [self._mask(t) for t in terms], self.index_base)
         return self.comm.all_reduce_sum(out)
 
     def norm2(self) -> Any:
+        self._materialize()
         out = self.ex.expect_z(self.state, self.nl, [0], self.index_base)
         return self.comm.all_reduce_sum(out)
 
@@ -533,6 +585,7 @@ class ShardedStatevector:
         for q, b in enumerate(bits):
             phys |= (int(b) & 1) << self.pos_of[q]
         owner, local = phys >> self.nl, phys & ((1 << self.nl) - 1)
+        self._materialize()
         v = self.ex.read(self.state, local if owner == self.rank else 0)
         if owner != self.rank:
             v = v * 0
@@ -610,11 +663,10 @@ def evolve(circuit: Any, comm: Any = None, executor: Any = None, chunk_elems: in
     vecs = product_vectors(prefix, gatebuf, n) if any(prefix) else None
     if reuse is not None and reuse.n == n:
         sv = reuse
-        sv.reset(vecs)
+        sv.reset(vecs, lazy=True)
     else:
         sv = ShardedStatevector(n, comm, executor, chunk_elems=chunk_elems)
-        if vecs is not None:
-            sv.reset(vecs)
+        sv.reset(vecs, lazy=True)
     sv.prefix = prefix  # type: ignore[attr-defined]
     sv.run(plan, ops, gatebuf)
     sv.plan, sv.ops, sv.gatebuf = plan, ops, gatebuf  # type: ignore[attr-defined]
