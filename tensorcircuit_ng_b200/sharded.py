@@ -420,6 +420,7 @@ class ShardedStatevector:
                 self._materialize()
                 self.swap(seg.pairs)
                 assert self.pos_of == seg.pos_of_after
+        self._materialize()  # (a plan without segments: the shard is the initial state itself)
 
     def swap(self, pairs: Sequence[Tuple[int, int]]) -> None:
         """Exchange the qubits at global positions P_i with those at local positions p_i."""
