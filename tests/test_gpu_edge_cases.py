@@ -113,3 +113,36 @@ def test_reference_closed_forms(cuda):
     assert set(counts) <= {"00", "11"} and sum(counts.values()) == 300 and min(counts.get("00", 0), counts.get("11", 0)) > 90
     bits, p = c.measure(0, 1, with_prob=True, status=torch.tensor([0.9, 0.1]))
     assert bits.cpu().tolist() == [1.0, 1.0] and abs(float(p) - 0.5) < 1e-6
+
+
+@pytest.mark.parametrize("n,with_prefix", [(12, True), (14, True), (15, False), (17, True)])
+def test_generated_start_equals_init_kernel_plus_passes(cuda, n, with_prefix):
+    """`tcb_sv_run_pass_generate` (the first pass builds its tiles of the initial product state in shared memory) against
+    the init kernel + in-place passes (same to rounding), and both against the oracle: |0...0> and absorbed leading gates,
+    the smallest state the T = 12 kernel takes and wider ones."""
+    import torch
+
+    import tensorcircuit_ng_b200 as tc
+    from helpers import build, oracle_state
+    from tensorcircuit_ng_b200 import svengine
+
+    rng = np.random.default_rng(n)
+    ops = []
+    if with_prefix:
+        for q in range(n):
+            ops.append(("h", [q], {}) if q % 3 else ("ry", [q], {"theta": float(rng.uniform(0, 6))}))
+    for _ in range(2):
+        for q in range(n - 1):
+            ops.append(("rzz", [q, q + 1], {"theta": float(rng.uniform(0, 6))}))
+        for q in range(n):
+            ops.append(("rx", [q], {"theta": float(rng.uniform(0, 6))}))
+        ops.append(("cnot", [0, n - 1], {}))
+    out = {}
+    for fuse in (True, False):
+        svengine.fuse_start = fuse
+        try:
+            out[fuse] = build(tc, n, ops).wavefunction().cpu().numpy()
+        finally:
+            svengine.fuse_start = True
+    assert np.abs(out[True] - out[False]).max() <= 3e-7  # (the product is associated differently: rounding only)
+    assert np.abs(out[True] - oracle_state(n, ops)).max() <= 1e-5
